@@ -1,0 +1,56 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the oracle's C helpers are test infrastructure; build them if missing (gcc only, ~1 s)
+    lib = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    if not os.path.exists(lib):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=False,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "golden_vectors.npz")
+    data = np.load(path)
+    cases = {}
+    for key in data.files:
+        name, field = key.split("/", 1)
+        cases.setdefault(name, {})[field] = data[key]
+    return cases
+
+
+def load_hamiltonian(tag):
+    d = np.load(os.path.join(ROOT, "tests", "golden", "hamiltonians", tag + ".npz"))
+    n = int(d["n_qubits"][0])
+    symp = np.unpackbits(d["symp"], axis=1)[:, :2 * n].astype(bool)
+    return symp, d["coeff"], d
+
+
+@pytest.fixture(scope="session")
+def hamiltonians():
+    return load_hamiltonian
