@@ -1,0 +1,196 @@
+/* symmer_b200 — C ABI of the B200 (sm_100a) engine for symmer's symplectic Pauli algebra.
+ *
+ * The reference (UCL-CCS/symmer) is pure Python and has no FFI of its own; its de-facto seams for the
+ * hot path are the array kernels of symmer/operators/utils.py and the PauliwordOp methods of
+ * symmer/operators/base.py. Each entry point below replaces one of those; the
+ * reference-side binding (ctypes) a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors in the Python host) unless
+ *     the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on that stream unless stated otherwise;
+ *   - return value: 0 = ok, <0 = error (SYM_E_*); sym_last_error() gives a message; no C++
+ *     exceptions cross the boundary; nothing is allocated inside — scratch memory comes from the
+ *     caller through (`ws`, `ws_bytes`), sized by the matching *_ws_bytes() query;
+ *   - packed operator layout: row-major uint64[M][2*W], W = ceil(n_qubits/64) (W >= 1); words
+ *     [0,W) are the X block, [W,2W) the Z block; qubit q is bit (q % 64) of word (q / 64) of its
+ *     block; padding bits are zero. Coefficients: complex128 as interleaved double[M][2].
+ */
+#ifndef SYMMER_B200_H
+#define SYMMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYM_ABI_VERSION 1
+
+#define SYM_OK 0
+#define SYM_E_INVALID (-1)   /* bad argument */
+#define SYM_E_CUDA (-2)      /* a CUDA runtime call failed */
+#define SYM_E_WORKSPACE (-3) /* ws_bytes smaller than the *_ws_bytes() query */
+#define SYM_E_CAPACITY (-4)  /* output capacity too small (n_out holds the required size) */
+#define SYM_E_UNSUPPORTED (-5)
+
+int sym_abi_version(void);
+const char *sym_last_error(void);
+/* Fails with SYM_E_UNSUPPORTED unless the current device is compute capability 10.x. */
+int sym_check_device(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+
+/* ---- a1 layout: PauliwordOp.__init__ (base.py:42-74) holds bool[M,2n]; the engine holds packed rows */
+int sym_pack(const uint8_t *symp, int64_t M, int32_t n_qubits, uint64_t *xz, void *stream);
+int sym_unpack(const uint64_t *xz, int64_t M, int32_t n_qubits, uint8_t *symp, void *stream);
+/* a3 Y_count (base.py:604-615): y[i] = popcount(X_i & Z_i) */
+int sym_ycount(const uint64_t *xz, int64_t M, int32_t W, int32_t *y, void *stream);
+/* GF(2)-linear 64-bit sketch of each row: L(r1 ^ r2) == L(r1) ^ L(r2). Dedup key of a row is
+ * a bijective 64-bit finaliser of L(row), so equal sketches <=> equal keys. */
+int sym_sketch_rows(const uint64_t *xz, int64_t M, int32_t W, uint64_t *sketch, void *stream);
+
+/* ---- a4 multiply: PauliwordOp._multiply_by_operator (base.py:764-794)
+ * Materialised cross terms in the reference's flattened order t = q*M + p (p indexes A, q indexes B):
+ *   out_xz[t] = A[p] ^ B[q];  out_c[t] = A.c[p]*B.c[q]*(-1)^{|A.x[p]&B.z[q]|}*i^{(3(Y_p+Y_q)+Y_out) mod 4}
+ * out_xz: uint64[M*N][2W], out_c: double[M*N][2]. For parity checks and small products. */
+int sym_cross_mul(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz,
+                  const double *b_c, int64_t N, int32_t W, uint64_t *out_xz, double *out_c, void *stream);
+
+/* Fused product + cleanup (base.py:764-794 followed by utils.py:230-279) that never materialises
+ * the M*N cross terms: dedup runs on 64-bit keys derived from the row sketches, rows are only
+ * written for the survivors. zero_threshold < 0 disables the |c| > threshold filter (the
+ * reference's `None`). Output rows are unique; their order is unspecified (reference order is
+ * first-occurrence; parity is defined on canonically sorted term sets).
+ * n_out: device int64[1], receives the number of surviving terms. out_capacity: rows available in
+ * out_xz/out_c; on overflow returns SYM_E_CAPACITY after a stream synchronise.
+ * This call synchronises the stream once (it needs the survivor count to size the emit launch). */
+size_t sym_mul_cleanup_ws_bytes(int64_t M, int64_t N, int32_t W);
+/* Two-phase form so the caller can allocate exact-size outputs: _count runs everything up to the
+ * survivor count U (one stream synchronise, plan left in ws); _emit writes the U rows (async) and
+ * must be given the same operands and the untouched ws. */
+int sym_mul_cleanup_count(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz,
+                          const double *b_c, int64_t N, int32_t W, double zero_threshold,
+                          int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
+int sym_mul_cleanup_emit(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz,
+                         const double *b_c, int64_t N, int32_t W, int64_t U, uint64_t *out_xz,
+                         double *out_c, void *ws, size_t ws_bytes, void *stream);
+int sym_mul_cleanup(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz,
+                    const double *b_c, int64_t N, int32_t W, double zero_threshold, uint64_t *out_xz,
+                    double *out_c, int64_t out_capacity, int64_t *n_out, int64_t *n_out_host,
+                    void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a5 cleanup: symplectic_cleanup (utils.py:230-279) / PauliwordOp.cleanup (base.py:617-638)
+ * Unique rows with duplicates' coefficients summed in input order, then |c| > zero_threshold.
+ * Output order: first occurrence (same as the reference). */
+size_t sym_cleanup_ws_bytes(int64_t T, int32_t W);
+int sym_cleanup_count(const uint64_t *xz, const double *c, int64_t T, int32_t W, double zero_threshold,
+                      int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
+int sym_cleanup_emit(const uint64_t *xz, const double *c, int64_t T, int32_t W, int64_t U,
+                     uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, void *stream);
+int sym_cleanup(const uint64_t *xz, const double *c, int64_t T, int32_t W, double zero_threshold,
+                uint64_t *out_xz, double *out_c, int64_t out_capacity, int64_t *n_out,
+                int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a7 commute: PauliwordOp.commutes_termwise (base.py:938-971) -> matmul_GF2 (utils.py:9-78)
+ * out[i*N + j] = 1 if A[i] commutes with B[j] else 0 (uint8, the reference's bool[M,N]). */
+int sym_commute(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
+                uint8_t *out, void *stream);
+/* Same symplectic inner product, bit-packed output: out_bits[i][j/32] bit j%32 (row stride
+ * ceil(N/32) uint32). Used when the matrix is consumed on the device (masks, graph colouring). */
+int sym_commute_bits(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
+                     uint32_t *out_bits, void *stream);
+
+/* ---- a8 rotations: PauliwordOp._rotate_by_single_Pword (base.py:1090-1161)
+ * One rotation R P R^dagger, R = exp(i*angle/2*Q), Q = q_xz (a single packed row, coefficient 1).
+ * mode 0: general angle: writes M + M_ac rows (row i keeps slot i with cos*c for anticommuting P;
+ *         the new terms -i*sin*P*Q are appended from slot M in row order) WITHOUT dedup; follow
+ *         with sym_cleanup (the one dedup the algebra needs; the reference runs four).
+ *         out_xz/out_c capacity must be 2*M rows.
+ * mode 1: Clifford, odd multiple of pi/2: anticommuting rows become (-i)*P*Q*sign; M rows out.
+ * mode 2: Clifford, even multiple: anticommuting rows * sign; M rows out.
+ * `sign` is +1 or -1 (the reference's `int_part in [2,3]` rule, base.py:1148-1149).
+ * n_out: device int64[1]. Fully asynchronous. */
+size_t sym_rotate_ws_bytes(int64_t M);
+int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_t W, const uint64_t *q_xz,
+               double cos_a, double sin_a, int32_t mode, double sign, uint64_t *out_xz, double *out_c,
+               int64_t *n_out, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a9/a10 matrix-free operator application: to_sparse_matrix (base.py:1458-1510) semantics,
+ * qubit 0 = most significant bit of the basis index.
+ * sym_term_masks: per term, basis-index masks x, z (int64, n_qubits <= 62) and the coefficient with
+ * (-i)^Y folded in. The apply/expval/CSR kernels take the terms SORTED BY x MASK (the host sorts
+ * with sym_sort_pairs) so that terms sharing a column offset share one gather of psi. */
+int sym_term_masks(const uint64_t *xz, const double *c, int64_t M, int32_t n_qubits, int64_t *x_masks,
+                   int64_t *z_masks, double *c_phased, void *stream);
+/*   y[r - row_begin] = sum_t c'_t (-1)^{popcount(r & z_t)} psi[r ^ x_t]   for r in [row_begin, row_end)
+ * psi: complex128[2^n]; y: complex128[row_end-row_begin]; n_qubits <= 40. */
+int sym_apply(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
+              int32_t n_qubits, const double *psi, double *y, int64_t row_begin, int64_t row_end,
+              void *stream);
+/* partial[0..1] += sum_{r in [row_begin,row_end)} conj(psi[r]) * (H psi)[r]  (device double[2],
+ * zero it first). The 2^n basis shards over ranks by row range; all-reduce the two doubles. */
+int sym_expval(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
+               int32_t n_qubits, const double *psi, double *partial, int64_t row_begin, int64_t row_end,
+               void *stream);
+/* CSR emitter for small n (parity with to_sparse_matrix): G distinct x masks (x_groups, ascending),
+ * terms sorted by x with group g spanning [group_start[g], group_start[g+1]). Every row gets exactly
+ * G entries sorted by column (explicit zeros kept). data: double[2^n*G][2], indices: int64[2^n*G],
+ * indptr: int64[2^n+1]. */
+int sym_to_csr(const int64_t *z_masks, const double *c_phased, int64_t M, int32_t n_qubits,
+               const int64_t *x_groups, int64_t G, const int32_t *group_start, double *data,
+               int64_t *indices, int64_t *indptr, void *stream);
+
+/* ---- a11 GF(2): _rref_binary (utils.py:292-315), row-driven pivot rule, no row swaps.
+ * bits: uint64[R][Cw] bit-packed rows (column j = bit j%64 of word j/64), reduced in place.
+ * pivots: device int32[R], pivot column of each row after reduction or -1 for a zero row. */
+size_t sym_rref_ws_bytes(int64_t R);
+int sym_rref(uint64_t *bits, int64_t R, int64_t C, int64_t Cw, int32_t *pivots, void *ws,
+             size_t ws_bytes, void *stream);
+/* bool[R][C] <-> packed uint64[R][Cw] helpers for the GF(2) matrices (any C). */
+int sym_pack_matrix(const uint8_t *m, int64_t R, int64_t C, uint64_t *bits, int64_t Cw, void *stream);
+int sym_unpack_matrix(const uint64_t *bits, int64_t R, int64_t C, int64_t Cw, uint8_t *m, void *stream);
+
+/* ---- multi-GPU building blocks: the product path split at its exchange point.
+ * Records are (key, t): key = (mix64(sketch(A[p]) ^ sketch(B[q])) & ~3) | phase_exponent(p,q),
+ * t = global flattened cross-term index q*M_total + p (uint32; M_total*N < 2^32).
+ * sym_pair_records: records of the block A[p_begin:p_end) x B, written in (q, p) order. */
+int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p_begin, int64_t p_end,
+                     const uint64_t *b_xz, int64_t N, int32_t W, uint64_t *keys, uint32_t *vals,
+                     void *ws, size_t ws_bytes, void *stream);
+size_t sym_pair_records_ws_bytes(int64_t M_total, int64_t N, int32_t W);
+/* Stable partition of records by owner = key >> (64 - log2_parts); counts: device int64[parts]. */
+size_t sym_partition_ws_bytes(int64_t T);
+int sym_partition_records(const uint64_t *keys, const uint32_t *vals, int64_t T, int32_t log2_parts,
+                          uint64_t *out_keys, uint32_t *out_vals, int64_t *counts, void *ws,
+                          size_t ws_bytes, void *stream);
+/* Dedup + coefficient reduction + row emission for a set of records whose rows are A[p] ^ B[q]
+ * (A, B fully resident). keys/vals are clobbered. Same output contract as sym_mul_cleanup. */
+size_t sym_dedup_records_ws_bytes(int64_t T, int32_t W);
+int sym_dedup_records_count(uint64_t *keys, uint32_t *vals, int64_t T, const uint64_t *a_xz,
+                            const double *a_c, int64_t M_total, const uint64_t *b_xz, const double *b_c,
+                            int64_t N, int32_t W, double zero_threshold, int64_t *n_out,
+                            int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
+int sym_dedup_records_emit(const uint32_t *vals, int64_t T, const uint64_t *a_xz, const double *a_c,
+                           int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W,
+                           int64_t U, uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes,
+                           void *stream);
+int sym_dedup_records(uint64_t *keys, uint32_t *vals, int64_t T, const uint64_t *a_xz, const double *a_c,
+                      int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W,
+                      double zero_threshold, uint64_t *out_xz, double *out_c, int64_t out_capacity,
+                      int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- primitives exported for tests and reuse */
+/* Stable LSD radix sort of (key, val) pairs on key bits [begin_bit, 64). Result in keys/vals. */
+size_t sym_sort_pairs_ws_bytes(int64_t T);
+int sym_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t T, int32_t begin_bit, void *ws,
+                   size_t ws_bytes, void *stream);
+/* Test hook: AND every dedup key with this mask (default ~0) to force sketch collisions. */
+int sym_debug_set_key_mask(uint64_t mask);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t sym_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYMMER_B200_H */

@@ -1,0 +1,19 @@
+"""symmer_b200 — B200-native (sm_100a) engine for symmer's symplectic Pauli algebra.
+
+Drop-in for the hot path behind UCL-CCS/symmer's PauliwordOp / QuantumState / IndependentOp API.
+Operators live in CUDA memory as bit-packed uint64 X|Z rows + complex128 coefficients (PyTorch
+owns the memory) and every kernel is reached through the C ABI of include/symmer_b200.h.
+"""
+from . import _cabi  # noqa: F401  (raises if the CUDA library is missing and cannot be built)
+
+__all__ = ["PauliwordOp", "QuantumState", "IndependentOp"]
+
+
+def __getattr__(name):
+    if name in ("PauliwordOp", "QuantumState"):
+        from . import base
+        return getattr(base, name)
+    if name == "IndependentOp":
+        from .independent_op import IndependentOp
+        return IndependentOp
+    raise AttributeError(name)

@@ -1,0 +1,207 @@
+// Layout kernels: bool <-> bit-packed rows, Y counts, GF(2)-linear row sketches, basis-index masks.
+// Also owns the library-wide globals (error string, launch counter, debug key mask).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace symb {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+uint64_t g_key_mask = ~0ull;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// one warp per (row, block, word): two coalesced 32-byte reads + ballots
+__global__ void pack_kernel(const uint8_t *__restrict__ symp, int64_t M, int n, int W, uint64_t *__restrict__ xz) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t total = M * 2 * W;
+    if (warp >= total) return;
+    int64_t row = warp / (2 * W);
+    int rem = (int)(warp % (2 * W));
+    int blk = rem / W, word = rem % W;
+    const uint8_t *src = symp + row * (2 * (int64_t)n) + (int64_t)blk * n;
+    int q0 = word * 64 + lane, q1 = q0 + 32;
+    uint32_t b0 = (q0 < n) ? (src[q0] != 0) : 0u;
+    uint32_t b1 = (q1 < n) ? (src[q1] != 0) : 0u;
+    uint32_t lo = __ballot_sync(0xffffffffu, b0);
+    uint32_t hi = __ballot_sync(0xffffffffu, b1);
+    if (lane == 0) xz[warp] = ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void unpack_kernel(const uint64_t *__restrict__ xz, int64_t M, int n, int W, uint8_t *__restrict__ symp) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = M * 2 * (int64_t)n;
+    if (i >= total) return;
+    int64_t row = i / (2 * n);
+    int col = (int)(i % (2 * n));
+    int blk = col / n, q = col % n;
+    uint64_t w = xz[row * 2 * W + (int64_t)blk * W + (q >> 6)];
+    symp[i] = (uint8_t)((w >> (q & 63)) & 1ull);
+}
+
+// one warp per row
+__global__ void ycount_kernel(const uint64_t *__restrict__ xz, int64_t M, int W, int32_t *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    const uint64_t *r = xz + row * 2 * W;
+    int cnt = 0;
+    for (int k = lane; k < W; k += 32) cnt += __popcll(r[k] & r[W + k]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    if (lane == 0) y[row] = cnt;
+}
+
+__global__ void sketch_kernel(const uint64_t *__restrict__ xz, int64_t M, int W, uint64_t *__restrict__ sk) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    uint64_t h = warp_sketch_row(xz + row * 2 * W, 2 * W, lane);
+    if (lane == 0) sk[row] = h;
+}
+
+// basis-index masks (qubit 0 = most significant bit), n <= 62, and coefficient * (-i)^Y
+__global__ void term_masks_kernel(const uint64_t *__restrict__ xz, const double *__restrict__ c, int64_t M, int n,
+                                  int64_t *__restrict__ xm, int64_t *__restrict__ zm, double *__restrict__ cp) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    uint64_t x = xz[2 * t], z = xz[2 * t + 1];  // W == 1
+    // packed bit q <-> basis bit (n-1-q): reverse the low n bits
+    uint64_t xr = __brevll(x) >> (64 - n), zr = __brevll(z) >> (64 - n);
+    xm[t] = (int64_t)xr;
+    zm[t] = (int64_t)zr;
+    double re = c[2 * t], im = c[2 * t + 1];
+    int k = __popcll(x & z) & 3;
+    mul_i_pow(re, im, (4 - k) & 3);  // (-i)^k = i^(-k)
+    cp[2 * t] = re;
+    cp[2 * t + 1] = im;
+}
+
+// generic GF(2) matrix packing (any column count): one warp per output word
+__global__ void pack_matrix_kernel(const uint8_t *__restrict__ m, int64_t R, int64_t C, uint64_t *__restrict__ bits,
+                                   int64_t Cw) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= R * Cw) return;
+    int64_t row = warp / Cw, word = warp % Cw;
+    const uint8_t *src = m + row * C;
+    int64_t q0 = word * 64 + lane, q1 = q0 + 32;
+    uint32_t b0 = (q0 < C) ? (src[q0] != 0) : 0u;
+    uint32_t b1 = (q1 < C) ? (src[q1] != 0) : 0u;
+    uint32_t lo = __ballot_sync(0xffffffffu, b0);
+    uint32_t hi = __ballot_sync(0xffffffffu, b1);
+    if (lane == 0) bits[warp] = ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void unpack_matrix_kernel(const uint64_t *__restrict__ bits, int64_t R, int64_t C, int64_t Cw,
+                                     uint8_t *__restrict__ m) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * C) return;
+    int64_t row = i / C, col = i % C;
+    m[i] = (uint8_t)((bits[row * Cw + (col >> 6)] >> (col & 63)) & 1ull);
+}
+
+}  // namespace symb
+
+using namespace symb;
+
+static inline unsigned blocks_for(int64_t threads, int per_block) {
+    int64_t b = (threads + per_block - 1) / per_block;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+extern "C" int sym_abi_version(void) { return SYM_ABI_VERSION; }
+extern "C" const char *sym_last_error(void) { return symb::g_err; }
+extern "C" int64_t sym_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int sym_debug_set_key_mask(uint64_t mask) {
+    g_key_mask = mask;
+    return SYM_OK;
+}
+
+extern "C" int sym_check_device(int *sm_count_host, int *cc_major_host, int *cc_minor_host) {
+    int dev = 0, major = 0, minor = 0, sms = 0;
+    SYM_CUDA_OK(cudaGetDevice(&dev));
+    SYM_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    SYM_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    SYM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sm_count_host) *sm_count_host = sms;
+    if (cc_major_host) *cc_major_host = major;
+    if (cc_minor_host) *cc_minor_host = minor;
+    if (major != 10) {
+        set_error("symmer_b200 is built for sm_100a only; device is sm_%d%d", major, minor);
+        return SYM_E_UNSUPPORTED;
+    }
+    return SYM_OK;
+}
+
+extern "C" int sym_pack(const uint8_t *symp, int64_t M, int32_t n, uint64_t *xz, void *stream) {
+    SYM_REQUIRE(M >= 0 && n >= 0, "negative size");
+    int W = n > 0 ? (n + 63) / 64 : 1;
+    if (M == 0) return SYM_OK;
+    if (n == 0) {
+        SYM_CUDA_OK(cudaMemsetAsync(xz, 0, sizeof(uint64_t) * 2 * (size_t)M, (cudaStream_t)stream));
+        return SYM_OK;
+    }
+    int64_t warps = M * 2 * W;
+    pack_kernel<<<blocks_for(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(symp, M, n, W, xz);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_unpack(const uint64_t *xz, int64_t M, int32_t n, uint8_t *symp, void *stream) {
+    SYM_REQUIRE(M >= 0 && n >= 0, "negative size");
+    if (M == 0 || n == 0) return SYM_OK;
+    int W = (n + 63) / 64;
+    unpack_kernel<<<blocks_for(M * 2 * (int64_t)n, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, n, W, symp);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_ycount(const uint64_t *xz, int64_t M, int32_t W, int32_t *y, void *stream) {
+    SYM_REQUIRE(M >= 0 && W >= 1, "bad size");
+    if (M == 0) return SYM_OK;
+    ycount_kernel<<<blocks_for(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, W, y);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_sketch_rows(const uint64_t *xz, int64_t M, int32_t W, uint64_t *sketch, void *stream) {
+    SYM_REQUIRE(M >= 0 && W >= 1, "bad size");
+    if (M == 0) return SYM_OK;
+    sketch_kernel<<<blocks_for(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, W, sketch);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_term_masks(const uint64_t *xz, const double *c, int64_t M, int32_t n, int64_t *x_masks,
+                              int64_t *z_masks, double *c_phased, void *stream) {
+    SYM_REQUIRE(M >= 0 && n >= 1 && n <= 62, "term masks need 1 <= n_qubits <= 62");
+    if (M == 0) return SYM_OK;
+    term_masks_kernel<<<blocks_for(M, 256), 256, 0, (cudaStream_t)stream>>>(xz, c, M, n, x_masks, z_masks, c_phased);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_pack_matrix(const uint8_t *m, int64_t R, int64_t C, uint64_t *bits, int64_t Cw, void *stream) {
+    SYM_REQUIRE(R >= 0 && C >= 0 && Cw * 64 >= C, "bad matrix shape");
+    if (R == 0 || Cw == 0) return SYM_OK;
+    pack_matrix_kernel<<<blocks_for(R * Cw * 32, 256), 256, 0, (cudaStream_t)stream>>>(m, R, C, bits, Cw);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_unpack_matrix(const uint64_t *bits, int64_t R, int64_t C, int64_t Cw, uint8_t *m, void *stream) {
+    SYM_REQUIRE(R >= 0 && C >= 0 && Cw * 64 >= C, "bad matrix shape");
+    if (R == 0 || C == 0) return SYM_OK;
+    unpack_matrix_kernel<<<blocks_for(R * C, 256), 256, 0, (cudaStream_t)stream>>>(bits, R, C, Cw, m);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}

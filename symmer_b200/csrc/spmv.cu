@@ -1,0 +1,175 @@
+// Matrix-free to_sparse_matrix / expval (symmer/operators/base.py:1458-1510; qiskit to_matrix_sparse):
+//   (H psi)[r] = sum_t c_t (-i)^{Y_t} (-1)^{popcount(r & z_t)} psi[r ^ x_t],   qubit 0 = MSB of r.
+// column = row XOR x, phase = popcount(row & z). Terms arrive sorted by x mask so that consecutive
+// terms with the same x share one gather of psi; one thread per basis row, terms streamed through
+// shared memory (broadcast reads). Bound by the integer + FP64 issue rate, not HBM.
+#include "common.cuh"
+
+namespace symb {
+
+constexpr int APPLY_THREADS = 256;
+constexpr int APPLY_TERMS = 512;  // terms per shared-memory tile
+
+struct TermTile {
+    int64_t x[APPLY_TERMS];
+    int64_t z[APPLY_TERMS];
+    double2 c[APPLY_TERMS];
+};
+
+template <bool EXPVAL>
+__global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const int64_t *__restrict__ xm, const int64_t *__restrict__ zm,
+                                                               const double2 *__restrict__ cp, int64_t M,
+                                                               const double2 *__restrict__ psi, double2 *__restrict__ y,
+                                                               int64_t row_begin, int64_t row_end, double *__restrict__ partial) {
+    __shared__ TermTile tile;
+    __shared__ double red[2][APPLY_THREADS / 32];
+    const int64_t r = row_begin + (int64_t)blockIdx.x * APPLY_THREADS + threadIdx.x;
+    const bool active = r < row_end;
+    double accr = 0.0, acci = 0.0;  // finished groups
+    double wr = 0.0, wi = 0.0;      // weight of the current x group
+    int64_t xcur = -1;
+    for (int64_t base = 0; base < M; base += APPLY_TERMS) {
+        const int nt = (int)min((int64_t)APPLY_TERMS, M - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt; i += APPLY_THREADS) {
+            tile.x[i] = xm[base + i];
+            tile.z[i] = zm[base + i];
+            tile.c[i] = cp[base + i];
+        }
+        __syncthreads();
+        if (active) {
+            for (int i = 0; i < nt; ++i) {
+                const int64_t x = tile.x[i];
+                if (x != xcur) {  // uniform across the CTA
+                    if (xcur >= 0) {
+                        const double2 p = psi[r ^ xcur];
+                        accr += wr * p.x - wi * p.y;
+                        acci += wr * p.y + wi * p.x;
+                    }
+                    xcur = x;
+                    wr = 0.0;
+                    wi = 0.0;
+                }
+                const double2 c = tile.c[i];
+                const bool neg = __popcll((uint64_t)(r & tile.z[i])) & 1;
+                wr += neg ? -c.x : c.x;
+                wi += neg ? -c.y : c.y;
+            }
+        }
+    }
+    if (active && xcur >= 0) {
+        const double2 p = psi[r ^ xcur];
+        accr += wr * p.x - wi * p.y;
+        acci += wr * p.y + wi * p.x;
+    }
+    if (!EXPVAL) {
+        if (active) y[r - row_begin] = make_double2(accr, acci);
+        return;
+    }
+    // conj(psi[r]) * (H psi)[r]
+    double er = 0.0, ei = 0.0;
+    if (active) {
+        const double2 p = psi[r];
+        er = p.x * accr + p.y * acci;
+        ei = p.x * acci - p.y * accr;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        er += __shfl_xor_sync(0xffffffffu, er, o);
+        ei += __shfl_xor_sync(0xffffffffu, ei, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[0][wid] = er;
+        red[1][wid] = ei;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int w = 0; w < APPLY_THREADS / 32; ++w) {
+            sr += red[0][w];
+            si += red[1][w];
+        }
+        atomicAdd(&partial[0], sr);
+        atomicAdd(&partial[1], si);
+    }
+}
+
+// CSR emitter for small n: thread per (row, group); value = sum over the group's terms, position =
+// rank of the column among the row's columns (counting), so rows come out sorted by column.
+__global__ void __launch_bounds__(256) csr_kernel(const int64_t *__restrict__ zm, const double2 *__restrict__ cp, int64_t M,
+                                                   int n, const int64_t *__restrict__ xg, int64_t G,
+                                                   const int32_t *__restrict__ group_start, double2 *__restrict__ data,
+                                                   int64_t *__restrict__ indices, int64_t *__restrict__ indptr) {
+    const int64_t side = (int64_t)1 << n;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) indptr[side] = side * G;
+    if (idx >= side * G) return;
+    const int64_t r = idx / G;
+    const int64_t g = idx - r * G;
+    const int64_t col = r ^ xg[g];
+    int64_t rank = 0;
+    for (int64_t h = 0; h < G; ++h) rank += ((r ^ xg[h]) < col) ? 1 : 0;
+    double sr = 0.0, si = 0.0;
+    for (int t = group_start[g]; t < group_start[g + 1]; ++t) {
+        const double2 c = cp[t];
+        const bool neg = __popcll((uint64_t)(r & zm[t])) & 1;
+        sr += neg ? -c.x : c.x;
+        si += neg ? -c.y : c.y;
+    }
+    data[r * G + rank] = make_double2(sr, si);
+    indices[r * G + rank] = col;
+    if (g == 0) indptr[r] = r * G;
+}
+
+}  // namespace symb
+
+using namespace symb;
+
+static int apply_common(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M, int32_t n,
+                        const double *psi, double *y, double *partial, int64_t row_begin, int64_t row_end, bool expval,
+                        cudaStream_t st) {
+    SYM_REQUIRE(n >= 1 && n <= 40, "n_qubits out of range for the dense-state path");
+    SYM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= ((int64_t)1 << n), "bad row range");
+    const int64_t rows = row_end - row_begin;
+    if (rows == 0) return SYM_OK;
+    const unsigned nb = (unsigned)((rows + APPLY_THREADS - 1) / APPLY_THREADS);
+    if (expval)
+        apply_kernel<true><<<nb, APPLY_THREADS, 0, st>>>(x_masks, z_masks, reinterpret_cast<const double2 *>(c_phased), M,
+                                                         reinterpret_cast<const double2 *>(psi), nullptr, row_begin,
+                                                         row_end, partial);
+    else
+        apply_kernel<false><<<nb, APPLY_THREADS, 0, st>>>(x_masks, z_masks, reinterpret_cast<const double2 *>(c_phased), M,
+                                                          reinterpret_cast<const double2 *>(psi),
+                                                          reinterpret_cast<double2 *>(y), row_begin, row_end, nullptr);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_apply(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
+                         int32_t n_qubits, const double *psi, double *y, int64_t row_begin, int64_t row_end,
+                         void *stream) {
+    return apply_common(x_masks, z_masks, c_phased, M, n_qubits, psi, y, nullptr, row_begin, row_end, false,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int sym_expval(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
+                          int32_t n_qubits, const double *psi, double *partial, int64_t row_begin, int64_t row_end,
+                          void *stream) {
+    return apply_common(x_masks, z_masks, c_phased, M, n_qubits, psi, nullptr, partial, row_begin, row_end, true,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int sym_to_csr(const int64_t *z_masks, const double *c_phased, int64_t M, int32_t n_qubits,
+                          const int64_t *x_groups, int64_t G, const int32_t *group_start, double *data, int64_t *indices,
+                          int64_t *indptr, void *stream) {
+    SYM_REQUIRE(n_qubits >= 1 && n_qubits <= 24, "CSR emitter is for small n_qubits");
+    SYM_REQUIRE(G >= 1 && M >= 1, "empty operator");
+    const int64_t total = ((int64_t)1 << n_qubits) * G;
+    csr_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        z_masks, reinterpret_cast<const double2 *>(c_phased), M, n_qubits, x_groups, G, group_start,
+        reinterpret_cast<double2 *>(data), indices, indptr);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}

@@ -1,0 +1,365 @@
+"""Device-level operators: thin torch plumbing (memory, streams) around the C ABI.
+
+Every function takes and returns CUDA tensors. Packed rows are `torch.int64[M, 2W]` (the bit
+pattern of the uint64 words of include/symmer_b200.h), coefficients `torch.complex128[M]`.
+There is no CPU path: without a CUDA device these raise.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _cabi
+
+_ws_cache = {}
+
+
+def lib():
+    return _cabi.load()
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("symmer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+_checked = set()
+
+
+def device():
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if dev.index not in _checked:
+        _cabi.check(lib().sym_check_device(None, None, None))
+        _checked.add(dev.index)
+    return dev
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def workspace(nbytes):
+    """Grow-only scratch buffer per device (torch owns the memory; the C ABI never allocates)."""
+    dev = device()
+    buf = _ws_cache.get(dev.index)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            del _ws_cache[dev.index]
+            del buf
+        buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=dev)
+        _ws_cache[dev.index] = buf
+    return buf
+
+
+def release_workspace():
+    _ws_cache.clear()
+
+
+def words_for(n_qubits):
+    return max(1, (int(n_qubits) + 63) // 64)
+
+
+def _rows(xz):
+    assert xz.is_cuda and xz.dtype == torch.int64 and xz.dim() == 2 and xz.is_contiguous()
+    return xz.shape[0], xz.shape[1] // 2
+
+
+def _coeff(c):
+    assert c.is_cuda and c.dtype == torch.complex128 and c.is_contiguous()
+    return c
+
+
+# ------------------------------------------------------------------------------------------ layout
+def pack(symp, n_qubits):
+    """bool/uint8[M, 2n] (device) -> int64[M, 2W]."""
+    dev = device()
+    symp = symp.to(device=dev)
+    if symp.dtype == torch.bool:
+        symp = symp.view(torch.uint8)
+    symp = symp.contiguous()
+    M = symp.shape[0]
+    W = words_for(n_qubits)
+    xz = torch.empty((M, 2 * W), dtype=torch.int64, device=dev)
+    _cabi.check(lib().sym_pack(_p(symp), M, int(n_qubits), _p(xz), _stream()))
+    return xz
+
+
+def unpack(xz, n_qubits):
+    M, W = _rows(xz)
+    out = torch.empty((M, 2 * int(n_qubits)), dtype=torch.uint8, device=xz.device)
+    _cabi.check(lib().sym_unpack(_p(xz), M, int(n_qubits), _p(out), _stream()))
+    return out.view(torch.bool)
+
+
+def ycount(xz):
+    M, W = _rows(xz)
+    y = torch.empty(M, dtype=torch.int32, device=xz.device)
+    _cabi.check(lib().sym_ycount(_p(xz), M, W, _p(y), _stream()))
+    return y
+
+
+def sketch(xz):
+    M, W = _rows(xz)
+    h = torch.empty(M, dtype=torch.int64, device=xz.device)
+    _cabi.check(lib().sym_sketch_rows(_p(xz), M, W, _p(h), _stream()))
+    return h
+
+
+# ---------------------------------------------------------------------------------------- multiply
+def cross_mul(a_xz, a_c, b_xz, b_c):
+    """Materialised cross terms in the reference's order t = q*M + p."""
+    M, W = _rows(a_xz)
+    N, W2 = _rows(b_xz)
+    assert W == W2
+    out_xz = torch.empty((M * N, 2 * W), dtype=torch.int64, device=a_xz.device)
+    out_c = torch.empty(M * N, dtype=torch.complex128, device=a_xz.device)
+    _cabi.check(lib().sym_cross_mul(_p(a_xz), _p(_coeff(a_c)), M, _p(b_xz), _p(_coeff(b_c)), N, W, _p(out_xz),
+                                    _p(out_c), _stream()))
+    return out_xz, out_c
+
+
+def _thr(zero_threshold):
+    return -1.0 if zero_threshold is None else float(zero_threshold)
+
+
+def mul_cleanup(a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
+    """Fused A*B + cleanup; returns (xz[U,2W], c[U]) in first-occurrence order of t = q*M + p."""
+    M, W = _rows(a_xz)
+    N, W2 = _rows(b_xz)
+    assert W == W2
+    dev = a_xz.device
+    if M * N == 0:
+        return (torch.empty((0, 2 * W), dtype=torch.int64, device=dev),
+                torch.empty(0, dtype=torch.complex128, device=dev))
+    L = lib()
+    nbytes = L.sym_mul_cleanup_ws_bytes(M, N, W)
+    ws = workspace(nbytes)
+    U = ctypes.c_int64(0)
+    _cabi.check(L.sym_mul_cleanup_count(_p(a_xz), _p(_coeff(a_c)), M, _p(b_xz), _p(_coeff(b_c)), N, W,
+                                        _thr(zero_threshold), None, ctypes.byref(U), _p(ws), ws.numel(), _stream()))
+    U = U.value
+    out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
+    out_c = torch.empty(U, dtype=torch.complex128, device=dev)
+    _cabi.check(L.sym_mul_cleanup_emit(_p(a_xz), _p(a_c), M, _p(b_xz), _p(b_c), N, W, U, _p(out_xz), _p(out_c),
+                                       _p(ws), ws.numel(), _stream()))
+    return out_xz, out_c
+
+
+def cleanup(xz, c, zero_threshold=1e-15):
+    T, W = _rows(xz)
+    dev = xz.device
+    if T == 0:
+        return xz.clone(), c.clone()
+    L = lib()
+    ws = workspace(L.sym_cleanup_ws_bytes(T, W))
+    U = ctypes.c_int64(0)
+    _cabi.check(L.sym_cleanup_count(_p(xz), _p(_coeff(c)), T, W, _thr(zero_threshold), None, ctypes.byref(U), _p(ws),
+                                    ws.numel(), _stream()))
+    U = U.value
+    out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
+    out_c = torch.empty(U, dtype=torch.complex128, device=dev)
+    _cabi.check(L.sym_cleanup_emit(_p(xz), _p(c), T, W, U, _p(out_xz), _p(out_c), _p(ws), ws.numel(), _stream()))
+    return out_xz, out_c
+
+
+# ----------------------------------------------------------------------------------------- commute
+def commute(a_xz, b_xz):
+    """bool[M, N], True where A[i] commutes with B[j]."""
+    M, W = _rows(a_xz)
+    N, W2 = _rows(b_xz)
+    assert W == W2
+    out = torch.empty((M, N), dtype=torch.uint8, device=a_xz.device)
+    _cabi.check(lib().sym_commute(_p(a_xz), M, _p(b_xz), N, W, _p(out), _stream()))
+    return out.view(torch.bool)
+
+
+def commute_bits(a_xz, b_xz):
+    M, W = _rows(a_xz)
+    N, _ = _rows(b_xz)
+    out = torch.zeros((M, (N + 31) // 32), dtype=torch.int32, device=a_xz.device)
+    _cabi.check(lib().sym_commute_bits(_p(a_xz), M, _p(b_xz), N, W, _p(out), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------- rotations
+def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0):
+    """One rotation step (no dedup). mode 0 general (returns M + M_ac rows), 1/2 Clifford."""
+    M, W = _rows(xz)
+    dev = xz.device
+    cap = 2 * M if mode == 0 else M
+    out_xz = torch.empty((cap, 2 * W), dtype=torch.int64, device=dev)
+    out_c = torch.empty(cap, dtype=torch.complex128, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    L = lib()
+    ws = workspace(L.sym_rotate_ws_bytes(M))
+    _cabi.check(L.sym_rotate(_p(xz), _p(_coeff(c)), M, W, _p(q_xz), float(cos_a), float(sin_a), int(mode), float(sign),
+                             _p(out_xz), _p(out_c), _p(n_out), _p(ws), ws.numel(), _stream()))
+    if mode == 0:
+        n = int(n_out.item())
+        return out_xz[:n], out_c[:n]
+    return out_xz, out_c
+
+
+# ------------------------------------------------------------------------------------- matrix-free
+def term_masks_sorted(xz, c, n_qubits):
+    """Basis-index masks and phased coefficients of every term, sorted by x mask."""
+    M, W = _rows(xz)
+    assert W == 1 and n_qubits <= 62
+    dev = xz.device
+    xm = torch.empty(M, dtype=torch.int64, device=dev)
+    zm = torch.empty(M, dtype=torch.int64, device=dev)
+    cp = torch.empty(M, dtype=torch.complex128, device=dev)
+    L = lib()
+    _cabi.check(L.sym_term_masks(_p(xz), _p(_coeff(c)), M, int(n_qubits), _p(xm), _p(zm), _p(cp), _stream()))
+    order = sort_pairs(xm.clone(), torch.arange(M, dtype=torch.int32, device=dev), begin_bit=0)[1].to(torch.int64)
+    return xm[order].contiguous(), zm[order].contiguous(), cp[order].contiguous()
+
+
+def apply_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
+    side = 1 << int(n_qubits)
+    row_end = side if row_end is None else row_end
+    psi = psi.contiguous()
+    assert psi.dtype == torch.complex128 and psi.numel() == side
+    y = torch.empty(row_end - row_begin, dtype=torch.complex128, device=psi.device)
+    _cabi.check(lib().sym_apply(_p(xm), _p(zm), _p(cp), xm.numel(), int(n_qubits), _p(psi), _p(y), row_begin, row_end,
+                                _stream()))
+    return y
+
+
+def expval_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
+    """Partial <psi|H|psi> over basis rows [row_begin, row_end) as a complex128 device scalar."""
+    side = 1 << int(n_qubits)
+    row_end = side if row_end is None else row_end
+    psi = psi.contiguous()
+    assert psi.dtype == torch.complex128 and psi.numel() == side
+    partial = torch.zeros(2, dtype=torch.float64, device=psi.device)
+    _cabi.check(lib().sym_expval(_p(xm), _p(zm), _p(cp), xm.numel(), int(n_qubits), _p(psi), _p(partial), row_begin,
+                                 row_end, _stream()))
+    return torch.view_as_complex(partial)
+
+
+def to_csr(xm, zm, cp, n_qubits):
+    """(data, indices, indptr) device tensors; every row has G = #distinct x entries sorted by column."""
+    dev = xm.device
+    xg, counts = torch.unique_consecutive(xm, return_counts=True)
+    G = xg.numel()
+    start = torch.zeros(G + 1, dtype=torch.int32, device=dev)
+    start[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    side = 1 << int(n_qubits)
+    data = torch.empty(side * G, dtype=torch.complex128, device=dev)
+    indices = torch.empty(side * G, dtype=torch.int64, device=dev)
+    indptr = torch.empty(side + 1, dtype=torch.int64, device=dev)
+    _cabi.check(lib().sym_to_csr(_p(zm), _p(cp), xm.numel(), int(n_qubits), _p(xg.contiguous()), G, _p(start), _p(data),
+                                 _p(indices), _p(indptr), _stream()))
+    return data, indices, indptr
+
+
+# ------------------------------------------------------------------------------------------- GF(2)
+def pack_matrix(m):
+    """bool[R, C] (device) -> int64[R, Cw]."""
+    dev = device()
+    m = m.to(device=dev)
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    m = m.contiguous()
+    R, C = m.shape
+    Cw = max(1, (C + 63) // 64)
+    bits = torch.zeros((R, Cw), dtype=torch.int64, device=dev)
+    _cabi.check(lib().sym_pack_matrix(_p(m), R, C, _p(bits), Cw, _stream()))
+    return bits
+
+
+def unpack_matrix(bits, C):
+    R, Cw = bits.shape
+    out = torch.empty((R, C), dtype=torch.uint8, device=bits.device)
+    _cabi.check(lib().sym_unpack_matrix(_p(bits), R, C, Cw, _p(out), _stream()))
+    return out.view(torch.bool)
+
+
+def rref_packed(bits, C):
+    """In-place _rref_binary on packed rows; returns the pivot column per row (-1 = zero row)."""
+    R, Cw = bits.shape
+    piv = torch.empty(R, dtype=torch.int32, device=bits.device)
+    L = lib()
+    ws = workspace(L.sym_rref_ws_bytes(R))
+    _cabi.check(L.sym_rref(_p(bits), R, C, Cw, _p(piv), _p(ws), ws.numel(), _stream()))
+    return piv
+
+
+# ---------------------------------------------------------------------------------- sort / records
+def sort_pairs(keys, vals, begin_bit=0):
+    """Stable sort of (int64-as-uint64 keys, int32-as-uint32 vals) in place; returns (keys, vals)."""
+    T = keys.numel()
+    assert keys.dtype == torch.int64 and vals.dtype == torch.int32 and vals.numel() == T
+    if T == 0:
+        return keys, vals
+    L = lib()
+    ws = workspace(L.sym_sort_pairs_ws_bytes(T))
+    _cabi.check(L.sym_sort_pairs(_p(keys), _p(vals), T, int(begin_bit), _p(ws), ws.numel(), _stream()))
+    return keys, vals
+
+
+def pair_records(a_xz, p_begin, p_end, b_xz):
+    """(keys int64[T], vals int32[T]) of the block A[p_begin:p_end) x B, T = (p_end-p_begin)*N."""
+    M, W = _rows(a_xz)
+    N, _ = _rows(b_xz)
+    T = (p_end - p_begin) * N
+    dev = a_xz.device
+    keys = torch.empty(T, dtype=torch.int64, device=dev)
+    vals = torch.empty(T, dtype=torch.int32, device=dev)
+    if T == 0:
+        return keys, vals
+    L = lib()
+    ws = workspace(L.sym_pair_records_ws_bytes(M, N, W))
+    _cabi.check(L.sym_pair_records(_p(a_xz), M, p_begin, p_end, _p(b_xz), N, W, _p(keys), _p(vals), _p(ws), ws.numel(),
+                                   _stream()))
+    return keys, vals
+
+
+def partition_records(keys, vals, log2_parts):
+    T = keys.numel()
+    dev = keys.device
+    ok = torch.empty_like(keys)
+    ov = torch.empty_like(vals)
+    counts = torch.zeros(1 << log2_parts, dtype=torch.int64, device=dev)
+    L = lib()
+    ws = workspace(L.sym_partition_ws_bytes(T))
+    _cabi.check(L.sym_partition_records(_p(keys), _p(vals), T, int(log2_parts), _p(ok), _p(ov), _p(counts), _p(ws),
+                                        ws.numel(), _stream()))
+    return ok, ov, counts
+
+
+def dedup_records(keys, vals, a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
+    """Dedup + reduce + emit for records whose rows are A[p]^B[q]; keys/vals are clobbered."""
+    T = keys.numel()
+    M, W = _rows(a_xz)
+    N, _ = _rows(b_xz)
+    dev = a_xz.device
+    if T == 0:
+        return (torch.empty((0, 2 * W), dtype=torch.int64, device=dev),
+                torch.empty(0, dtype=torch.complex128, device=dev))
+    L = lib()
+    ws = workspace(L.sym_dedup_records_ws_bytes(T, W))
+    U = ctypes.c_int64(0)
+    _cabi.check(L.sym_dedup_records_count(_p(keys), _p(vals), T, _p(a_xz), _p(_coeff(a_c)), M, _p(b_xz),
+                                          _p(_coeff(b_c)), N, W, _thr(zero_threshold), None, ctypes.byref(U), _p(ws),
+                                          ws.numel(), _stream()))
+    U = U.value
+    out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
+    out_c = torch.empty(U, dtype=torch.complex128, device=dev)
+    _cabi.check(L.sym_dedup_records_emit(_p(vals), T, _p(a_xz), _p(a_c), M, _p(b_xz), _p(b_c), N, W, U, _p(out_xz),
+                                         _p(out_c), _p(ws), ws.numel(), _stream()))
+    return out_xz, out_c
+
+
+def launch_count():
+    return int(lib().sym_launch_count())
+
+
+def set_debug_key_mask(mask):
+    _cabi.check(lib().sym_debug_set_key_mask(ctypes.c_uint64(mask & 0xFFFFFFFFFFFFFFFF)))

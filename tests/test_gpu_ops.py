@@ -1,0 +1,259 @@
+"""GPU parity tests of the C-ABI kernels (through symmer_b200.ops) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pauli_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import symmer_b200.ops as o
+    o.device()
+    return o
+
+
+def dev_op(ops, symp, coeff):
+    n = symp.shape[1] // 2
+    xz = ops.pack(torch.from_numpy(np.ascontiguousarray(symp)), n)
+    c = torch.from_numpy(np.asarray(coeff, dtype=complex)).cuda()
+    return xz, c
+
+
+def host_op(ops, xz, c, n):
+    return ops.unpack(xz, n).cpu().numpy(), c.cpu().numpy()
+
+
+@pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 130, 1000, 1100])
+def test_pack_unpack_ycount(ops, n):
+    rng = np.random.default_rng(n)
+    symp = rng.random((37, 2 * n)) < 0.3
+    xz = ops.pack(torch.from_numpy(symp), n)
+    assert np.array_equal(xz.cpu().numpy().view(np.uint64), po.pack_bits(symp))
+    assert np.array_equal(ops.unpack(xz, n).cpu().numpy(), symp)
+    assert np.array_equal(ops.ycount(xz).cpu().numpy(), po.y_count(symp))
+
+
+def test_sketch_is_linear(ops):
+    rng = np.random.default_rng(0)
+    for n in [3, 64, 200, 1000, 3000]:
+        a = rng.random((50, 2 * n)) < 0.3
+        b = rng.random((50, 2 * n)) < 0.3
+        ha = ops.sketch(ops.pack(torch.from_numpy(a), n))
+        hb = ops.sketch(ops.pack(torch.from_numpy(b), n))
+        hab = ops.sketch(ops.pack(torch.from_numpy(a ^ b), n))
+        assert torch.equal(ha ^ hb, hab)
+        assert len(set(ha.cpu().tolist())) == 50
+
+
+def test_sort_pairs(ops):
+    rng = np.random.default_rng(1)
+    for T in [1, 31, 4096, 4097, 100003]:
+        keys = rng.integers(0, 2**63 - 1, size=T, dtype=np.int64) * 2 + rng.integers(0, 2, size=T)
+        keys[::5] = keys[0]                       # many duplicates: checks stability
+        vals = np.arange(T, dtype=np.int32)
+        k = torch.from_numpy(keys.copy()).cuda()
+        v = torch.from_numpy(vals.copy()).cuda()
+        ops.sort_pairs(k, v, 0)
+        order = np.argsort(keys.view(np.uint64), kind="stable")
+        assert np.array_equal(k.cpu().numpy(), keys[order])
+        assert np.array_equal(v.cpu().numpy(), vals[order])
+
+
+@pytest.mark.parametrize("n,m1,m2", [(1, 3, 2), (5, 20, 7), (63, 12, 9), (64, 10, 13), (65, 9, 11), (130, 16, 5),
+                                     (1000, 40, 30), (1100, 7, 5)])
+def test_cross_terms_bit_exact(ops, n, m1, m2):
+    a_s, a_c = po.random_operator(n, m1, seed=n + m1)
+    b_s, b_c = po.random_operator(n, m2, seed=n + m2 + 1)
+    ref_rows, ref_c = po.cross_terms(a_s, a_c, b_s, b_c)
+    xz, c = ops.cross_mul(*dev_op(ops, a_s, a_c), *dev_op(ops, b_s, b_c))
+    rows, cc = host_op(ops, xz, c, n)
+    assert np.array_equal(rows, ref_rows)               # rows and order: bit-exact
+    assert np.allclose(cc, ref_c, rtol=1e-14, atol=0)   # one complex multiply of rounding
+
+
+def _check_product(ops, a_s, a_c, b_s, b_c, thr=1e-15):
+    n = a_s.shape[1] // 2
+    ref_s, ref_c = po.multiply_by_operator(a_s, a_c, b_s, b_c, thr)
+    xz, c = ops.mul_cleanup(*dev_op(ops, a_s, a_c), *dev_op(ops, b_s, b_c), thr)
+    s, cc = host_op(ops, xz, c, n)
+    scale = max(1e-300, np.abs(a_c).max() * np.abs(b_c).max())
+    ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=scale)
+    assert ok, why
+    return s, cc, ref_s, ref_c
+
+
+@pytest.mark.parametrize("n,m1,m2", [(1, 3, 2), (2, 4, 4), (5, 20, 7), (8, 30, 30), (64, 10, 13), (65, 9, 11),
+                                     (130, 16, 5), (1000, 60, 45), (1100, 6, 9), (4, 1, 1), (6, 1, 17), (6, 17, 1)])
+def test_mul_cleanup_matches_oracle(ops, n, m1, m2):
+    a_s, a_c = po.random_operator(n, m1, seed=10 * n + m1)
+    b_s, b_c = po.random_operator(n, m2, seed=10 * n + m2 + 3)
+    s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, b_s, b_c)
+    if len(ref_c) == len(cc):
+        # first-occurrence order, like the reference
+        assert np.array_equal(s, ref_s)
+
+
+def test_square_cancels_anticommuting_pairs_exactly(ops):
+    a_s, a_c = po.random_operator(1000, 120, seed=1)
+    s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, a_s, a_c)
+    comm = po.commutes_termwise(a_s, a_s)
+    n_comm_pairs = (np.count_nonzero(comm) - 120) // 2
+    assert len(cc) == n_comm_pairs + 1                  # commuting pairs + identity, residues are exact zeros
+
+
+def test_mul_cleanup_golden(ops, golden):
+    for nm in sorted(k for k in golden if k.startswith(("mul_rand_", "mul_single_"))):
+        g = golden[nm]
+        a_s, a_c, b_s, b_c = g["a_symp"], g["a_coeff"], g["b_symp"], g["b_coeff"]
+        n = a_s.shape[1] // 2
+        if a_s.shape[0] < b_s.shape[0]:                 # the reference's dagger swap (base.py:846-851)
+            xz, c = ops.mul_cleanup(*dev_op(ops, b_s, b_c.conj()), *dev_op(ops, a_s, a_c.conj()))
+            c = c.conj()
+        else:
+            xz, c = ops.mul_cleanup(*dev_op(ops, a_s, a_c), *dev_op(ops, b_s, b_c))
+        s, cc = host_op(ops, xz, c, n)
+        ok, why = po.compare_term_sets(s, cc, g["out_symp"], g["out_coeff"],
+                                       scale=np.abs(a_c).max() * np.abs(b_c).max())
+        assert ok, (nm, why)
+
+
+def test_forced_key_collisions_still_exact(ops):
+    """Mask the dedup keys down to a few bits so that distinct rows share keys: exercises the
+    irregular (linked) path; results must not change."""
+    a_s, a_c = po.random_operator(70, 40, seed=5)
+    b_s, b_c = po.random_operator(70, 35, seed=6)
+    b_s[:10] = a_s[:10]
+    try:
+        for mask in [0xFF00000000000000, 0xF000000000000000, 0x0]:
+            ops.set_debug_key_mask(mask)
+            _check_product(ops, a_s, a_c, b_s, b_c)
+            _check_product(ops, a_s, a_c, a_s, a_c)
+            symp = np.vstack([a_s, b_s, a_s[::-1]])
+            coeff = np.hstack([a_c, b_c, a_c])
+            xz, c = ops.cleanup(*dev_op(ops, symp, coeff))
+            s, cc = host_op(ops, xz, c, 70)
+            ref_s, ref_c = po.cleanup(symp, coeff)
+            ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(coeff).max())
+            assert ok, why
+    finally:
+        ops.set_debug_key_mask(0xFFFFFFFFFFFFFFFF)
+
+
+def test_cleanup_golden_and_order(ops, golden):
+    for nm in sorted(k for k in golden if k.startswith("cleanup_")):
+        g = golden[nm]
+        n = g["symp"].shape[1] // 2
+        xz, c = ops.cleanup(*dev_op(ops, g["symp"], g["coeff"]))
+        s, cc = host_op(ops, xz, c, n)
+        assert s.shape == g["out_symp"].shape, nm
+        assert np.array_equal(s, g["out_symp"]), nm      # same first-occurrence order as the reference
+        assert np.allclose(cc, g["out_coeff"], rtol=1e-12, atol=1e-15), nm
+
+
+def test_cleanup_threshold_none_keeps_zeros(ops):
+    symp, coeff = po.from_strings(["XX", "YY", "XX"], [1, 0, -1])
+    xz, c = ops.cleanup(*dev_op(ops, symp, coeff), zero_threshold=None)
+    assert xz.shape[0] == 2
+    xz, c = ops.cleanup(*dev_op(ops, symp, coeff), zero_threshold=1e-15)
+    assert xz.shape[0] == 0
+
+
+def test_commute_golden(ops, golden):
+    for nm in sorted(k for k in golden if k.startswith("commute_")):
+        g = golden[nm]
+        n = g["a_symp"].shape[1] // 2
+        a = ops.pack(torch.from_numpy(g["a_symp"]), n)
+        b = ops.pack(torch.from_numpy(g["b_symp"]), n)
+        assert np.array_equal(ops.commute(a, b).cpu().numpy(), g["out"]), nm
+        bits = ops.commute_bits(a, b).cpu().numpy().view(np.uint32)
+        N = g["b_symp"].shape[0]
+        unp = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(bits.shape[0], -1)[:, :N].astype(bool)
+        assert np.array_equal(unp, g["out"]), nm
+    for nm in sorted(k for k in golden if k.startswith("adj_ref_")):
+        g = golden[nm]
+        a = ops.pack(torch.from_numpy(g["symp"]), g["symp"].shape[1] // 2)
+        assert np.array_equal(ops.commute(a, a).cpu().numpy(), g["adj"]), nm
+
+
+@pytest.mark.parametrize("n,m1,m2", [(36, 700, 513), (1000, 300, 257), (1500, 40, 33)])
+def test_commute_random(ops, n, m1, m2):
+    a_s, _ = po.random_operator(n, m1, seed=n)
+    b_s, _ = po.random_operator(n, m2, seed=n + 1)
+    a = ops.pack(torch.from_numpy(a_s), n)
+    b = ops.pack(torch.from_numpy(b_s), n)
+    assert np.array_equal(ops.commute(a, b).cpu().numpy(), po.commutes_termwise(a_s, b_s))
+
+
+def test_gf2_golden(ops, golden):
+    for nm in sorted(k for k in golden if k.startswith("gf2_rand_")):
+        g = golden[nm]
+        m = g["matrix"]
+        bits = ops.pack_matrix(torch.from_numpy(m))
+        piv = ops.rref_packed(bits, m.shape[1])
+        red = ops.unpack_matrix(bits, m.shape[1]).cpu().numpy()
+        assert np.array_equal(red, g["rref_norows"]), nm
+        exp_piv = np.array([np.flatnonzero(r)[0] if r.any() else -1 for r in g["rref_norows"]])
+        assert np.array_equal(piv.cpu().numpy(), exp_piv), nm
+
+
+def test_gf2_large_path(ops):
+    rng = np.random.default_rng(3)
+    m = rng.random((300, 9000)) < 0.02        # 300 x 141 words > 200 KB: multi-launch path
+    bits = ops.pack_matrix(torch.from_numpy(m))
+    ops.rref_packed(bits, m.shape[1])
+    assert np.array_equal(ops.unpack_matrix(bits, m.shape[1]).cpu().numpy(), po._rref_binary(m))
+
+
+def test_apply_expval_csr(ops, golden):
+    for nm in sorted(k for k in golden if k.startswith("matrix_rand_")):
+        g = golden[nm]
+        n = g["symp"].shape[1] // 2
+        xz, c = dev_op(ops, g["symp"], g["coeff"])
+        xm, zm, cp = ops.term_masks_sorted(xz, c, n)
+        psi = torch.from_numpy(g["psi"]).cuda()
+        y = ops.apply_dense(xm, zm, cp, n, psi).cpu().numpy()
+        assert np.allclose(y, g["Hpsi"], rtol=1e-12, atol=1e-13), nm
+        e = complex(ops.expval_dense(xm, zm, cp, n, psi).cpu().numpy())
+        assert np.isclose(e, g["expval"][0], rtol=1e-12), nm
+        half = (1 << n) // 2
+        if half:
+            e2 = ops.expval_dense(xm, zm, cp, n, psi, 0, half) + ops.expval_dense(xm, zm, cp, n, psi, half, 1 << n)
+            assert np.isclose(complex(e2.cpu().numpy()), g["expval"][0], rtol=1e-12), nm
+        if g["dense"].size:
+            import scipy.sparse as sps
+            data, indices, indptr = [t.cpu().numpy() for t in ops.to_csr(xm, zm, cp, n)]
+            M = sps.csr_matrix((data, indices, indptr), shape=(1 << n, 1 << n))
+            assert M.has_canonical_format
+            assert np.allclose(M.toarray(), g["dense"], rtol=1e-13, atol=1e-13), nm
+
+
+def _rotate_dev(ops, symp, coeff, q_symp, angle):
+    """host logic of _rotate_by_single_Pword + cleanup, on device tensors (mirrors symmer_b200.base)."""
+    n = symp.shape[1] // 2
+    xz, c = dev_op(ops, symp, coeff)
+    q = ops.pack(torch.from_numpy(q_symp.reshape(1, -1)), n)
+    if angle is None:
+        angle = np.pi / 2
+    multiple = angle * 2 / np.pi
+    int_part = round(multiple)
+    if abs(int_part - multiple) <= 1e-18:
+        sign = -1.0 if int_part in [2, 3] else 1.0
+        oxz, oc = ops.rotate(xz, c, q, 0.0, 0.0, 1 if int_part % 2 else 2, sign)
+    else:
+        oxz, oc = ops.rotate(xz, c, q, np.cos(angle), np.sin(angle), 0)
+    oxz, oc = ops.cleanup(oxz, oc)
+    return host_op(ops, oxz, oc, n)
+
+
+def test_rotations_golden(ops, golden):
+    names = sorted(k for k in golden if k.startswith("rot_single_"))
+    assert len(names) >= 40
+    for nm in names:
+        g = golden[nm]
+        ang = None if np.isnan(g["angle"][0]) else float(g["angle"][0])
+        s, cc = _rotate_dev(ops, g["symp"], g["coeff"], g["q_symp"][0], ang)
+        ok, why = po.compare_term_sets(s, cc, g["out_symp"], g["out_coeff"], scale=np.abs(g["coeff"]).max())
+        assert ok, (nm, why)
