@@ -60,8 +60,9 @@ int sym_cross_mul(const uint64_t *a_xz, const double *a_c, int64_t M, const uint
 /* Fused product + cleanup (base.py:764-794 followed by utils.py:230-279) that never materialises
  * the M*N cross terms: dedup runs on 64-bit keys derived from the row sketches, rows are only
  * written for the survivors. zero_threshold < 0 disables the |c| > threshold filter (the
- * reference's `None`). Output rows are unique; their order is unspecified (reference order is
- * first-occurrence; parity is defined on canonically sorted term sets).
+ * reference's `None`). Output rows are unique; order is first-occurrence (the reference's) for
+ * products up to 2^22 cross terms and sorted-hash order above (parity is defined on canonically
+ * sorted term sets).
  * n_out: device int64[1], receives the number of surviving terms. out_capacity: rows available in
  * out_xz/out_c; on overflow returns SYM_E_CAPACITY after a stream synchronise.
  * This call synchronises the stream once (it needs the survivor count to size the emit launch). */
@@ -152,30 +153,34 @@ int sym_pack_matrix(const uint8_t *m, int64_t R, int64_t C, uint64_t *bits, int6
 int sym_unpack_matrix(const uint64_t *bits, int64_t R, int64_t C, int64_t Cw, uint8_t *m, void *stream);
 
 /* ---- multi-GPU building blocks: the product path split at its exchange point.
- * Records are (key, t): key = (mix64(sketch(A[p]) ^ sketch(B[q])) & ~3) | phase_exponent(p,q),
- * t = global flattened cross-term index q*M_total + p (uint32; M_total*N < 2^32).
+ * A record is one 64-bit word  [ hash : 62-tb bits | t : tb bits | e : 2 bits ]  with
+ * hash = top bits of mix64(sketch(A[p]) ^ sketch(B[q])), t = global flattened cross-term index
+ * q*M_total + p, e = phase exponent of the pair, tb = ceil(log2(M_total*N)) (M_total*N < 4e9).
+ * Equal rows have equal hash fields, so the owner of a row is a function of its top hash bits and
+ * only these 8-byte records (never rows) cross NVLink; the owner rebuilds rows from its replicas of
+ * A and B.
  * sym_pair_records: records of the block A[p_begin:p_end) x B, written in (q, p) order. */
-int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p_begin, int64_t p_end,
-                     const uint64_t *b_xz, int64_t N, int32_t W, uint64_t *keys, uint32_t *vals,
-                     void *ws, size_t ws_bytes, void *stream);
 size_t sym_pair_records_ws_bytes(int64_t M_total, int64_t N, int32_t W);
-/* Stable partition of records by owner = key >> (64 - log2_parts); counts: device int64[parts]. */
+int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p_begin, int64_t p_end,
+                     const uint64_t *b_xz, int64_t N, int32_t W, uint64_t *recs, void *ws,
+                     size_t ws_bytes, void *stream);
+/* Stable partition of records by owner = rec >> (64 - log2_parts); counts: device int64[parts]. */
 size_t sym_partition_ws_bytes(int64_t T);
-int sym_partition_records(const uint64_t *keys, const uint32_t *vals, int64_t T, int32_t log2_parts,
-                          uint64_t *out_keys, uint32_t *out_vals, int64_t *counts, void *ws,
-                          size_t ws_bytes, void *stream);
-/* Dedup + coefficient reduction + row emission for a set of records whose rows are A[p] ^ B[q]
- * (A, B fully resident). keys/vals are clobbered. Same output contract as sym_mul_cleanup. */
+int sym_partition_records(const uint64_t *recs, int64_t T, int32_t log2_parts, uint64_t *out_recs,
+                          int64_t *counts, void *ws, size_t ws_bytes, void *stream);
+/* Dedup + coefficient reduction + row emission for T records whose rows are A[p] ^ B[q] (A, B
+ * fully resident, M_total rows in A). recs is clobbered; pass the same buffer to _emit. Output in
+ * sorted-hash order. Same two-phase contract as sym_mul_cleanup_count/_emit. */
 size_t sym_dedup_records_ws_bytes(int64_t T, int32_t W);
-int sym_dedup_records_count(uint64_t *keys, uint32_t *vals, int64_t T, const uint64_t *a_xz,
-                            const double *a_c, int64_t M_total, const uint64_t *b_xz, const double *b_c,
-                            int64_t N, int32_t W, double zero_threshold, int64_t *n_out,
-                            int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
-int sym_dedup_records_emit(const uint32_t *vals, int64_t T, const uint64_t *a_xz, const double *a_c,
+int sym_dedup_records_count(uint64_t *recs, int64_t T, const uint64_t *a_xz, const double *a_c,
+                            int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N,
+                            int32_t W, double zero_threshold, int64_t *n_out, int64_t *n_out_host,
+                            void *ws, size_t ws_bytes, void *stream);
+int sym_dedup_records_emit(const uint64_t *recs, int64_t T, const uint64_t *a_xz, const double *a_c,
                            int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W,
                            int64_t U, uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes,
                            void *stream);
-int sym_dedup_records(uint64_t *keys, uint32_t *vals, int64_t T, const uint64_t *a_xz, const double *a_c,
+int sym_dedup_records(uint64_t *recs, int64_t T, const uint64_t *a_xz, const double *a_c,
                       int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W,
                       double zero_threshold, uint64_t *out_xz, double *out_c, int64_t out_capacity,
                       int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
@@ -185,6 +190,9 @@ int sym_dedup_records(uint64_t *keys, uint32_t *vals, int64_t T, const uint64_t 
 size_t sym_sort_pairs_ws_bytes(int64_t T);
 int sym_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t T, int32_t begin_bit, void *ws,
                    size_t ws_bytes, void *stream);
+/* Tuning knobs. which = 0: cross-term count up to which sym_mul_cleanup emits in first-occurrence
+ * (reference) order instead of sorted-hash order (default 2^22). */
+int sym_set_tuning(int32_t which, int64_t value);
 /* Test hook: AND every dedup key with this mask (default ~0) to force sketch collisions. */
 int sym_debug_set_key_mask(uint64_t mask);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */

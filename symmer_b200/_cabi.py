@@ -45,16 +45,17 @@ SIGNATURES = {
     "sym_pack_matrix": (ctypes.c_int, [c_p, c_i64, c_i64, c_p, c_i64, c_p]),
     "sym_unpack_matrix": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     "sym_pair_records_ws_bytes": (c_sz, [c_i64, c_i64, c_i32]),
-    "sym_pair_records": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_i64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
+    "sym_pair_records": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
     "sym_partition_ws_bytes": (c_sz, [c_i64]),
-    "sym_partition_records": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "sym_partition_records": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
     "sym_dedup_records_ws_bytes": (c_sz, [c_i64, c_i32]),
-    "sym_dedup_records": (ctypes.c_int, [c_p, c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_f64, c_p, c_p,
+    "sym_dedup_records": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_f64, c_p, c_p,
                                          c_i64, c_p, c_p, c_p, c_sz, c_p]),
-    "sym_dedup_records_count": (ctypes.c_int, [c_p, c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_f64, c_p,
+    "sym_dedup_records_count": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_f64, c_p,
                                                c_p, c_p, c_sz, c_p]),
     "sym_dedup_records_emit": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_i64, c_p, c_p,
                                               c_p, c_sz, c_p]),
+    "sym_set_tuning": (ctypes.c_int, [c_i32, c_i64]),
     "sym_sort_pairs_ws_bytes": (c_sz, [c_i64]),
     "sym_sort_pairs": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_sz, c_p]),
     "sym_debug_set_key_mask": (ctypes.c_int, [c_u64]),

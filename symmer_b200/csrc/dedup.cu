@@ -1,13 +1,14 @@
-// Dedup of terms by 64-bit key with exact row verification, segmented coefficient reduction in input
-// order, threshold filter and row emission. Replaces qiskit's `unordered_unique` + `np.add.at`
-// (symmer/operators/utils.py:271-278) — HBM-bound integer/byte work, no tensor cores.
+// Dedup of terms by hashed 64-bit records with exact row verification, segmented coefficient
+// reduction in input order, threshold filter and row emission. Replaces qiskit's `unordered_unique`
+// + `np.add.at` (symmer/operators/utils.py:271-278) — HBM-bound integer/byte work, no tensor cores.
 //
 // Pipeline (all on one stream):
-//   1. stable LSD radix sort of (key, t) on the top K key bits   -> equal rows become neighbours
-//   2. link: every sorted position decides head / same-as-predecessor / irregular
-//   3. sum: each head adds the coefficients of its chain in input (t) order
-//   4. irregular chains (key collisions inside a sort bucket; rare) are folded in with atomics
-//   5. keep = head && |sum| > threshold ; exclusive scan -> output slots ; compact ; emit rows
+//   1. stable LSD radix sort of the records on their top hash bits -> equal rows become neighbours,
+//      ordered by t inside a run
+//   2. link: every sorted position decides head / same-as-predecessor / irregular (exact row compare)
+//   3. sum: each head adds the coefficients of its chain in input (t) order and applies |c| > thr
+//   4. irregular chains (hash collisions inside a sort bucket; rare) are folded in with atomics
+//   5. exclusive scan of keep flags -> output slots ; compact ; emit rows with 16-byte stores
 #include "rows.cuh"
 #include "sort.cuh"
 
@@ -16,24 +17,23 @@ namespace symb {
 constexpr uint8_t FLAG_HEAD = 0, FLAG_PREV = 1, FLAG_LINK = 2;
 
 template <class Rows>
-__global__ void __launch_bounds__(256) link_kernel(Rows rows, const uint64_t *__restrict__ sk, const uint32_t *__restrict__ st,
-                                                    int64_t T, int sort_shift, uint8_t *__restrict__ flag,
-                                                    uint32_t *__restrict__ link) {
+__global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                                    int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     uint8_t f = FLAG_HEAD;
     if (i > 0) {
-        const uint64_t ki = sk[i], kp = sk[i - 1];
-        if ((ki >> sort_shift) == (kp >> sort_shift)) {
-            const uint32_t ti = st[i];
-            if (((ki ^ kp) >> 2) == 0 && rows.equal(ti, st[i - 1])) {
+        const uint64_t ri = sr[i], rp = sr[i - 1];
+        if (((ri ^ rp) >> sort_shift) == 0) {
+            const uint32_t ti = fmt.t(ri);
+            if (fmt.same_hash(ri, rp) && rows.equal(ti, fmt.t(rp))) {
                 f = FLAG_PREV;
             } else {
                 // irregular: a different row shares this sort bucket; look further back for a twin
                 for (int64_t j = i - 2; j >= 0; --j) {
-                    const uint64_t kj = sk[j];
-                    if ((kj >> sort_shift) != (ki >> sort_shift)) break;
-                    if (((ki ^ kj) >> 2) == 0 && rows.equal(ti, st[j])) {
+                    const uint64_t rj = sr[j];
+                    if (((ri ^ rj) >> sort_shift) != 0) break;
+                    if (fmt.same_hash(ri, rj) && rows.equal(ti, fmt.t(rj))) {
                         f = FLAG_LINK;
                         link[i] = (uint32_t)j;
                         break;
@@ -45,64 +45,76 @@ __global__ void __launch_bounds__(256) link_kernel(Rows rows, const uint64_t *__
     flag[i] = f;
 }
 
+__device__ __forceinline__ uint8_t keep_test(double re, double im, double thr) {
+    return (thr < 0.0) ? 1 : (hypot(re, im) > thr ? 1 : 0);
+}
+
 // heads: sequential sum over the chain of FLAG_PREV successors (input order, like np.add.at)
 template <class Rows, bool BY_T>
-__global__ void __launch_bounds__(256) sum_kernel(Rows rows, const uint64_t *__restrict__ sk, const uint32_t *__restrict__ st,
-                                                   int64_t T, const uint8_t *__restrict__ flag, double2 *__restrict__ acc) {
+__global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                                   const uint8_t *__restrict__ flag, double thr, double2 *__restrict__ acc,
+                                                   uint8_t *__restrict__ keep) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
-    if (flag[i] != FLAG_HEAD) return;
+    const uint64_t r0 = sr[i];
+    const int64_t d = BY_T ? (int64_t)fmt.t(r0) : i;
+    if (flag[i] != FLAG_HEAD) {
+        keep[d] = 0;
+        return;
+    }
     double re, im;
-    const uint32_t t0 = st[i];
-    rows.coeff(t0, sk[i], re, im);
+    rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
     for (int64_t j = i + 1; j < T && flag[j] == FLAG_PREV; ++j) {
         double r2, i2;
-        rows.coeff(st[j], sk[j], r2, i2);
+        const uint64_t rj = sr[j];
+        rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
         re += r2;
         im += i2;
     }
-    acc[BY_T ? (int64_t)t0 : i] = make_double2(re, im);
+    acc[d] = make_double2(re, im);
+    keep[d] = keep_test(re, im, thr);
+}
+
+__device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_t *link, int64_t i) {
+    int64_t r = link[i];
+    while (flag[r] != FLAG_HEAD) r = (flag[r] == FLAG_PREV) ? r - 1 : (int64_t)link[r];
+    return r;
 }
 
 template <class Rows, bool BY_T>
-__global__ void __launch_bounds__(256) sum_irregular_kernel(Rows rows, const uint64_t *__restrict__ sk,
-                                                             const uint32_t *__restrict__ st, int64_t T,
+__global__ void __launch_bounds__(256) sum_irregular_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
                                                              const uint8_t *__restrict__ flag, const uint32_t *__restrict__ link,
                                                              double2 *__restrict__ acc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     if (flag[i] != FLAG_LINK) return;
     double re, im;
-    rows.coeff(st[i], sk[i], re, im);
+    const uint64_t r0 = sr[i];
+    rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
     for (int64_t j = i + 1; j < T && flag[j] == FLAG_PREV; ++j) {
         double r2, i2;
-        rows.coeff(st[j], sk[j], r2, i2);
+        const uint64_t rj = sr[j];
+        rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
         re += r2;
         im += i2;
     }
-    int64_t r = link[i];
-    while (flag[r] != FLAG_HEAD) r = (flag[r] == FLAG_PREV) ? r - 1 : (int64_t)link[r];
-    double2 *dst = acc + (BY_T ? (int64_t)st[r] : r);
+    const int64_t r = chain_root(flag, link, i);
+    double2 *dst = acc + (BY_T ? (int64_t)fmt.t(sr[r]) : r);
     atomicAdd(&dst->x, re);
     atomicAdd(&dst->y, im);
 }
 
 template <bool BY_T>
-__global__ void __launch_bounds__(256) keep_kernel(const uint32_t *__restrict__ st, int64_t T, const uint8_t *__restrict__ flag,
-                                                    const double2 *__restrict__ acc, double thr, uint8_t *__restrict__ keep) {
+__global__ void __launch_bounds__(256) keep_fix_kernel(RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                                        const uint8_t *__restrict__ flag, const uint32_t *__restrict__ link,
+                                                        const double2 *__restrict__ acc, double thr, uint8_t *__restrict__ keep) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
-    const int64_t d = BY_T ? (int64_t)st[i] : i;
-    uint8_t k = 0;
-    if (flag[i] == FLAG_HEAD) {
-        if (thr < 0.0) {
-            k = 1;
-        } else {
-            double2 a = acc[d];
-            k = hypot(a.x, a.y) > thr ? 1 : 0;
-        }
-    }
-    keep[d] = k;
+    if (flag[i] != FLAG_LINK) return;
+    const int64_t r = chain_root(flag, link, i);
+    const int64_t d = BY_T ? (int64_t)fmt.t(sr[r]) : r;
+    const double2 a = acc[d];
+    keep[d] = keep_test(a.x, a.y, thr);
 }
 
 __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict__ keep, const uint32_t *__restrict__ slot,
@@ -114,50 +126,93 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict_
 
 __global__ void total_to_i64_kernel(const uint32_t *__restrict__ total, int64_t *__restrict__ n_out) { *n_out = (int64_t)*total; }
 
-// one thread per (kept record, word): coalesced 8-byte stores of the surviving rows
+// Row emission. One thread per (kept record, 16-byte chunk), EMIT_UN records per thread so that
+// 2*EMIT_UN independent 16-byte loads are in flight per thread (the kernel is latency-bound
+// otherwise). Stores are streaming (st.global.cs): the output is never re-read, and A/B must stay
+// L2-resident. LW: chunks per row = 1 << LW.
+int g_emit_variant = 4;  // tuning knob 1: 2 records per thread, plain stores (measured best on B200)
+
+__device__ __forceinline__ void store_streaming(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <class Rows, bool BY_T, int LW, int EMIT_UN, bool CS>
+__global__ void __launch_bounds__(256) emit_kernel(Rows rows, RecFmt fmt, const uint32_t *__restrict__ kept, uint32_t U,
+                                                    const uint64_t *__restrict__ sr, const double2 *__restrict__ acc,
+                                                    uint4 *__restrict__ out_xz, double2 *__restrict__ out_c) {
+    constexpr uint32_t ROWS_PP = 256u >> LW;
+    const uint32_t r_in = threadIdx.x >> LW;
+    const uint32_t c = threadIdx.x & ((1u << LW) - 1u);
+    uint32_t rec[EMIT_UN], d[EMIT_UN], t[EMIT_UN];
+    uint4 v[EMIT_UN];
+#pragma unroll
+    for (int u = 0; u < EMIT_UN; ++u) {
+        rec[u] = (blockIdx.x * EMIT_UN + u) * ROWS_PP + r_in;
+        d[u] = rec[u] < U ? kept[rec[u]] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < EMIT_UN; ++u) t[u] = BY_T ? d[u] : fmt.t(sr[d[u]]);
+#pragma unroll
+    for (int u = 0; u < EMIT_UN; ++u) v[u] = rows.chunk(t[u], (int)c);
+#pragma unroll
+    for (int u = 0; u < EMIT_UN; ++u) {
+        if (rec[u] < U) {
+            if (CS) store_streaming(out_xz + (((size_t)rec[u]) << LW) + c, v[u]);
+            else out_xz[(((size_t)rec[u]) << LW) + c] = v[u];
+            if (c == 0) out_c[rec[u]] = acc[d[u]];
+        }
+    }
+}
+
+// generic chunk count (W not a power of two, or W > 16)
 template <class Rows, bool BY_T>
-__global__ void __launch_bounds__(256) emit_kernel(Rows rows, const uint32_t *__restrict__ kept, int64_t U,
-                                                    const uint32_t *__restrict__ st, const double2 *__restrict__ acc,
-                                                    uint64_t *__restrict__ out_xz, double2 *__restrict__ out_c) {
-    const int words = rows.words;
-    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t rec = g / words;
+__global__ void __launch_bounds__(256) emit_generic_kernel(Rows rows, RecFmt fmt, const uint32_t *__restrict__ kept, uint32_t U,
+                                                            uint32_t chunks, const uint64_t *__restrict__ sr,
+                                                            const double2 *__restrict__ acc, uint4 *__restrict__ out_xz,
+                                                            double2 *__restrict__ out_c) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t rec = (uint32_t)(g / chunks);
+    const uint32_t c = (uint32_t)(g - (size_t)rec * chunks);
     if (rec >= U) return;
-    int k = (int)(g - rec * words);
     const uint32_t d = kept[rec];
-    const uint32_t t = BY_T ? d : st[d];
-    out_xz[g] = rows.word(t, k);
-    if (k == 0) out_c[rec] = acc[d];
+    const uint32_t t = BY_T ? d : fmt.t(sr[d]);
+    store_streaming(out_xz + g, rows.chunk(t, (int)c));
+    if (c == 0) out_c[rec] = acc[d];
 }
 
 size_t dedup_ws_bytes(int64_t T) {
     if (T < 1) T = 1;
     size_t n = (size_t)T;
-    return arena_need(n, 8)                        // keys_alt
-           + arena_need(n, 4)                      // vals_alt
-           + arena_need(sort_hist_elems(T), 4)     // radix histograms + scan scratch
-           + arena_need(n, 1)                      // flag
-           + arena_need(n, 4)                      // link
-           + arena_need(n, 16)                     // acc
-           + arena_need(n, 1)                      // keep
-           + arena_need(n, 4)                      // slot
-           + arena_need(n, 4)                      // kept
-           + arena_need(scan_scratch_elems(T), 4)  // scan scratch
+    return arena_need(n, 8)                          // alt record buffer
+           + arena_need(record_hist_elems(T), 4)     // radix histograms + scan scratch
+           + arena_need(n, 1)                        // flag
+           + arena_need(n, 4)                        // link
+           + arena_need(n, 16)                       // acc
+           + arena_need(n, 1)                        // keep
+           + arena_need(n, 4)                        // slot
+           + arena_need(n, 4)                        // kept
+           + arena_need(scan_scratch_elems(T), 4)    // scan scratch
            + arena_need(4, 4) + 4096;
 }
 
-static int sort_bits_for(int64_t T) {
-    int lg = 0;
-    while ((int64_t(1) << lg) < T) ++lg;
-    int k = ((lg + 8 + 7) / 8) * 8;
-    if (k > 56) k = 56;
-    if (k < 8) k = 8;
-    return k;
+// Sort on at least tb + 5 hash bits (rounded up to whole 8-bit passes): the expected number of
+// distinct rows sharing a sort bucket is then <= T / 32, and those are resolved exactly by the
+// irregular path.
+static int sort_begin_bit(int64_t T, RecFmt fmt) {
+    int lg = t_bits_for(T);
+    int want = ((lg + 5 + 7) / 8) * 8;
+    int begin = 64 - want;
+    if (begin < fmt.tb + 2) begin = fmt.tb + 2;
+    return begin;
+}
+
+static bool sorted_in_alt(int begin_bit) {
+    int passes = (64 - begin_bit + 7) / 8;
+    return (passes & 1) != 0;
 }
 
 struct DedupLayout {
-    uint64_t *keys_alt;
-    uint32_t *vals_alt;
+    uint64_t *alt;
     uint32_t *hist;
     uint8_t *flag;
     uint32_t *link;
@@ -173,9 +228,8 @@ struct DedupLayout {
 static DedupLayout dedup_layout(void *ws, size_t ws_bytes, int64_t T) {
     Arena ar(ws, ws_bytes);
     DedupLayout L;
-    L.keys_alt = ar.take<uint64_t>((size_t)T);
-    L.vals_alt = ar.take<uint32_t>((size_t)T);
-    L.hist = ar.take<uint32_t>(sort_hist_elems(T));
+    L.alt = ar.take<uint64_t>((size_t)T);
+    L.hist = ar.take<uint32_t>(record_hist_elems(T));
     L.flag = ar.take<uint8_t>((size_t)T);
     L.link = ar.take<uint32_t>((size_t)T);
     L.acc = ar.take<double2>((size_t)T);
@@ -190,8 +244,8 @@ static DedupLayout dedup_layout(void *ws, size_t ws_bytes, int64_t T) {
 
 // Phase 1: everything up to the survivor count (synchronises the stream once to read it).
 template <class Rows, bool BY_T>
-static int dedup_plan(uint64_t *keys, uint32_t *vals, bool vals_iota, int64_t T, const Rows &rows, double thr,
-                      int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
+static int dedup_plan(uint64_t *recs, int64_t T, RecFmt fmt, const Rows &rows, double thr, int64_t *n_out,
+                      int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (T == 0) {
         if (n_out) SYM_CUDA_OK(cudaMemsetAsync(n_out, 0, sizeof(int64_t), st));
         if (n_out_host) *n_out_host = 0;
@@ -206,18 +260,18 @@ static int dedup_plan(uint64_t *keys, uint32_t *vals, bool vals_iota, int64_t T,
         set_error("workspace arena exhausted");
         return SYM_E_WORKSPACE;
     }
-    const int sort_bits = sort_bits_for(T);
-    const int sort_shift = 64 - sort_bits;
-    SYM_TRY(radix_sort_pairs(keys, vals, L.keys_alt, L.vals_alt, T, sort_shift, vals_iota, L.hist, st));
+    const int begin = sort_begin_bit(T, fmt);
+    uint64_t *sr = nullptr;
+    SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
 
     const unsigned nb = (unsigned)((T + 255) / 256);
-    link_kernel<Rows><<<nb, 256, 0, st>>>(rows, keys, vals, T, sort_shift, L.flag, L.link);
+    link_kernel<Rows><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link);
     SYM_LAUNCH_OK();
-    sum_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, keys, vals, T, L.flag, L.acc);
+    sum_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, fmt, sr, T, L.flag, thr, L.acc, L.keep);
     SYM_LAUNCH_OK();
-    sum_irregular_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, keys, vals, T, L.flag, L.link, L.acc);
+    sum_irregular_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, fmt, sr, T, L.flag, L.link, L.acc);
     SYM_LAUNCH_OK();
-    keep_kernel<BY_T><<<nb, 256, 0, st>>>(vals, T, L.flag, L.acc, thr, L.keep);
+    keep_fix_kernel<BY_T><<<nb, 256, 0, st>>>(fmt, sr, T, L.flag, L.link, L.acc, thr, L.keep);
     SYM_LAUNCH_OK();
     SYM_TRY(scan_exclusive_u8(L.keep, L.slot, T, L.total, L.scratch, st));
     compact_kernel<<<nb, 256, 0, st>>>(L.keep, L.slot, T, L.kept);
@@ -233,54 +287,84 @@ static int dedup_plan(uint64_t *keys, uint32_t *vals, bool vals_iota, int64_t T,
     return SYM_OK;
 }
 
-// Phase 2: write the U surviving rows + coefficients (asynchronous). `vals` must be the sorted
-// values left by the plan phase (only read when !BY_T).
+// Phase 2: write the U surviving rows + coefficients (asynchronous). `recs` is the same buffer
+// that was given to the plan phase.
 template <class Rows, bool BY_T>
-static int dedup_emit(const uint32_t *vals, int64_t T, const Rows &rows, int64_t U, uint64_t *out_xz, double *out_c,
-                      void *ws, size_t ws_bytes, cudaStream_t st) {
+static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &rows, int64_t U, uint64_t *out_xz,
+                      double *out_c, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (T == 0 || U == 0) return SYM_OK;
     DedupLayout L = dedup_layout(ws, ws_bytes, T);
     if (!L.ok) {
         set_error("workspace arena exhausted");
         return SYM_E_WORKSPACE;
     }
-    int64_t threads = U * rows.words;
-    emit_kernel<Rows, BY_T><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rows, L.kept, U, vals, L.acc, out_xz,
-                                                                              reinterpret_cast<double2 *>(out_c));
+    const uint64_t *sr = (T > 1 && sorted_in_alt(sort_begin_bit(T, fmt))) ? L.alt : recs;
+    const uint32_t chunks = (uint32_t)(rows.words / 2);
+    uint4 *o = reinterpret_cast<uint4 *>(out_xz);
+    double2 *oc = reinterpret_cast<double2 *>(out_c);
+#define EMIT_LAUNCH(LW, UN, CS)                                                                                    \
+    {                                                                                                              \
+        const uint32_t rows_per_block = (256u >> LW) * UN;                                                         \
+        const unsigned nb = (unsigned)((U + rows_per_block - 1) / rows_per_block);                                 \
+        emit_kernel<Rows, BY_T, LW, UN, CS><<<nb, 256, 0, st>>>(rows, fmt, L.kept, (uint32_t)U, sr, L.acc, o, oc); \
+    }
+#define EMIT_CASE(LW)                                       \
+    switch (g_emit_variant) {                               \
+        case 1: EMIT_LAUNCH(LW, 8, false); break;           \
+        case 2: EMIT_LAUNCH(LW, 8, true); break;            \
+        case 3: EMIT_LAUNCH(LW, 4, false); break;           \
+        case 4: EMIT_LAUNCH(LW, 2, false); break;           \
+        case 5: EMIT_LAUNCH(LW, 1, true); break;            \
+        default: EMIT_LAUNCH(LW, 1, false); break;          \
+    }
+    switch (chunks) {
+        case 1: EMIT_CASE(0); break;
+        case 2: EMIT_CASE(1); break;
+        case 4: EMIT_CASE(2); break;
+        case 8: EMIT_CASE(3); break;
+        case 16: EMIT_CASE(4); break;
+        default: {
+            const size_t threads = (size_t)U * chunks;
+            emit_generic_kernel<Rows, BY_T><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+                rows, fmt, L.kept, (uint32_t)U, chunks, sr, L.acc, o, oc);
+        } break;
+    }
+#undef EMIT_CASE
+#undef EMIT_LAUNCH
     SYM_LAUNCH_OK();
     return SYM_OK;
 }
 
-int dedup_product_plan(uint64_t *keys, uint32_t *vals, bool vals_iota, int64_t T, const ProductRows &rows, bool by_t,
-                       double thr, int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
-    if (by_t) return dedup_plan<ProductRows, true>(keys, vals, vals_iota, T, rows, thr, n_out, n_out_host, ws, ws_bytes, st);
-    return dedup_plan<ProductRows, false>(keys, vals, vals_iota, T, rows, thr, n_out, n_out_host, ws, ws_bytes, st);
+int dedup_product_plan(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, bool by_t, double thr,
+                       int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (by_t) return dedup_plan<ProductRows, true>(recs, T, fmt, rows, thr, n_out, n_out_host, ws, ws_bytes, st);
+    return dedup_plan<ProductRows, false>(recs, T, fmt, rows, thr, n_out, n_out_host, ws, ws_bytes, st);
 }
 
-int dedup_product_emit(const uint32_t *vals, int64_t T, const ProductRows &rows, bool by_t, int64_t U, uint64_t *out_xz,
-                       double *out_c, void *ws, size_t ws_bytes, cudaStream_t st) {
-    if (by_t) return dedup_emit<ProductRows, true>(vals, T, rows, U, out_xz, out_c, ws, ws_bytes, st);
-    return dedup_emit<ProductRows, false>(vals, T, rows, U, out_xz, out_c, ws, ws_bytes, st);
+int dedup_product_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, bool by_t, int64_t U,
+                       uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (by_t) return dedup_emit<ProductRows, true>(recs, T, fmt, rows, U, out_xz, out_c, ws, ws_bytes, st);
+    return dedup_emit<ProductRows, false>(recs, T, fmt, rows, U, out_xz, out_c, ws, ws_bytes, st);
 }
 
-int dedup_plain_plan(uint64_t *keys, uint32_t *vals, int64_t T, const PlainRows &rows, double thr, int64_t *n_out,
+int dedup_plain_plan(uint64_t *recs, int64_t T, RecFmt fmt, const PlainRows &rows, double thr, int64_t *n_out,
                      int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
-    return dedup_plan<PlainRows, true>(keys, vals, true, T, rows, thr, n_out, n_out_host, ws, ws_bytes, st);
+    return dedup_plan<PlainRows, true>(recs, T, fmt, rows, thr, n_out, n_out_host, ws, ws_bytes, st);
 }
 
-int dedup_plain_emit(int64_t T, const PlainRows &rows, int64_t U, uint64_t *out_xz, double *out_c, void *ws,
-                     size_t ws_bytes, cudaStream_t st) {
-    return dedup_emit<PlainRows, true>(nullptr, T, rows, U, out_xz, out_c, ws, ws_bytes, st);
+int dedup_plain_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const PlainRows &rows, int64_t U, uint64_t *out_xz,
+                     double *out_c, void *ws, size_t ws_bytes, cudaStream_t st) {
+    return dedup_emit<PlainRows, true>(recs, T, fmt, rows, U, out_xz, out_c, ws, ws_bytes, st);
 }
 
-// keys of stored rows: mix64(sketch) with the two low bits cleared (no phase for plain rows)
-__global__ void __launch_bounds__(256) plain_keys_kernel(const uint64_t *__restrict__ xz, int64_t T, int words, uint64_t mask,
-                                                          uint64_t *__restrict__ keys) {
+// records of stored rows: hash of the row sketch, t = row index, e = 0
+__global__ void __launch_bounds__(256) plain_records_kernel(const uint64_t *__restrict__ xz, int64_t T, int words, uint64_t mask,
+                                                             RecFmt fmt, uint64_t *__restrict__ recs) {
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= T) return;
     uint64_t h = warp_sketch_row(xz + row * words, words, lane);
-    if (lane == 0) keys[row] = (mix64(h) & mask) & ~3ull;
+    if (lane == 0) recs[row] = fmt.make(mix64(h) & mask, (uint64_t)row, 0);
 }
 
 }  // namespace symb
@@ -290,7 +374,7 @@ using namespace symb;
 extern "C" size_t sym_cleanup_ws_bytes(int64_t T, int32_t W) {
     (void)W;
     if (T < 1) T = 1;
-    return dedup_ws_bytes(T) + arena_need((size_t)T, 8) + arena_need((size_t)T, 4) + 1024;
+    return dedup_ws_bytes(T) + arena_need((size_t)T, 8) + 1024;
 }
 
 static int cleanup_check(int64_t T, int32_t W, size_t ws_bytes) {
@@ -313,13 +397,12 @@ extern "C" int sym_cleanup_count(const uint64_t *xz, const double *c, int64_t T,
         return SYM_OK;
     }
     Arena ar(ws, ws_bytes);
-    uint64_t *keys = ar.take<uint64_t>((size_t)T);
-    uint32_t *vals = ar.take<uint32_t>((size_t)T);
-    plain_keys_kernel<<<(unsigned)((T * 32 + 255) / 256), 256, 0, st>>>(xz, T, 2 * W, g_key_mask, keys);
+    uint64_t *recs = ar.take<uint64_t>((size_t)T);
+    RecFmt fmt{t_bits_for(T)};
+    plain_records_kernel<<<(unsigned)((T * 32 + 255) / 256), 256, 0, st>>>(xz, T, 2 * W, g_key_mask, fmt, recs);
     SYM_LAUNCH_OK();
     PlainRows rows{xz, c, 2 * W};
-    return dedup_plain_plan(keys, vals, T, rows, zero_threshold, n_out, n_out_host, ar.base + ar.off, ws_bytes - ar.off,
-                            st);
+    return dedup_plain_plan(recs, T, fmt, rows, zero_threshold, n_out, n_out_host, ar.base + ar.off, ws_bytes - ar.off, st);
 }
 
 extern "C" int sym_cleanup_emit(const uint64_t *xz, const double *c, int64_t T, int32_t W, int64_t U, uint64_t *out_xz,
@@ -327,10 +410,11 @@ extern "C" int sym_cleanup_emit(const uint64_t *xz, const double *c, int64_t T, 
     SYM_TRY(cleanup_check(T, W, ws_bytes));
     if (T == 0 || U == 0) return SYM_OK;
     Arena ar(ws, ws_bytes);
-    ar.take<uint64_t>((size_t)T);
-    ar.take<uint32_t>((size_t)T);
+    uint64_t *recs = ar.take<uint64_t>((size_t)T);
+    RecFmt fmt{t_bits_for(T)};
     PlainRows rows{xz, c, 2 * W};
-    return dedup_plain_emit(T, rows, U, out_xz, out_c, ar.base + ar.off, ws_bytes - ar.off, (cudaStream_t)stream);
+    return dedup_plain_emit(recs, T, fmt, rows, U, out_xz, out_c, ar.base + ar.off, ws_bytes - ar.off,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int sym_cleanup(const uint64_t *xz, const double *c, int64_t T, int32_t W, double zero_threshold,

@@ -29,8 +29,7 @@ template <int WT>
 __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
     const uint64_t *__restrict__ a_xz, const uint64_t *__restrict__ a_sk, const int32_t *__restrict__ a_y, uint32_t M_total,
     uint32_t p_begin, uint32_t p_end, const uint64_t *__restrict__ b_xz, const uint64_t *__restrict__ b_sk,
-    const int32_t *__restrict__ b_y, uint32_t N, int W, uint64_t key_mask, uint64_t *__restrict__ keys,
-    uint32_t *__restrict__ vals) {
+    const int32_t *__restrict__ b_y, uint32_t N, int W, uint64_t key_mask, RecFmt fmt, uint64_t *__restrict__ recs) {
     // B tile: QCH rows, (x_w, z_w) interleaved so one 16-byte shared load feeds a word step
     __shared__ ulonglong2 sb[PAIR_QCH][WT];
     __shared__ uint64_t sb_sk[PAIR_QCH];
@@ -87,10 +86,8 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
             c0 ^= v;
         }
         const int e = finish_phase(ya, sb_y[qi], s, c0, c1);
-        const uint64_t key = ((mix64(ska ^ sb_sk[qi]) & key_mask) & ~3ull) | (uint64_t)e;
         const size_t j = (size_t)(q0 + qi) * m_blk + p_local;
-        keys[j] = key;
-        if (vals != nullptr) vals[j] = (q0 + qi) * M_total + p;
+        recs[j] = fmt.make(mix64(ska ^ sb_sk[qi]) & key_mask, (uint64_t)(q0 + qi) * M_total + p, e);
     }
 }
 
@@ -98,8 +95,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
 __global__ void __launch_bounds__(256) pair_records_generic_kernel(
     const uint64_t *__restrict__ a_xz, const uint64_t *__restrict__ a_sk, const int32_t *__restrict__ a_y, uint32_t M_total,
     uint32_t p_begin, uint32_t p_end, const uint64_t *__restrict__ b_xz, const uint64_t *__restrict__ b_sk,
-    const int32_t *__restrict__ b_y, uint32_t N, int W, uint64_t key_mask, uint64_t *__restrict__ keys,
-    uint32_t *__restrict__ vals) {
+    const int32_t *__restrict__ b_y, uint32_t N, int W, uint64_t key_mask, RecFmt fmt, uint64_t *__restrict__ recs) {
     const uint32_t m_blk = p_end - p_begin;
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (size_t)m_blk * N) return;
@@ -115,20 +111,19 @@ __global__ void __launch_bounds__(256) pair_records_generic_kernel(
         c0 ^= v;
     }
     int e = finish_phase(a_y[p], b_y[q], s, c0, c1);
-    keys[j] = ((mix64(a_sk[p] ^ b_sk[q]) & key_mask) & ~3ull) | (uint64_t)e;
-    if (vals != nullptr) vals[j] = q * M_total + p;
+    recs[j] = fmt.make(mix64(a_sk[p] ^ b_sk[q]) & key_mask, (uint64_t)q * M_total + p, e);
 }
 
 static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const int32_t *a_y, int64_t M_total,
                                int64_t p_begin, int64_t p_end, const uint64_t *b_xz, const uint64_t *b_sk,
-                               const int32_t *b_y, int64_t N, int W, uint64_t *keys, uint32_t *vals, cudaStream_t st) {
+                               const int32_t *b_y, int64_t N, int W, RecFmt fmt, uint64_t *recs, cudaStream_t st) {
     const int64_t m_blk = p_end - p_begin;
     if (m_blk <= 0 || N <= 0) return SYM_OK;
     dim3 grid((unsigned)((m_blk + PAIR_THREADS - 1) / PAIR_THREADS), (unsigned)((N + PAIR_QCH - 1) / PAIR_QCH));
 #define PAIR_CASE(WT)                                                                                               \
     pair_records_kernel<WT><<<grid, PAIR_THREADS, 0, st>>>(a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin,   \
                                                            (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N, W,        \
-                                                           g_key_mask, keys, vals)
+                                                           g_key_mask, fmt, recs)
     if (grid.y > 65535) {
         set_error("too many B rows for one launch (N=%lld)", (long long)N);
         return SYM_E_UNSUPPORTED;
@@ -142,7 +137,7 @@ static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const
         int64_t total = m_blk * N;
         pair_records_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
             a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin, (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N, W,
-            g_key_mask, keys, vals);
+            g_key_mask, fmt, recs);
     }
 #undef PAIR_CASE
     SYM_LAUNCH_OK();
@@ -232,8 +227,8 @@ static int prepare_operand_tables(const uint64_t *a_xz, int64_t M, const uint64_
 }
 
 extern "C" int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p_begin, int64_t p_end,
-                                const uint64_t *b_xz, int64_t N, int32_t W, uint64_t *keys, uint32_t *vals, void *ws,
-                                size_t ws_bytes, void *stream) {
+                                const uint64_t *b_xz, int64_t N, int32_t W, uint64_t *recs, void *ws, size_t ws_bytes,
+                                void *stream) {
     SYM_REQUIRE(M_total >= 0 && N >= 0 && W >= 1, "bad size");
     SYM_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= M_total, "bad row block");
     SYM_REQUIRE(M_total * N < (int64_t)4000000000LL, "M_total*N must be < 4e9");
@@ -246,7 +241,26 @@ extern "C" int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p
     uint64_t *a_sk, *b_sk;
     int32_t *a_y, *b_y;
     SYM_TRY(prepare_operand_tables(a_xz, M_total, b_xz, N, W, ar, a_sk, b_sk, a_y, b_y, st));
-    return launch_pair_records(a_xz, a_sk, a_y, M_total, p_begin, p_end, b_xz, b_sk, b_y, N, W, keys, vals, st);
+    RecFmt fmt{t_bits_for(M_total * N)};
+    return launch_pair_records(a_xz, a_sk, a_y, M_total, p_begin, p_end, b_xz, b_sk, b_y, N, W, fmt, recs, st);
+}
+
+extern "C" size_t sym_partition_ws_bytes(int64_t T) {
+    if (T < 1) T = 1;
+    return arena_need(record_hist_elems(T), 4) + 1024;
+}
+
+extern "C" int sym_partition_records(const uint64_t *recs, int64_t T, int32_t log2_parts, uint64_t *out_recs,
+                                     int64_t *counts, void *ws, size_t ws_bytes, void *stream) {
+    SYM_REQUIRE(T >= 0 && T < (int64_t)4000000000LL, "T out of range");
+    SYM_REQUIRE(log2_parts >= 0 && log2_parts <= 8, "log2_parts must be in [0,8]");
+    if (ws_bytes < sym_partition_ws_bytes(T)) {
+        set_error("workspace too small");
+        return SYM_E_WORKSPACE;
+    }
+    Arena ar(ws, ws_bytes);
+    uint32_t *hist = ar.take<uint32_t>(record_hist_elems(T));
+    return radix_partition_records(recs, out_recs, T, log2_parts, counts, hist, (cudaStream_t)stream);
 }
 
 extern "C" size_t sym_dedup_records_ws_bytes(int64_t T, int32_t W) {
@@ -254,54 +268,73 @@ extern "C" size_t sym_dedup_records_ws_bytes(int64_t T, int32_t W) {
     return dedup_ws_bytes(T);
 }
 
-extern "C" int sym_dedup_records_count(uint64_t *keys, uint32_t *vals, int64_t T, const uint64_t *a_xz, const double *a_c,
+extern "C" int sym_dedup_records_count(uint64_t *recs, int64_t T, const uint64_t *a_xz, const double *a_c,
                                        int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W,
                                        double zero_threshold, int64_t *n_out, int64_t *n_out_host, void *ws,
                                        size_t ws_bytes, void *stream) {
     SYM_REQUIRE(T >= 0 && T < (int64_t)4000000000LL, "T out of range");
     SYM_REQUIRE(M_total >= 1 && N >= 1 && W >= 1, "bad size");
+    SYM_REQUIRE(M_total * N < (int64_t)4000000000LL, "M_total*N must be < 4e9");
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W};
-    return dedup_product_plan(keys, vals, false, T, rows, false, zero_threshold, n_out, n_out_host, ws, ws_bytes,
+    RecFmt fmt{t_bits_for(M_total * N)};
+    return dedup_product_plan(recs, T, fmt, rows, false, zero_threshold, n_out, n_out_host, ws, ws_bytes,
                               (cudaStream_t)stream);
 }
 
-extern "C" int sym_dedup_records_emit(const uint32_t *vals, int64_t T, const uint64_t *a_xz, const double *a_c,
+extern "C" int sym_dedup_records_emit(const uint64_t *recs, int64_t T, const uint64_t *a_xz, const double *a_c,
                                       int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W,
                                       int64_t U, uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, void *stream) {
     SYM_REQUIRE(T >= 0 && U >= 0 && U <= T, "bad counts");
     SYM_REQUIRE(M_total >= 1 && N >= 1 && W >= 1, "bad size");
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W};
-    return dedup_product_emit(vals, T, rows, false, U, out_xz, out_c, ws, ws_bytes, (cudaStream_t)stream);
+    RecFmt fmt{t_bits_for(M_total * N)};
+    return dedup_product_emit(recs, T, fmt, rows, false, U, out_xz, out_c, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int sym_dedup_records(uint64_t *keys, uint32_t *vals, int64_t T, const uint64_t *a_xz, const double *a_c,
-                                 int64_t M_total, const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W,
-                                 double zero_threshold, uint64_t *out_xz, double *out_c, int64_t out_capacity,
-                                 int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream) {
+extern "C" int sym_dedup_records(uint64_t *recs, int64_t T, const uint64_t *a_xz, const double *a_c, int64_t M_total,
+                                 const uint64_t *b_xz, const double *b_c, int64_t N, int32_t W, double zero_threshold,
+                                 uint64_t *out_xz, double *out_c, int64_t out_capacity, int64_t *n_out,
+                                 int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream) {
     int64_t U = 0;
-    SYM_TRY(sym_dedup_records_count(keys, vals, T, a_xz, a_c, M_total, b_xz, b_c, N, W, zero_threshold, n_out, &U, ws,
-                                    ws_bytes, stream));
+    SYM_TRY(sym_dedup_records_count(recs, T, a_xz, a_c, M_total, b_xz, b_c, N, W, zero_threshold, n_out, &U, ws, ws_bytes,
+                                    stream));
     if (n_out_host) *n_out_host = U;
     if (U > out_capacity) {
         set_error("output capacity %lld < %lld surviving terms", (long long)out_capacity, (long long)U);
         return SYM_E_CAPACITY;
     }
-    return sym_dedup_records_emit(vals, T, a_xz, a_c, M_total, b_xz, b_c, N, W, U, out_xz, out_c, ws, ws_bytes, stream);
+    return sym_dedup_records_emit(recs, T, a_xz, a_c, M_total, b_xz, b_c, N, W, U, out_xz, out_c, ws, ws_bytes, stream);
 }
 
 extern "C" size_t sym_mul_cleanup_ws_bytes(int64_t M, int64_t N, int32_t W) {
     int64_t T = M * N;
     if (T < 1) T = 1;
-    return sym_pair_records_ws_bytes(M, N, W) + arena_need((size_t)T, 8) + arena_need((size_t)T, 4) + dedup_ws_bytes(T) +
-           1024;
+    return sym_pair_records_ws_bytes(M, N, W) + arena_need((size_t)T, 8) + dedup_ws_bytes(T) + 1024;
+}
+
+// Below this many cross terms the product is emitted in first-occurrence (reference) order; above,
+// in sorted-hash order, which keeps every pass of the dedup streaming (no T-sized scatters).
+static int64_t g_by_t_limit = (int64_t)1 << 22;
+namespace symb { extern int g_emit_variant; }
+
+extern "C" int sym_set_tuning(int32_t which, int64_t value) {
+    if (which == 0) {
+        g_by_t_limit = value;
+        return SYM_OK;
+    }
+    if (which == 1) {
+        symb::g_emit_variant = (int)value;
+        return SYM_OK;
+    }
+    set_error("unknown tuning knob %d", which);
+    return SYM_E_INVALID;
 }
 
 // workspace layout shared by the count and emit phases
 struct MulPlan {
     uint64_t *a_sk, *b_sk;
     int32_t *a_y, *b_y;
-    uint64_t *keys;
-    uint32_t *vals;
+    uint64_t *recs;
     void *rest;
     size_t rest_bytes;
     bool ok;
@@ -315,9 +348,8 @@ static MulPlan mul_plan_layout(void *ws, size_t ws_bytes, int64_t M, int64_t N) 
     P.b_sk = ar.take<uint64_t>((size_t)(N > 0 ? N : 1));
     P.a_y = ar.take<int32_t>((size_t)(M > 0 ? M : 1));
     P.b_y = ar.take<int32_t>((size_t)(N > 0 ? N : 1));
-    P.keys = ar.take<uint64_t>((size_t)(T > 0 ? T : 1));
-    P.vals = ar.take<uint32_t>((size_t)(T > 0 ? T : 1));
-    P.ok = P.vals != nullptr;
+    P.recs = ar.take<uint64_t>((size_t)(T > 0 ? T : 1));
+    P.ok = P.recs != nullptr;
     P.rest = ar.base + ar.off;
     P.rest_bytes = ws_bytes > ar.off ? ws_bytes - ar.off : 0;
     return P;
@@ -353,10 +385,10 @@ extern "C" int sym_mul_cleanup_count(const uint64_t *a_xz, const double *a_c, in
     SYM_TRY(sym_sketch_rows(b_xz, N, W, P.b_sk, st));
     SYM_TRY(sym_ycount(a_xz, M, W, P.a_y, st));
     SYM_TRY(sym_ycount(b_xz, N, W, P.b_y, st));
-    // records are written in t order, so vals are implicit (iota) in the first sort pass
-    SYM_TRY(launch_pair_records(a_xz, P.a_sk, P.a_y, M, 0, M, b_xz, P.b_sk, P.b_y, N, W, P.keys, nullptr, st));
+    RecFmt fmt{t_bits_for(T)};
+    SYM_TRY(launch_pair_records(a_xz, P.a_sk, P.a_y, M, 0, M, b_xz, P.b_sk, P.b_y, N, W, fmt, P.recs, st));
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W};
-    return dedup_product_plan(P.keys, P.vals, true, T, rows, true, zero_threshold, n_out, n_out_host, P.rest,
+    return dedup_product_plan(P.recs, T, fmt, rows, T <= g_by_t_limit, zero_threshold, n_out, n_out_host, P.rest,
                               P.rest_bytes, st);
 }
 
@@ -368,7 +400,9 @@ extern "C" int sym_mul_cleanup_emit(const uint64_t *a_xz, const double *a_c, int
     if (T == 0 || U == 0) return SYM_OK;
     MulPlan P = mul_plan_layout(ws, ws_bytes, M, N);
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W};
-    return dedup_product_emit(P.vals, T, rows, true, U, out_xz, out_c, P.rest, P.rest_bytes, (cudaStream_t)stream);
+    RecFmt fmt{t_bits_for(T)};
+    return dedup_product_emit(P.recs, T, fmt, rows, T <= g_by_t_limit, U, out_xz, out_c, P.rest, P.rest_bytes,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int sym_mul_cleanup(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz, const double *b_c,

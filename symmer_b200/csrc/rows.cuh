@@ -1,12 +1,30 @@
-// Row accessors shared by the dedup pipeline: where a "term" t gets its packed row and coefficient.
+// Row accessors and the record format shared by the dedup pipeline.
 #pragma once
 #include "common.cuh"
 
 namespace symb {
 
+// A dedup record is one 64-bit word:   [ hash : 62 - tb bits | t : tb bits | e : 2 bits ]
+// hash = top bits of mix64(sketch(row)); t = term index (cross-term index q*M + p for products);
+// e = phase exponent of the cross term (0 for stored rows). Equal rows have equal hash fields.
+struct RecFmt {
+    int tb;
+    __host__ __device__ __forceinline__ uint32_t t(uint64_t rec) const { return (uint32_t)((rec >> 2) & ((1ull << tb) - 1ull)); }
+    __host__ __device__ __forceinline__ int e(uint64_t rec) const { return (int)(rec & 3ull); }
+    __host__ __device__ __forceinline__ bool same_hash(uint64_t a, uint64_t b) const { return ((a ^ b) >> (tb + 2)) == 0; }
+    __host__ __device__ __forceinline__ uint64_t make(uint64_t key, uint64_t t, int e) const {
+        return ((key >> (tb + 2)) << (tb + 2)) | (t << 2) | (uint64_t)e;
+    }
+};
+
+static inline int t_bits_for(int64_t T) {
+    int tb = 1;
+    while ((int64_t(1) << tb) < T) ++tb;
+    return tb;
+}
+
 // Term t is the cross term (p, q) of a product A*B in the reference's flattened order t = q*M + p
-// (base.py:783-792); its row is A[p] ^ B[q] and is never stored. The record key carries the phase
-// exponent of the pair in its two low bits.
+// (base.py:783-792); its row is A[p] ^ B[q] and is never stored.
 struct ProductRows {
     const uint64_t *__restrict__ A;
     const uint64_t *__restrict__ B;
@@ -19,10 +37,12 @@ struct ProductRows {
         q = t / M;
         p = t - q * M;
     }
-    __device__ __forceinline__ uint64_t word(uint32_t t, int k) const {
+    __device__ __forceinline__ uint4 chunk(uint32_t t, int c) const {  // 16-byte chunk c of the row
         uint32_t p, q;
         split(t, p, q);
-        return A[(size_t)p * words + k] ^ B[(size_t)q * words + k];
+        const uint4 a = reinterpret_cast<const uint4 *>(A + (size_t)p * words)[c];
+        const uint4 b = reinterpret_cast<const uint4 *>(B + (size_t)q * words)[c];
+        return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w);
     }
     __device__ __forceinline__ bool equal(uint32_t t1, uint32_t t2) const {
         uint32_t p1, q1, p2, q2;
@@ -34,11 +54,11 @@ struct ProductRows {
             if ((a1[k] ^ b1[k]) != (a2[k] ^ b2[k])) return false;
         return true;
     }
-    __device__ __forceinline__ void coeff(uint32_t t, uint64_t key, double &re, double &im) const {
+    __device__ __forceinline__ void coeff(uint32_t t, int e, double &re, double &im) const {
         uint32_t p, q;
         split(t, p, q);
         cmul(Ac[2 * (size_t)p], Ac[2 * (size_t)p + 1], Bc[2 * (size_t)q], Bc[2 * (size_t)q + 1], re, im);
-        mul_i_pow(re, im, (int)(key & 3ull));
+        mul_i_pow(re, im, e);
     }
 };
 
@@ -48,30 +68,33 @@ struct PlainRows {
     const double *__restrict__ C;
     int words;
 
-    __device__ __forceinline__ uint64_t word(uint32_t t, int k) const { return X[(size_t)t * words + k]; }
+    __device__ __forceinline__ uint4 chunk(uint32_t t, int c) const {
+        return reinterpret_cast<const uint4 *>(X + (size_t)t * words)[c];
+    }
     __device__ __forceinline__ bool equal(uint32_t t1, uint32_t t2) const {
         const uint64_t *r1 = X + (size_t)t1 * words, *r2 = X + (size_t)t2 * words;
         for (int k = 0; k < words; ++k)
             if (r1[k] != r2[k]) return false;
         return true;
     }
-    __device__ __forceinline__ void coeff(uint32_t t, uint64_t, double &re, double &im) const {
+    __device__ __forceinline__ void coeff(uint32_t t, int, double &re, double &im) const {
         re = C[2 * (size_t)t];
         im = C[2 * (size_t)t + 1];
     }
 };
 
-// dedup driver (dedup.cu), split at the point where the survivor count is known so that the caller
-// can allocate exact-size outputs. by_t: vals are a permutation of 0..T-1 and the output is written
-// in increasing-t (first occurrence) order; otherwise output is in sorted-key order.
+// Dedup driver (dedup.cu), split where the survivor count is known so the caller can allocate
+// exact-size outputs. `recs` holds T records (clobbered). by_t: the t fields are a permutation of
+// 0..T-1 and the output is written in increasing-t (first occurrence) order; otherwise the output
+// is in sorted-hash order.
 size_t dedup_ws_bytes(int64_t T);
-int dedup_product_plan(uint64_t *keys, uint32_t *vals, bool vals_iota, int64_t T, const ProductRows &rows, bool by_t,
-                       double thr, int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
-int dedup_product_emit(const uint32_t *vals, int64_t T, const ProductRows &rows, bool by_t, int64_t U, uint64_t *out_xz,
-                       double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);
-int dedup_plain_plan(uint64_t *keys, uint32_t *vals, int64_t T, const PlainRows &rows, double thr, int64_t *n_out,
+int dedup_product_plan(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, bool by_t, double thr,
+                       int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
+int dedup_product_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, bool by_t, int64_t U,
+                       uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);
+int dedup_plain_plan(uint64_t *recs, int64_t T, RecFmt fmt, const PlainRows &rows, double thr, int64_t *n_out,
                      int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
-int dedup_plain_emit(int64_t T, const PlainRows &rows, int64_t U, uint64_t *out_xz, double *out_c, void *ws,
-                     size_t ws_bytes, cudaStream_t st);
+int dedup_plain_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const PlainRows &rows, int64_t U, uint64_t *out_xz,
+                     double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace symb

@@ -351,21 +351,3 @@ extern "C" int sym_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t T, int32_t
     return radix_sort_pairs(keys, vals, ka, va, T, begin_bit, false, hist, (cudaStream_t)stream);
 }
 
-extern "C" size_t sym_partition_ws_bytes(int64_t T) {
-    if (T < 1) T = 1;
-    return arena_need(sort_hist_elems(T), 4) + 1024;
-}
-
-extern "C" int sym_partition_records(const uint64_t *keys, const uint32_t *vals, int64_t T, int32_t log2_parts,
-                                     uint64_t *out_keys, uint32_t *out_vals, int64_t *counts, void *ws, size_t ws_bytes,
-                                     void *stream) {
-    SYM_REQUIRE(T >= 0 && T < (int64_t)4000000000LL, "T out of range");
-    SYM_REQUIRE(log2_parts >= 0 && log2_parts <= 8, "log2_parts must be in [0,8]");
-    if (ws_bytes < sym_partition_ws_bytes(T)) {
-        set_error("workspace too small");
-        return SYM_E_WORKSPACE;
-    }
-    Arena ar(ws, ws_bytes);
-    uint32_t *hist = ar.take<uint32_t>(sort_hist_elems(T));
-    return radix_partition_top(keys, vals, out_keys, out_vals, T, log2_parts, counts, hist, (cudaStream_t)stream);
-}

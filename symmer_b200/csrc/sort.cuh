@@ -28,3 +28,15 @@ int radix_partition_top(const uint64_t *keys, const uint32_t *vals, uint64_t *ou
                         int64_t T, int bits, int64_t *counts, uint32_t *hist, cudaStream_t st);
 
 }  // namespace symb
+
+namespace symb {
+// Hot-path sort: stable LSD radix sort of single 64-bit records on bits [begin_bit, 64), shared-
+// memory staged so that every digit run of a tile leaves as one contiguous (coalesced) store.
+// `*result` receives whichever of keys/alt holds the sorted records (no copy-back).
+size_t record_hist_elems(int64_t T);
+int radix_sort_records(uint64_t *keys, uint64_t *alt, int64_t T, int begin_bit, uint32_t *hist, uint64_t **result,
+                       cudaStream_t st);
+// One stable partition pass on the top `bits` (<= 8) bits; counts: device int64[1 << bits].
+int radix_partition_records(const uint64_t *keys, uint64_t *out, int64_t T, int bits, int64_t *counts, uint32_t *hist,
+                            cudaStream_t st);
+}  // namespace symb

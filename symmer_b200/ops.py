@@ -305,38 +305,35 @@ def sort_pairs(keys, vals, begin_bit=0):
 
 
 def pair_records(a_xz, p_begin, p_end, b_xz):
-    """(keys int64[T], vals int32[T]) of the block A[p_begin:p_end) x B, T = (p_end-p_begin)*N."""
+    """int64[T] records of the block A[p_begin:p_end) x B, T = (p_end-p_begin)*N."""
     M, W = _rows(a_xz)
     N, _ = _rows(b_xz)
     T = (p_end - p_begin) * N
-    dev = a_xz.device
-    keys = torch.empty(T, dtype=torch.int64, device=dev)
-    vals = torch.empty(T, dtype=torch.int32, device=dev)
+    recs = torch.empty(T, dtype=torch.int64, device=a_xz.device)
     if T == 0:
-        return keys, vals
+        return recs
     L = lib()
     ws = workspace(L.sym_pair_records_ws_bytes(M, N, W))
-    _cabi.check(L.sym_pair_records(_p(a_xz), M, p_begin, p_end, _p(b_xz), N, W, _p(keys), _p(vals), _p(ws), ws.numel(),
+    _cabi.check(L.sym_pair_records(_p(a_xz), M, p_begin, p_end, _p(b_xz), N, W, _p(recs), _p(ws), ws.numel(),
                                    _stream()))
-    return keys, vals
+    return recs
 
 
-def partition_records(keys, vals, log2_parts):
-    T = keys.numel()
-    dev = keys.device
-    ok = torch.empty_like(keys)
-    ov = torch.empty_like(vals)
-    counts = torch.zeros(1 << log2_parts, dtype=torch.int64, device=dev)
+def partition_records(recs, log2_parts):
+    """Stable partition by owner (top log2_parts bits); returns (recs_by_owner, counts int64[parts])."""
+    T = recs.numel()
+    out = torch.empty_like(recs)
+    counts = torch.zeros(1 << log2_parts, dtype=torch.int64, device=recs.device)
     L = lib()
     ws = workspace(L.sym_partition_ws_bytes(T))
-    _cabi.check(L.sym_partition_records(_p(keys), _p(vals), T, int(log2_parts), _p(ok), _p(ov), _p(counts), _p(ws),
-                                        ws.numel(), _stream()))
-    return ok, ov, counts
+    _cabi.check(L.sym_partition_records(_p(recs), T, int(log2_parts), _p(out), _p(counts), _p(ws), ws.numel(),
+                                        _stream()))
+    return out, counts
 
 
-def dedup_records(keys, vals, a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
-    """Dedup + reduce + emit for records whose rows are A[p]^B[q]; keys/vals are clobbered."""
-    T = keys.numel()
+def dedup_records(recs, a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
+    """Dedup + reduce + emit for records whose rows are A[p]^B[q]; recs is clobbered."""
+    T = recs.numel()
     M, W = _rows(a_xz)
     N, _ = _rows(b_xz)
     dev = a_xz.device
@@ -346,15 +343,18 @@ def dedup_records(keys, vals, a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
     L = lib()
     ws = workspace(L.sym_dedup_records_ws_bytes(T, W))
     U = ctypes.c_int64(0)
-    _cabi.check(L.sym_dedup_records_count(_p(keys), _p(vals), T, _p(a_xz), _p(_coeff(a_c)), M, _p(b_xz),
-                                          _p(_coeff(b_c)), N, W, _thr(zero_threshold), None, ctypes.byref(U), _p(ws),
-                                          ws.numel(), _stream()))
+    _cabi.check(L.sym_dedup_records_count(_p(recs), T, _p(a_xz), _p(_coeff(a_c)), M, _p(b_xz), _p(_coeff(b_c)), N, W,
+                                          _thr(zero_threshold), None, ctypes.byref(U), _p(ws), ws.numel(), _stream()))
     U = U.value
     out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
     out_c = torch.empty(U, dtype=torch.complex128, device=dev)
-    _cabi.check(L.sym_dedup_records_emit(_p(vals), T, _p(a_xz), _p(a_c), M, _p(b_xz), _p(b_c), N, W, U, _p(out_xz),
+    _cabi.check(L.sym_dedup_records_emit(_p(recs), T, _p(a_xz), _p(a_c), M, _p(b_xz), _p(b_c), N, W, U, _p(out_xz),
                                          _p(out_c), _p(ws), ws.numel(), _stream()))
     return out_xz, out_c
+
+
+def set_tuning(which, value):
+    _cabi.check(lib().sym_set_tuning(int(which), int(value)))
 
 
 def launch_count():
