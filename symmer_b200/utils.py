@@ -1,0 +1,160 @@
+"""Array-level seams of the reference (symmer/operators/utils.py) on the B200 engine.
+
+Same names, argument meaning and return types (NumPy in, NumPy out) as the reference functions they
+replace, so `symmer_b200.patch.install()` can bind them into an unmodified symmer. Each call copies
+its inputs to the device, runs the CUDA kernels through the C ABI and copies the result back; code
+that wants to stay on the device uses `symmer_b200.base.PauliwordOp` / `symmer_b200.ops` instead.
+"""
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _to_dev_bool(a: np.ndarray) -> torch.Tensor:
+    a = np.array(a, dtype=bool, order='C', copy=True)      # private writable copy (torch wants writable)
+    return torch.from_numpy(a).to(ops.device(), non_blocking=True)
+
+
+def symplectic_cleanup(symp_matrix: np.ndarray, coeff_vec: np.ndarray,
+                       zero_threshold: float = None) -> Tuple[np.ndarray, np.ndarray]:
+    """utils.py:230-279. Unique rows (first-occurrence order), duplicate coefficients summed in input
+    order, then |c| > zero_threshold."""
+    symp_matrix = np.asarray(symp_matrix, dtype=bool)
+    coeff_vec = np.asarray(coeff_vec, dtype=complex)
+    T, two_n = symp_matrix.shape
+    n = two_n // 2
+    if T == 0:
+        return symp_matrix.copy(), coeff_vec.copy()
+    xz = ops.pack(_to_dev_bool(symp_matrix), n)
+    c = torch.from_numpy(np.ascontiguousarray(coeff_vec)).to(xz.device)
+    oxz, oc = ops.cleanup(xz, c, zero_threshold)
+    return ops.unpack(oxz, n).cpu().numpy(), oc.cpu().numpy()
+
+
+def matmul_GF2(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """utils.py:9-26: (A @ B) mod 2 for boolean A[M,K], B[K,N]. Runs the bit-packed symplectic
+    inner-product kernel with A's rows as X blocks and B's columns as Z blocks."""
+    A = np.asarray(A, dtype=bool)
+    B = np.asarray(B, dtype=bool)
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2
+    dev = ops.device()
+    if M == 0 or N == 0:
+        return np.zeros((M, N), dtype=bool)
+    a_rows = torch.zeros((M, 2 * K), dtype=torch.bool, device=dev)
+    a_rows[:, :K] = _to_dev_bool(A)
+    b_rows = torch.zeros((N, 2 * K), dtype=torch.bool, device=dev)
+    b_rows[:, K:] = _to_dev_bool(B.T)
+    commute = ops.commute(ops.pack(a_rows, K), ops.pack(b_rows, K))
+    return (~commute).cpu().numpy()
+
+
+def commutes_termwise(a_symp: np.ndarray, b_symp: np.ndarray) -> np.ndarray:
+    """base.py:938-971 on plain arrays: True where A[i] commutes with B[j]."""
+    a_symp = np.asarray(a_symp, dtype=bool)
+    b_symp = np.asarray(b_symp, dtype=bool)
+    n = a_symp.shape[1] // 2
+    assert b_symp.shape[1] == 2 * n, 'Pauliwords defined for different number of qubits'
+    a = ops.pack(_to_dev_bool(a_symp), n)
+    b = ops.pack(_to_dev_bool(b_symp), n)
+    return ops.commute(a, b).cpu().numpy()
+
+
+def _rref_device(matrix: np.ndarray):
+    matrix = np.asarray(matrix, dtype=bool)
+    if matrix.ndim != 2:
+        raise ValueError("matrix must be 2-dimensional")
+    R, C = matrix.shape
+    if R == 0 or C == 0:
+        return matrix.copy(), np.full(R, -1, dtype=np.int32)
+    bits = ops.pack_matrix(_to_dev_bool(matrix))
+    piv = ops.rref_packed(bits, C)
+    return ops.unpack_matrix(bits, C).cpu().numpy(), piv.cpu().numpy()
+
+
+def _rref_binary(matrix: np.ndarray) -> np.ndarray:
+    """utils.py:292-315: row reduction over GF(2), rows not reordered."""
+    return _rref_device(matrix)[0]
+
+
+def rref_binary(matrix: np.ndarray) -> np.ndarray:
+    """utils.py:317-335: rows ordered by pivot column, zero rows last."""
+    red, piv = _rref_device(matrix)
+    nz = np.flatnonzero(piv >= 0)
+    order = list(nz[np.argsort(piv[nz], kind="stable")])
+    seen = set(order)
+    order += [i for i in range(red.shape[0]) if i not in seen]
+    return red[order]
+
+
+def _cref_binary(matrix: np.ndarray) -> np.ndarray:
+    return _rref_binary(np.asarray(matrix).T).T            # utils.py:337-347
+
+
+def cref_binary(matrix: np.ndarray) -> np.ndarray:
+    return rref_binary(np.asarray(matrix).T).T             # utils.py:349-359
+
+
+def check_independent(operators) -> bool:
+    """utils.py:504-519 (accepts anything with n_terms, n_qubits, symp_matrix)."""
+    if operators.n_terms > 2 * operators.n_qubits:
+        return False
+    _, piv = _rref_device(operators.symp_matrix)
+    return bool(np.all(piv >= 0))
+
+
+def check_adjmat_noncontextual(adjmat) -> bool:
+    """utils.py:567-589 — host logic on the (small) set of distinct commutation characters."""
+    adjmat = np.asarray(adjmat, dtype=bool)
+    mask = np.where(~np.all(adjmat, axis=1))[0]
+    unique = np.unique(adjmat[mask, :][:, mask], axis=0)
+    return bool(np.all(np.count_nonzero(unique, axis=0) == 1))
+
+
+def random_symplectic_matrix(n_qubits, n_terms, diagonal=False, density=0.3):
+    """utils.py:281-290: same draws from the global NumPy RNG as the reference."""
+    if diagonal:
+        Z_block = np.random.choice([True, False], size=[n_terms, n_qubits], p=[density / 2, 1 - density / 2])
+        return np.hstack([np.zeros_like(Z_block), Z_block])
+    return np.random.choice([True, False], size=[n_terms, 2 * n_qubits], p=[density, 1 - density])
+
+
+_X_OF = {"I": False, "X": True, "Y": True, "Z": False}
+_Z_OF = {"I": False, "X": False, "Y": True, "Z": True}
+
+
+def string_to_symplectic(pauli_str, n_qubits):
+    """utils.py:140-163."""
+    assert (len(pauli_str) == n_qubits), 'Number of qubits is incompatible with pauli string'
+    assert (set(pauli_str).issubset({'I', 'X', 'Y', 'Z'})), 'pauliword must only contain X,Y,Z,I terms'
+    out = np.zeros(2 * n_qubits, dtype=int)
+    out[:n_qubits] = [_X_OF[ch] for ch in pauli_str]
+    out[n_qubits:] = [_Z_OF[ch] for ch in pauli_str]
+    return out
+
+
+def strings_to_symplectic(pauli_terms, n_qubits) -> np.ndarray:
+    """Vectorised ingest of many Pauli strings: one pass over a byte view instead
+    of a Python loop per character."""
+    if len(pauli_terms) == 0:
+        return np.zeros((0, 2 * n_qubits), dtype=bool)
+    for s in pauli_terms:
+        assert (len(s) == n_qubits), 'Number of qubits is incompatible with pauli string'
+    chars = np.frombuffer("".join(pauli_terms).encode("ascii"), dtype=np.uint8).reshape(len(pauli_terms), n_qubits)
+    is_x, is_y, is_z, is_i = chars == ord("X"), chars == ord("Y"), chars == ord("Z"), chars == ord("I")
+    assert bool(np.all(is_x | is_y | is_z | is_i)), 'pauliword must only contain X,Y,Z,I terms'
+    return np.hstack([is_x | is_y, is_z | is_y])
+
+
+_LUT = np.array(list("IXZY"))
+
+
+def symplectic_to_string(symp_vec) -> str:
+    """utils.py:80-107."""
+    symp_vec = np.asarray(symp_vec, dtype=bool)
+    n = symp_vec.size // 2
+    return "".join(_LUT[symp_vec[:n].astype(int) + 2 * symp_vec[n:].astype(int)])
