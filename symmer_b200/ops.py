@@ -12,6 +12,23 @@ import torch
 from . import _cabi
 
 _ws_cache = {}
+# bench.py sets this to a list to collect (start, end) CUDA events around every row-emission launch
+emit_events = None
+
+
+def _emit_begin():
+    if emit_events is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _emit_end(start):
+    if start is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        emit_events.append((start, e))
 
 
 def lib():
@@ -145,8 +162,10 @@ def mul_cleanup(a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
     U = U.value
     out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
     out_c = torch.empty(U, dtype=torch.complex128, device=dev)
+    ev = _emit_begin()
     _cabi.check(L.sym_mul_cleanup_emit(_p(a_xz), _p(a_c), M, _p(b_xz), _p(b_c), N, W, U, _p(out_xz), _p(out_c),
                                        _p(ws), ws.numel(), _stream()))
+    _emit_end(ev)
     return out_xz, out_c
 
 
@@ -348,8 +367,10 @@ def dedup_records(recs, a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
     U = U.value
     out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
     out_c = torch.empty(U, dtype=torch.complex128, device=dev)
+    ev = _emit_begin()
     _cabi.check(L.sym_dedup_records_emit(_p(recs), T, _p(a_xz), _p(a_c), M, _p(b_xz), _p(b_c), N, W, U, _p(out_xz),
                                          _p(out_c), _p(ws), ws.numel(), _stream()))
+    _emit_end(ev)
     return out_xz, out_c
 
 
