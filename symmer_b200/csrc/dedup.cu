@@ -18,7 +18,8 @@ constexpr uint8_t FLAG_HEAD = 0, FLAG_PREV = 1, FLAG_LINK = 2;
 
 template <class Rows>
 __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                    int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
+                                                    int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link,
+                                                    uint32_t *__restrict__ irr_list, uint32_t *__restrict__ irr_count) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     uint8_t f = FLAG_HEAD;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const 
                     if (fmt.same_hash(ri, rj) && rows.equal(ti, fmt.t(rj))) {
                         f = FLAG_LINK;
                         link[i] = (uint32_t)j;
+                        irr_list[atomicAdd(irr_count, 1u)] = (uint32_t)i;   // rare: hash collision in a bucket
                         break;
                     }
                 }
@@ -84,44 +86,56 @@ __device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_
 template <class Rows, bool BY_T>
 __global__ void __launch_bounds__(256) sum_irregular_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
                                                              const uint8_t *__restrict__ flag, const uint32_t *__restrict__ link,
-                                                             double2 *__restrict__ acc) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    if (flag[i] != FLAG_LINK) return;
-    double re, im;
-    const uint64_t r0 = sr[i];
-    rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
-    for (int64_t j = i + 1; j < T && flag[j] == FLAG_PREV; ++j) {
-        double r2, i2;
-        const uint64_t rj = sr[j];
-        rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
-        re += r2;
-        im += i2;
+                                                             const uint32_t *__restrict__ irr_list,
+                                                             const uint32_t *__restrict__ irr_count, double2 *__restrict__ acc) {
+    const uint32_t n = *irr_count;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int64_t i = irr_list[k];
+        double re, im;
+        const uint64_t r0 = sr[i];
+        rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+        for (int64_t j = i + 1; j < T && flag[j] == FLAG_PREV; ++j) {
+            double r2, i2;
+            const uint64_t rj = sr[j];
+            rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
+            re += r2;
+            im += i2;
+        }
+        const int64_t r = chain_root(flag, link, i);
+        double2 *dst = acc + (BY_T ? (int64_t)fmt.t(sr[r]) : r);
+        atomicAdd(&dst->x, re);
+        atomicAdd(&dst->y, im);
     }
-    const int64_t r = chain_root(flag, link, i);
-    double2 *dst = acc + (BY_T ? (int64_t)fmt.t(sr[r]) : r);
-    atomicAdd(&dst->x, re);
-    atomicAdd(&dst->y, im);
 }
 
 template <bool BY_T>
-__global__ void __launch_bounds__(256) keep_fix_kernel(RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+__global__ void __launch_bounds__(256) keep_fix_kernel(RecFmt fmt, const uint64_t *__restrict__ sr,
                                                         const uint8_t *__restrict__ flag, const uint32_t *__restrict__ link,
+                                                        const uint32_t *__restrict__ irr_list,
+                                                        const uint32_t *__restrict__ irr_count,
                                                         const double2 *__restrict__ acc, double thr, uint8_t *__restrict__ keep) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    if (flag[i] != FLAG_LINK) return;
-    const int64_t r = chain_root(flag, link, i);
-    const int64_t d = BY_T ? (int64_t)fmt.t(sr[r]) : r;
-    const double2 a = acc[d];
-    keep[d] = keep_test(a.x, a.y, thr);
+    const uint32_t n = *irr_count;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int64_t r = chain_root(flag, link, irr_list[k]);
+        const int64_t d = BY_T ? (int64_t)fmt.t(sr[r]) : r;
+        const double2 a = acc[d];
+        keep[d] = keep_test(a.x, a.y, thr);
+    }
 }
 
-__global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict__ keep, const uint32_t *__restrict__ slot,
-                                                       int64_t T, uint32_t *__restrict__ kept) {
+// Compaction (emit phase): kept_t[slot] = term index of the survivor, out_c[slot] = its coefficient,
+// so that the row-emission kernel has a two-step dependency chain (kept_t -> rows) only.
+template <bool BY_T>
+__global__ void __launch_bounds__(256) compact_kernel(RecFmt fmt, const uint64_t *__restrict__ sr, const uint8_t *__restrict__ keep,
+                                                       const uint32_t *__restrict__ slot, const double2 *__restrict__ acc,
+                                                       int64_t T, uint32_t *__restrict__ kept_t, double2 *__restrict__ out_c) {
     int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= T) return;
-    if (keep[d]) kept[slot[d]] = (uint32_t)d;
+    if (keep[d]) {
+        const uint32_t s = slot[d];
+        kept_t[s] = BY_T ? (uint32_t)d : fmt.t(sr[d]);
+        out_c[s] = acc[d];
+    }
 }
 
 __global__ void total_to_i64_kernel(const uint32_t *__restrict__ total, int64_t *__restrict__ n_out) { *n_out = (int64_t)*total; }
@@ -130,28 +144,25 @@ __global__ void total_to_i64_kernel(const uint32_t *__restrict__ total, int64_t 
 // 2*EMIT_UN independent 16-byte loads are in flight per thread (the kernel is latency-bound
 // otherwise). Stores are streaming (st.global.cs): the output is never re-read, and A/B must stay
 // L2-resident. LW: chunks per row = 1 << LW.
-int g_emit_variant = 4;  // tuning knob 1: 2 records per thread, plain stores (measured best on B200)
+int g_emit_variant = 1;  // tuning knob 1: 8 records per thread, plain stores (measured best on B200)
 
 __device__ __forceinline__ void store_streaming(uint4 *p, const uint4 &v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <class Rows, bool BY_T, int LW, int EMIT_UN, bool CS>
-__global__ void __launch_bounds__(256) emit_kernel(Rows rows, RecFmt fmt, const uint32_t *__restrict__ kept, uint32_t U,
-                                                    const uint64_t *__restrict__ sr, const double2 *__restrict__ acc,
-                                                    uint4 *__restrict__ out_xz, double2 *__restrict__ out_c) {
+template <class Rows, int LW, int EMIT_UN, bool CS>
+__global__ void __launch_bounds__(256) emit_kernel(Rows rows, const uint32_t *__restrict__ kept_t, uint32_t U,
+                                                    uint4 *__restrict__ out_xz) {
     constexpr uint32_t ROWS_PP = 256u >> LW;
     const uint32_t r_in = threadIdx.x >> LW;
     const uint32_t c = threadIdx.x & ((1u << LW) - 1u);
-    uint32_t rec[EMIT_UN], d[EMIT_UN], t[EMIT_UN];
+    uint32_t rec[EMIT_UN], t[EMIT_UN];
     uint4 v[EMIT_UN];
 #pragma unroll
     for (int u = 0; u < EMIT_UN; ++u) {
         rec[u] = (blockIdx.x * EMIT_UN + u) * ROWS_PP + r_in;
-        d[u] = rec[u] < U ? kept[rec[u]] : 0u;
+        t[u] = rec[u] < U ? kept_t[rec[u]] : 0u;
     }
-#pragma unroll
-    for (int u = 0; u < EMIT_UN; ++u) t[u] = BY_T ? d[u] : fmt.t(sr[d[u]]);
 #pragma unroll
     for (int u = 0; u < EMIT_UN; ++u) v[u] = rows.chunk(t[u], (int)c);
 #pragma unroll
@@ -159,25 +170,19 @@ __global__ void __launch_bounds__(256) emit_kernel(Rows rows, RecFmt fmt, const 
         if (rec[u] < U) {
             if (CS) store_streaming(out_xz + (((size_t)rec[u]) << LW) + c, v[u]);
             else out_xz[(((size_t)rec[u]) << LW) + c] = v[u];
-            if (c == 0) out_c[rec[u]] = acc[d[u]];
         }
     }
 }
 
 // generic chunk count (W not a power of two, or W > 16)
-template <class Rows, bool BY_T>
-__global__ void __launch_bounds__(256) emit_generic_kernel(Rows rows, RecFmt fmt, const uint32_t *__restrict__ kept, uint32_t U,
-                                                            uint32_t chunks, const uint64_t *__restrict__ sr,
-                                                            const double2 *__restrict__ acc, uint4 *__restrict__ out_xz,
-                                                            double2 *__restrict__ out_c) {
+template <class Rows>
+__global__ void __launch_bounds__(256) emit_generic_kernel(Rows rows, const uint32_t *__restrict__ kept_t, uint32_t U,
+                                                            uint32_t chunks, uint4 *__restrict__ out_xz) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t rec = (uint32_t)(g / chunks);
     const uint32_t c = (uint32_t)(g - (size_t)rec * chunks);
     if (rec >= U) return;
-    const uint32_t d = kept[rec];
-    const uint32_t t = BY_T ? d : fmt.t(sr[d]);
-    store_streaming(out_xz + g, rows.chunk(t, (int)c));
-    if (c == 0) out_c[rec] = acc[d];
+    out_xz[g] = rows.chunk(kept_t[rec], (int)c);
 }
 
 size_t dedup_ws_bytes(int64_t T) {
@@ -191,6 +196,7 @@ size_t dedup_ws_bytes(int64_t T) {
            + arena_need(n, 1)                        // keep
            + arena_need(n, 4)                        // slot
            + arena_need(n, 4)                        // kept
+           + arena_need(n, 4)                        // irregular list
            + arena_need(scan_scratch_elems(T), 4)    // scan scratch
            + arena_need(4, 4) + 4096;
 }
@@ -220,8 +226,9 @@ struct DedupLayout {
     uint8_t *keep;
     uint32_t *slot;
     uint32_t *kept;
+    uint32_t *irr_list;
     uint32_t *scratch;
-    uint32_t *total;
+    uint32_t *total;      // [0] survivor count, [1] irregular count
     bool ok;
 };
 
@@ -236,6 +243,7 @@ static DedupLayout dedup_layout(void *ws, size_t ws_bytes, int64_t T) {
     L.keep = ar.take<uint8_t>((size_t)T);
     L.slot = ar.take<uint32_t>((size_t)T);
     L.kept = ar.take<uint32_t>((size_t)T);
+    L.irr_list = ar.take<uint32_t>((size_t)T);
     L.scratch = ar.take<uint32_t>(scan_scratch_elems(T));
     L.total = ar.take<uint32_t>(4);
     L.ok = L.total != nullptr;
@@ -265,17 +273,18 @@ static int dedup_plan(uint64_t *recs, int64_t T, RecFmt fmt, const Rows &rows, d
     SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
 
     const unsigned nb = (unsigned)((T + 255) / 256);
-    link_kernel<Rows><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link);
+    const unsigned nb_rare = (unsigned)(nb < 296u ? nb : 296u);
+    SYM_CUDA_OK(cudaMemsetAsync(L.total, 0, 4 * sizeof(uint32_t), st));
+    link_kernel<Rows><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link, L.irr_list, L.total + 1);
     SYM_LAUNCH_OK();
     sum_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, fmt, sr, T, L.flag, thr, L.acc, L.keep);
     SYM_LAUNCH_OK();
-    sum_irregular_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, fmt, sr, T, L.flag, L.link, L.acc);
+    sum_irregular_kernel<Rows, BY_T><<<nb_rare, 256, 0, st>>>(rows, fmt, sr, T, L.flag, L.link, L.irr_list, L.total + 1,
+                                                              L.acc);
     SYM_LAUNCH_OK();
-    keep_fix_kernel<BY_T><<<nb, 256, 0, st>>>(fmt, sr, T, L.flag, L.link, L.acc, thr, L.keep);
+    keep_fix_kernel<BY_T><<<nb_rare, 256, 0, st>>>(fmt, sr, L.flag, L.link, L.irr_list, L.total + 1, L.acc, thr, L.keep);
     SYM_LAUNCH_OK();
     SYM_TRY(scan_exclusive_u8(L.keep, L.slot, T, L.total, L.scratch, st));
-    compact_kernel<<<nb, 256, 0, st>>>(L.keep, L.slot, T, L.kept);
-    SYM_LAUNCH_OK();
     if (n_out) {
         total_to_i64_kernel<<<1, 1, 0, st>>>(L.total, n_out);
         SYM_LAUNCH_OK();
@@ -302,11 +311,13 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
     const uint32_t chunks = (uint32_t)(rows.words / 2);
     uint4 *o = reinterpret_cast<uint4 *>(out_xz);
     double2 *oc = reinterpret_cast<double2 *>(out_c);
-#define EMIT_LAUNCH(LW, UN, CS)                                                                                    \
-    {                                                                                                              \
-        const uint32_t rows_per_block = (256u >> LW) * UN;                                                         \
-        const unsigned nb = (unsigned)((U + rows_per_block - 1) / rows_per_block);                                 \
-        emit_kernel<Rows, BY_T, LW, UN, CS><<<nb, 256, 0, st>>>(rows, fmt, L.kept, (uint32_t)U, sr, L.acc, o, oc); \
+    compact_kernel<BY_T><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(fmt, sr, L.keep, L.slot, L.acc, T, L.kept, oc);
+    SYM_LAUNCH_OK();
+#define EMIT_LAUNCH(LW, UN, CS)                                                                   \
+    {                                                                                             \
+        const uint32_t rows_per_block = (256u >> LW) * UN;                                        \
+        const unsigned nbe = (unsigned)((U + rows_per_block - 1) / rows_per_block);               \
+        emit_kernel<Rows, LW, UN, CS><<<nbe, 256, 0, st>>>(rows, L.kept, (uint32_t)U, o);         \
     }
 #define EMIT_CASE(LW)                                       \
     switch (g_emit_variant) {                               \
@@ -325,8 +336,7 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
         case 16: EMIT_CASE(4); break;
         default: {
             const size_t threads = (size_t)U * chunks;
-            emit_generic_kernel<Rows, BY_T><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-                rows, fmt, L.kept, (uint32_t)U, chunks, sr, L.acc, o, oc);
+            emit_generic_kernel<Rows><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rows, L.kept, (uint32_t)U, chunks, o);
         } break;
     }
 #undef EMIT_CASE
