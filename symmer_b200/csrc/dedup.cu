@@ -5,10 +5,9 @@
 // Pipeline (all on one stream):
 //   1. stable LSD radix sort of the records on their top hash bits -> equal rows become neighbours,
 //      ordered by t inside a run
-//   2. link: every sorted position decides head / same-as-predecessor / irregular (exact row compare)
-//   3. sum: each head adds the coefficients of its chain in input (t) order and applies |c| > thr
-//   4. irregular chains (hash collisions inside a sort bucket; rare) are folded in with atomics
-//   5. exclusive scan of keep flags -> output slots ; compact ; emit rows with 16-byte stores
+//   2. link: every sorted position finds its nearest earlier twin inside its sort bucket (exact row compare)
+//   3. sum: each head adds the coefficients of its group in input (t) order and applies |c| > thr
+//   4. exclusive scan of keep flags -> output slots ; compact ; emit rows with 16-byte stores
 #include "rows.cuh"
 #include "sort.cuh"
 
@@ -16,31 +15,33 @@ namespace symb {
 
 constexpr uint8_t FLAG_HEAD = 0, FLAG_PREV = 1, FLAG_LINK = 2;
 
+// A "bucket" is a maximal run of sorted records sharing the sorted hash prefix (bits >= sort_shift).
+// The sort leaves each bucket in input (t) order. On average a bucket holds <= 8 records
+// (sort_begin_bit), so the scans below are a handful of cached 8-byte reads per record.
+//
+// link: every sorted position finds the nearest EARLIER record of its bucket with the same row
+// (full hash match, then exact word-by-word compare): none -> HEAD, the immediate predecessor ->
+// PREV, further back -> LINK (position stored in link[]).
 template <class Rows>
 __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                    int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link,
-                                                    uint32_t *__restrict__ irr_list, uint32_t *__restrict__ irr_count) {
+                                                    int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     uint8_t f = FLAG_HEAD;
     if (i > 0) {
-        const uint64_t ri = sr[i], rp = sr[i - 1];
-        if (((ri ^ rp) >> sort_shift) == 0) {
-            const uint32_t ti = fmt.t(ri);
-            if (fmt.same_hash(ri, rp) && rows.equal(ti, fmt.t(rp))) {
-                f = FLAG_PREV;
-            } else {
-                // irregular: a different row shares this sort bucket; look further back for a twin
-                for (int64_t j = i - 2; j >= 0; --j) {
-                    const uint64_t rj = sr[j];
-                    if (((ri ^ rj) >> sort_shift) != 0) break;
-                    if (fmt.same_hash(ri, rj) && rows.equal(ti, fmt.t(rj))) {
-                        f = FLAG_LINK;
-                        link[i] = (uint32_t)j;
-                        irr_list[atomicAdd(irr_count, 1u)] = (uint32_t)i;   // rare: hash collision in a bucket
-                        break;
-                    }
+        const uint64_t ri = sr[i];
+        const uint32_t ti = fmt.t(ri);
+        for (int64_t j = i - 1; j >= 0; --j) {
+            const uint64_t rj = sr[j];
+            if (((ri ^ rj) >> sort_shift) != 0) break;   // left the bucket
+            if (fmt.same_hash(ri, rj) && rows.equal(ti, fmt.t(rj))) {
+                if (j == i - 1) {
+                    f = FLAG_PREV;
+                } else {
+                    f = FLAG_LINK;
+                    link[i] = (uint32_t)j;
                 }
+                break;
             }
         }
     }
@@ -51,10 +52,17 @@ __device__ __forceinline__ uint8_t keep_test(double re, double im, double thr) {
     return (thr < 0.0) ? 1 : (hypot(re, im) > thr ? 1 : 0);
 }
 
-// heads: sequential sum over the chain of FLAG_PREV successors (input order, like np.add.at)
+__device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_t *link, int64_t i) {
+    while (flag[i] != FLAG_HEAD) i = (flag[i] == FLAG_PREV) ? i - 1 : (int64_t)link[i];
+    return i;
+}
+
+// sum: each HEAD walks forward through its bucket and adds the coefficients of the records whose
+// chain leads back to it, in input (t) order like np.add.at — deterministic, no atomics.
 template <class Rows, bool BY_T>
 __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                   const uint8_t *__restrict__ flag, double thr, double2 *__restrict__ acc,
+                                                   int sort_shift, const uint8_t *__restrict__ flag,
+                                                   const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
                                                    uint8_t *__restrict__ keep) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
@@ -66,61 +74,25 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
     }
     double re, im;
     rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
-    for (int64_t j = i + 1; j < T && flag[j] == FLAG_PREV; ++j) {
-        double r2, i2;
+    bool prev_mine = true;   // is record j-1 a member of this head's group?
+    for (int64_t j = i + 1; j < T; ++j) {
         const uint64_t rj = sr[j];
-        rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
-        re += r2;
-        im += i2;
-    }
-    acc[d] = make_double2(re, im);
-    keep[d] = keep_test(re, im, thr);
-}
-
-__device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_t *link, int64_t i) {
-    int64_t r = link[i];
-    while (flag[r] != FLAG_HEAD) r = (flag[r] == FLAG_PREV) ? r - 1 : (int64_t)link[r];
-    return r;
-}
-
-template <class Rows, bool BY_T>
-__global__ void __launch_bounds__(256) sum_irregular_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                             const uint8_t *__restrict__ flag, const uint32_t *__restrict__ link,
-                                                             const uint32_t *__restrict__ irr_list,
-                                                             const uint32_t *__restrict__ irr_count, double2 *__restrict__ acc) {
-    const uint32_t n = *irr_count;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int64_t i = irr_list[k];
-        double re, im;
-        const uint64_t r0 = sr[i];
-        rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
-        for (int64_t j = i + 1; j < T && flag[j] == FLAG_PREV; ++j) {
+        if (((r0 ^ rj) >> sort_shift) != 0) break;       // end of the bucket
+        const uint8_t fj = flag[j];
+        bool mine;
+        if (fj == FLAG_PREV) mine = prev_mine;
+        else if (fj == FLAG_LINK) mine = fmt.same_hash(r0, rj) && chain_root(flag, link, (int64_t)link[j]) == i;
+        else mine = false;
+        if (mine) {
             double r2, i2;
-            const uint64_t rj = sr[j];
             rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
             re += r2;
             im += i2;
         }
-        const int64_t r = chain_root(flag, link, i);
-        double2 *dst = acc + (BY_T ? (int64_t)fmt.t(sr[r]) : r);
-        atomicAdd(&dst->x, re);
-        atomicAdd(&dst->y, im);
+        prev_mine = mine;
     }
-}
-
-template <bool BY_T>
-__global__ void __launch_bounds__(256) keep_fix_kernel(RecFmt fmt, const uint64_t *__restrict__ sr,
-                                                        const uint8_t *__restrict__ flag, const uint32_t *__restrict__ link,
-                                                        const uint32_t *__restrict__ irr_list,
-                                                        const uint32_t *__restrict__ irr_count,
-                                                        const double2 *__restrict__ acc, double thr, uint8_t *__restrict__ keep) {
-    const uint32_t n = *irr_count;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int64_t r = chain_root(flag, link, irr_list[k]);
-        const int64_t d = BY_T ? (int64_t)fmt.t(sr[r]) : r;
-        const double2 a = acc[d];
-        keep[d] = keep_test(a.x, a.y, thr);
-    }
+    acc[d] = make_double2(re, im);
+    keep[d] = keep_test(re, im, thr);
 }
 
 // Compaction (emit phase): kept_t[slot] = term index of the survivor, out_c[slot] = its coefficient,
@@ -196,17 +168,18 @@ size_t dedup_ws_bytes(int64_t T) {
            + arena_need(n, 1)                        // keep
            + arena_need(n, 4)                        // slot
            + arena_need(n, 4)                        // kept
-           + arena_need(n, 4)                        // irregular list
            + arena_need(scan_scratch_elems(T), 4)    // scan scratch
            + arena_need(4, 4) + 4096;
 }
 
-// Sort on at least tb + 5 hash bits (rounded up to whole 8-bit passes): the expected number of
-// distinct rows sharing a sort bucket is then <= T / 32, and those are resolved exactly by the
-// irregular path.
+// Sort on log2(T) + g_sort_extra_bits hash bits, rounded up to whole 8-bit passes. A sort bucket then
+// holds T / 2^bits records on average, which link/sum resolve exactly with in-bucket scans: fewer
+// bits save radix passes (24 B of HBM traffic per record each) but lengthen those scans.
+int g_sort_extra_bits = 5;  // tuning knob 3
 static int sort_begin_bit(int64_t T, RecFmt fmt) {
     int lg = t_bits_for(T);
-    int want = ((lg + 5 + 7) / 8) * 8;
+    int want = ((lg + g_sort_extra_bits + 7) / 8) * 8;
+    if (want < 8) want = 8;
     int begin = 64 - want;
     if (begin < fmt.tb + 2) begin = fmt.tb + 2;
     return begin;
@@ -226,9 +199,8 @@ struct DedupLayout {
     uint8_t *keep;
     uint32_t *slot;
     uint32_t *kept;
-    uint32_t *irr_list;
     uint32_t *scratch;
-    uint32_t *total;      // [0] survivor count, [1] irregular count
+    uint32_t *total;
     bool ok;
 };
 
@@ -243,7 +215,6 @@ static DedupLayout dedup_layout(void *ws, size_t ws_bytes, int64_t T) {
     L.keep = ar.take<uint8_t>((size_t)T);
     L.slot = ar.take<uint32_t>((size_t)T);
     L.kept = ar.take<uint32_t>((size_t)T);
-    L.irr_list = ar.take<uint32_t>((size_t)T);
     L.scratch = ar.take<uint32_t>(scan_scratch_elems(T));
     L.total = ar.take<uint32_t>(4);
     L.ok = L.total != nullptr;
@@ -273,16 +244,9 @@ static int dedup_plan(uint64_t *recs, int64_t T, RecFmt fmt, const Rows &rows, d
     SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
 
     const unsigned nb = (unsigned)((T + 255) / 256);
-    const unsigned nb_rare = (unsigned)(nb < 296u ? nb : 296u);
-    SYM_CUDA_OK(cudaMemsetAsync(L.total, 0, 4 * sizeof(uint32_t), st));
-    link_kernel<Rows><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link, L.irr_list, L.total + 1);
+    link_kernel<Rows><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link);
     SYM_LAUNCH_OK();
-    sum_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, fmt, sr, T, L.flag, thr, L.acc, L.keep);
-    SYM_LAUNCH_OK();
-    sum_irregular_kernel<Rows, BY_T><<<nb_rare, 256, 0, st>>>(rows, fmt, sr, T, L.flag, L.link, L.irr_list, L.total + 1,
-                                                              L.acc);
-    SYM_LAUNCH_OK();
-    keep_fix_kernel<BY_T><<<nb_rare, 256, 0, st>>>(fmt, sr, L.flag, L.link, L.irr_list, L.total + 1, L.acc, thr, L.keep);
+    sum_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link, thr, L.acc, L.keep);
     SYM_LAUNCH_OK();
     SYM_TRY(scan_exclusive_u8(L.keep, L.slot, T, L.total, L.scratch, st));
     if (n_out) {
