@@ -125,15 +125,16 @@ int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_t W, const 
 int sym_term_masks(const uint64_t *xz, const double *c, int64_t M, int32_t n_qubits, int64_t *x_masks,
                    int64_t *z_masks, double *c_phased, void *stream);
 /*   y[r - row_begin] = sum_t c'_t (-1)^{popcount(r & z_t)} psi[r ^ x_t]   for r in [row_begin, row_end)
- * psi: complex128[2^n]; y: complex128[row_end-row_begin]; n_qubits <= 40. */
+ * psi: complex128[2^n]; y: complex128[row_end-row_begin]; n_qubits <= 40. real_coeffs != 0 promises
+ * that every c' has zero imaginary part (halves the FP64 work; molecular Hamiltonians). */
 int sym_apply(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
               int32_t n_qubits, const double *psi, double *y, int64_t row_begin, int64_t row_end,
-              void *stream);
+              int32_t real_coeffs, void *stream);
 /* partial[0..1] += sum_{r in [row_begin,row_end)} conj(psi[r]) * (H psi)[r]  (device double[2],
  * zero it first). The 2^n basis shards over ranks by row range; all-reduce the two doubles. */
 int sym_expval(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
                int32_t n_qubits, const double *psi, double *partial, int64_t row_begin, int64_t row_end,
-               void *stream);
+               int32_t real_coeffs, void *stream);
 /* CSR emitter for small n (parity with to_sparse_matrix): G distinct x masks (x_groups, ascending),
  * terms sorted by x with group g spanning [group_start[g], group_start[g+1]). Every row gets exactly
  * G entries sorted by column (explicit zeros kept). data: double[2^n*G][2], indices: int64[2^n*G],

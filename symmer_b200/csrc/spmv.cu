@@ -96,6 +96,113 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(const int64_t *__r
     }
 }
 
+// Four basis rows per thread (r0 + k*256, k = 0..3, block base aligned to 1024 so the rows of a thread
+// differ only in bits 8 and 9): one AND + POPC per term gives the sign of row 0 and the other three
+// follow from bits 8/9 of z; the sign is applied by XOR on the sign bit. Per (row, term) this leaves
+// ~2 LOP + 2 DADD (1 DADD when all coefficients are real): the FP64 add rate is the bound.
+template <bool EXPVAL, bool REAL>
+__global__ void __launch_bounds__(APPLY_THREADS) apply4_kernel(const int64_t *__restrict__ xm, const int64_t *__restrict__ zm,
+                                                                const double2 *__restrict__ cp, int64_t M,
+                                                                const double2 *__restrict__ psi, double2 *__restrict__ y,
+                                                                int64_t row_begin, double *__restrict__ partial) {
+    __shared__ TermTile tile;
+    __shared__ double red[2][APPLY_THREADS / 32];
+    const int64_t r0 = row_begin + (int64_t)blockIdx.x * (4 * APPLY_THREADS) + threadIdx.x;
+    double ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
+    double wr[4] = {0, 0, 0, 0}, wi[4] = {0, 0, 0, 0};
+    int64_t xcur = -1;
+    for (int64_t base = 0; base < M; base += APPLY_TERMS) {
+        const int nt = (int)min((int64_t)APPLY_TERMS, M - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt; i += APPLY_THREADS) {
+            tile.x[i] = xm[base + i];
+            tile.z[i] = zm[base + i];
+            tile.c[i] = cp[base + i];
+        }
+        __syncthreads();
+        for (int i = 0; i < nt; ++i) {
+            const int64_t x = tile.x[i];
+            if (x != xcur) {  // uniform across the CTA
+                if (xcur >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double2 p = psi[(r0 + k * APPLY_THREADS) ^ xcur];
+                        if (REAL) {
+                            ar[k] += wr[k] * p.x;
+                            ai[k] += wr[k] * p.y;
+                        } else {
+                            ar[k] += wr[k] * p.x - wi[k] * p.y;
+                            ai[k] += wr[k] * p.y + wi[k] * p.x;
+                        }
+                        wr[k] = 0.0;
+                        wi[k] = 0.0;
+                    }
+                }
+                xcur = x;
+            }
+            const uint64_t z = (uint64_t)tile.z[i];
+            const double2 c = tile.c[i];
+            const uint32_t p0 = __popcll((uint64_t)r0 & z) & 1u;
+            const uint32_t z8 = (uint32_t)(z >> 8) & 1u, z9 = (uint32_t)(z >> 9) & 1u;
+            const uint32_t par[4] = {p0, p0 ^ z8, p0 ^ z9, p0 ^ z8 ^ z9};
+            const int cxh = __double2hiint(c.x), cxl = __double2loint(c.x);
+            const int cyh = __double2hiint(c.y), cyl = __double2loint(c.y);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int flip = (int)(par[k] << 31);
+                wr[k] += __hiloint2double(cxh ^ flip, cxl);
+                if (!REAL) wi[k] += __hiloint2double(cyh ^ flip, cyl);
+            }
+        }
+    }
+    if (xcur >= 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double2 p = psi[(r0 + k * APPLY_THREADS) ^ xcur];
+            if (REAL) {
+                ar[k] += wr[k] * p.x;
+                ai[k] += wr[k] * p.y;
+            } else {
+                ar[k] += wr[k] * p.x - wi[k] * p.y;
+                ai[k] += wr[k] * p.y + wi[k] * p.x;
+            }
+        }
+    }
+    if (!EXPVAL) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[r0 + k * APPLY_THREADS - row_begin] = make_double2(ar[k], ai[k]);
+        return;
+    }
+    double er = 0.0, ei = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double2 p = psi[r0 + k * APPLY_THREADS];
+        er += p.x * ar[k] + p.y * ai[k];
+        ei += p.x * ai[k] - p.y * ar[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        er += __shfl_xor_sync(0xffffffffu, er, o);
+        ei += __shfl_xor_sync(0xffffffffu, ei, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[0][wid] = er;
+        red[1][wid] = ei;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int w = 0; w < APPLY_THREADS / 32; ++w) {
+            sr += red[0][w];
+            si += red[1][w];
+        }
+        atomicAdd(&partial[0], sr);
+        atomicAdd(&partial[1], si);
+    }
+}
+
 // CSR emitter for small n: thread per (row, group); value = sum over the group's terms, position =
 // rank of the column among the row's columns (counting), so rows come out sorted by column.
 __global__ void __launch_bounds__(256) csr_kernel(const int64_t *__restrict__ zm, const double2 *__restrict__ cp, int64_t M,
@@ -129,36 +236,47 @@ using namespace symb;
 
 static int apply_common(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M, int32_t n,
                         const double *psi, double *y, double *partial, int64_t row_begin, int64_t row_end, bool expval,
-                        cudaStream_t st) {
+                        bool real_coeffs, cudaStream_t st) {
     SYM_REQUIRE(n >= 1 && n <= 40, "n_qubits out of range for the dense-state path");
     SYM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= ((int64_t)1 << n), "bad row range");
     const int64_t rows = row_end - row_begin;
     if (rows == 0) return SYM_OK;
+    const double2 *c2 = reinterpret_cast<const double2 *>(c_phased);
+    const double2 *p2 = reinterpret_cast<const double2 *>(psi);
+    double2 *y2 = reinterpret_cast<double2 *>(y);
+    if (rows % (4 * APPLY_THREADS) == 0 && row_begin % (4 * APPLY_THREADS) == 0) {
+        const unsigned nb4 = (unsigned)(rows / (4 * APPLY_THREADS));
+        if (expval) {
+            if (real_coeffs) apply4_kernel<true, true><<<nb4, APPLY_THREADS, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
+            else apply4_kernel<true, false><<<nb4, APPLY_THREADS, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
+        } else {
+            if (real_coeffs) apply4_kernel<false, true><<<nb4, APPLY_THREADS, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
+            else apply4_kernel<false, false><<<nb4, APPLY_THREADS, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
+        }
+        SYM_LAUNCH_OK();
+        return SYM_OK;
+    }
     const unsigned nb = (unsigned)((rows + APPLY_THREADS - 1) / APPLY_THREADS);
     if (expval)
-        apply_kernel<true><<<nb, APPLY_THREADS, 0, st>>>(x_masks, z_masks, reinterpret_cast<const double2 *>(c_phased), M,
-                                                         reinterpret_cast<const double2 *>(psi), nullptr, row_begin,
-                                                         row_end, partial);
+        apply_kernel<true><<<nb, APPLY_THREADS, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, row_end, partial);
     else
-        apply_kernel<false><<<nb, APPLY_THREADS, 0, st>>>(x_masks, z_masks, reinterpret_cast<const double2 *>(c_phased), M,
-                                                          reinterpret_cast<const double2 *>(psi),
-                                                          reinterpret_cast<double2 *>(y), row_begin, row_end, nullptr);
+        apply_kernel<false><<<nb, APPLY_THREADS, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, row_end, nullptr);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }
 
 extern "C" int sym_apply(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
                          int32_t n_qubits, const double *psi, double *y, int64_t row_begin, int64_t row_end,
-                         void *stream) {
+                         int32_t real_coeffs, void *stream) {
     return apply_common(x_masks, z_masks, c_phased, M, n_qubits, psi, y, nullptr, row_begin, row_end, false,
-                        (cudaStream_t)stream);
+                        real_coeffs != 0, (cudaStream_t)stream);
 }
 
 extern "C" int sym_expval(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
                           int32_t n_qubits, const double *psi, double *partial, int64_t row_begin, int64_t row_end,
-                          void *stream) {
+                          int32_t real_coeffs, void *stream) {
     return apply_common(x_masks, z_masks, c_phased, M, n_qubits, psi, nullptr, partial, row_begin, row_end, true,
-                        (cudaStream_t)stream);
+                        real_coeffs != 0, (cudaStream_t)stream);
 }
 
 extern "C" int sym_to_csr(const int64_t *z_masks, const double *c_phased, int64_t M, int32_t n_qubits,

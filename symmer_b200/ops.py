@@ -236,7 +236,16 @@ def term_masks_sorted(xz, c, n_qubits):
     L = lib()
     _cabi.check(L.sym_term_masks(_p(xz), _p(_coeff(c)), M, int(n_qubits), _p(xm), _p(zm), _p(cp), _stream()))
     order = sort_pairs(xm.clone(), torch.arange(M, dtype=torch.int32, device=dev), begin_bit=0)[1].to(torch.int64)
-    return xm[order].contiguous(), zm[order].contiguous(), cp[order].contiguous()
+    cp = cp[order].contiguous()
+    _real_flags[cp.data_ptr()] = bool((cp.imag == 0).all().item())     # one sync, once per operator
+    return xm[order].contiguous(), zm[order].contiguous(), cp
+
+
+_real_flags = {}
+
+
+def _is_real(cp):
+    return 1 if _real_flags.get(cp.data_ptr(), False) else 0
 
 
 def apply_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
@@ -246,7 +255,7 @@ def apply_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
     assert psi.dtype == torch.complex128 and psi.numel() == side
     y = torch.empty(row_end - row_begin, dtype=torch.complex128, device=psi.device)
     _cabi.check(lib().sym_apply(_p(xm), _p(zm), _p(cp), xm.numel(), int(n_qubits), _p(psi), _p(y), row_begin, row_end,
-                                _stream()))
+                                _is_real(cp), _stream()))
     return y
 
 
@@ -258,7 +267,7 @@ def expval_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
     assert psi.dtype == torch.complex128 and psi.numel() == side
     partial = torch.zeros(2, dtype=torch.float64, device=psi.device)
     _cabi.check(lib().sym_expval(_p(xm), _p(zm), _p(cp), xm.numel(), int(n_qubits), _p(psi), _p(partial), row_begin,
-                                 row_end, _stream()))
+                                 row_end, _is_real(cp), _stream()))
     return torch.view_as_complex(partial)
 
 
