@@ -97,6 +97,12 @@ int sym_cleanup(const uint64_t *xz, const double *c, int64_t T, int32_t W, doubl
  * out[i*N + j] = 1 if A[i] commutes with B[j] else 0 (uint8, the reference's bool[M,N]). */
 int sym_commute(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
                 uint8_t *out, void *stream);
+/* Tensor-core variant of sym_commute (same output): int8 tcgen05.mma on bits unpacked on the fly in
+ * shared memory, int32 accumulators in TMEM, parity epilogue — the reference's own "integer GEMM,
+ * then mod 2" formulation (utils.py:63-78). Wins over the bit-packed kernel for wide operators. */
+size_t sym_commute_mma_ws_bytes(int64_t M, int64_t N, int32_t W);
+int sym_commute_mma(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
+                    uint8_t *out, void *ws, size_t ws_bytes, void *stream);
 /* Same symplectic inner product, bit-packed output: out_bits[i][j/32] bit j%32 (row stride
  * ceil(N/32) uint32). Used when the matrix is consumed on the device (masks, graph colouring). */
 int sym_commute_bits(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,

@@ -187,13 +187,40 @@ def cleanup(xz, c, zero_threshold=1e-15):
 
 
 # ----------------------------------------------------------------------------------------- commute
+# Measured on B200 (scripts/probe_commute_cross.py, profiles/r01_commute.md): the tcgen05 int8 kernel
+# beats the bit-packed one at every width once the output is large enough to amortise its two
+# operand transposes; the bit-packed kernel keeps the small (launch-bound) cases.
+MMA_MIN_PAIRS = 1 << 22
+
+
 def commute(a_xz, b_xz):
-    """bool[M, N], True where A[i] commutes with B[j]."""
+    """bool[M, N], True where A[i] commutes with B[j] (dispatches to the kernel ncu shows winning)."""
+    M, W = _rows(a_xz)
+    N, _ = _rows(b_xz)
+    if M * N >= MMA_MIN_PAIRS or W > 16:
+        return commute_mma(a_xz, b_xz)
+    return commute_packed(a_xz, b_xz)
+
+
+def commute_packed(a_xz, b_xz):
+    """Bit-packed AND/XOR + popcount-parity kernel."""
     M, W = _rows(a_xz)
     N, W2 = _rows(b_xz)
     assert W == W2
     out = torch.empty((M, N), dtype=torch.uint8, device=a_xz.device)
     _cabi.check(lib().sym_commute(_p(a_xz), M, _p(b_xz), N, W, _p(out), _stream()))
+    return out.view(torch.bool)
+
+
+def commute_mma(a_xz, b_xz):
+    """Tensor-core (tcgen05 int8) variant of `commute`; identical output."""
+    M, W = _rows(a_xz)
+    N, W2 = _rows(b_xz)
+    assert W == W2
+    out = torch.empty((M, N), dtype=torch.uint8, device=a_xz.device)
+    L = lib()
+    ws = workspace(L.sym_commute_mma_ws_bytes(M, N, W))
+    _cabi.check(L.sym_commute_mma(_p(a_xz), M, _p(b_xz), N, W, _p(out), _p(ws), ws.numel(), _stream()))
     return out.view(torch.bool)
 
 

@@ -168,6 +168,7 @@ def test_commute_golden(ops, golden):
         a = ops.pack(torch.from_numpy(g["a_symp"]), n)
         b = ops.pack(torch.from_numpy(g["b_symp"]), n)
         assert np.array_equal(ops.commute(a, b).cpu().numpy(), g["out"]), nm
+        assert np.array_equal(ops.commute_mma(a, b).cpu().numpy(), g["out"]), nm
         bits = ops.commute_bits(a, b).cpu().numpy().view(np.uint32)
         N = g["b_symp"].shape[0]
         unp = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(bits.shape[0], -1)[:, :N].astype(bool)
@@ -178,13 +179,27 @@ def test_commute_golden(ops, golden):
         assert np.array_equal(ops.commute(a, a).cpu().numpy(), g["adj"]), nm
 
 
-@pytest.mark.parametrize("n,m1,m2", [(36, 700, 513), (1000, 300, 257), (1500, 40, 33)])
-def test_commute_random(ops, n, m1, m2):
+@pytest.mark.parametrize("n,m1,m2", [(1, 5, 7), (36, 700, 513), (64, 128, 256), (100, 130, 300), (1000, 300, 257),
+                                     (1100, 70, 50), (1500, 40, 33), (2100, 129, 257)])
+def test_commute_random_both_kernels(ops, n, m1, m2):
+    """Bit-packed kernel and tcgen05 int8 tensor-core kernel against the oracle, bit-exact."""
     a_s, _ = po.random_operator(n, m1, seed=n)
     b_s, _ = po.random_operator(n, m2, seed=n + 1)
     a = ops.pack(torch.from_numpy(a_s), n)
     b = ops.pack(torch.from_numpy(b_s), n)
-    assert np.array_equal(ops.commute(a, b).cpu().numpy(), po.commutes_termwise(a_s, b_s))
+    ref = po.commutes_termwise(a_s, b_s)
+    assert np.array_equal(ops.commute_packed(a, b).cpu().numpy(), ref)
+    assert np.array_equal(ops.commute_mma(a, b).cpu().numpy(), ref)
+    assert np.array_equal(ops.commute(a, b).cpu().numpy(), ref)
+
+
+def test_commute_large_dispatches_to_tensor_cores(ops):
+    n, M = 200, 3000                                   # 9e6 pairs > MMA_MIN_PAIRS
+    a_s, _ = po.random_operator(n, M, seed=9)
+    a = ops.pack(torch.from_numpy(a_s), n)
+    adj = ops.commute(a, a).cpu().numpy()
+    assert np.array_equal(adj, po.commutes_termwise(a_s, a_s))
+    assert np.array_equal(adj, adj.T) and adj.diagonal().all()
 
 
 def test_gf2_golden(ops, golden):
