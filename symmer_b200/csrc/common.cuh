@@ -131,6 +131,30 @@ __device__ __forceinline__ uint64_t warp_sketch_row(const uint64_t *__restrict__
     return h;
 }
 
+// Same sketch for rows of at most 32 words with an even word count per block (W even, W <= 16),
+// computed by a group of 8 lanes with 16-byte loads: 4 rows per warp, 4x the bytes in flight of the
+// warp-per-row form. g = lane within the group. Every lane of the group returns the sketch.
+__device__ __forceinline__ uint64_t group8_sketch_row(const uint64_t *__restrict__ row, int words, int g) {
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
+    const int chunks = words >> 1;
+    uint64_t h = 0;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+        const int c = g + 8 * rep;
+        if (c < chunks) {
+            const uint4 v = r4[c];
+            const uint64_t w0 = ((uint64_t)v.y << 32) | v.x, w1 = ((uint64_t)v.w << 32) | v.z;
+            h ^= lane_linear(w0, 2 * c) ^ lane_linear(w1, 2 * c + 1);
+        }
+    }
+    h ^= __shfl_xor_sync(0xffffffffu, h, 1);
+    h ^= __shfl_xor_sync(0xffffffffu, h, 2);
+    h ^= __shfl_xor_sync(0xffffffffu, h, 4);
+    return h;
+}
+
+__host__ __device__ __forceinline__ bool group8_ok(int W) { return W <= 16 && (W % 2 == 0); }
+
 // i^k applied to a complex number (k mod 4), exact.
 __device__ __forceinline__ void mul_i_pow(double &re, double &im, int k) {
     double r = re, i = im;

@@ -8,6 +8,8 @@
 //   2. link: every sorted position finds its nearest earlier twin inside its sort bucket (exact row compare)
 //   3. sum: each head adds the coefficients of its group in input (t) order and applies |c| > thr
 //   4. exclusive scan of keep flags -> output slots ; compact ; emit rows with 16-byte stores
+#include <type_traits>
+
 #include "rows.cuh"
 #include "sort.cuh"
 
@@ -59,11 +61,11 @@ __device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_
 
 // sum: each HEAD walks forward through its bucket and adds the coefficients of the records whose
 // chain leads back to it, in input (t) order like np.add.at — deterministic, no atomics.
-template <class Rows, bool BY_T>
+template <class Rows, bool BY_T, bool DIRECT>
 __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
                                                    int sort_shift, const uint8_t *__restrict__ flag,
                                                    const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
-                                                   uint8_t *__restrict__ keep) {
+                                                   uint8_t *__restrict__ keep, uint8_t *__restrict__ multi) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     const uint64_t r0 = sr[i];
@@ -72,8 +74,8 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
         keep[d] = 0;
         return;
     }
-    double re, im;
-    rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+    double re = 0.0, im = 0.0;
+    bool have = false, is_multi = false;
     bool prev_mine = true;   // is record j-1 a member of this head's group?
     for (int64_t j = i + 1; j < T; ++j) {
         const uint64_t rj = sr[j];
@@ -84,29 +86,59 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
         else if (fj == FLAG_LINK) mine = fmt.same_hash(r0, rj) && chain_root(flag, link, (int64_t)link[j]) == i;
         else mine = false;
         if (mine) {
+            if (!have) {
+                rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+                have = true;
+            }
             double r2, i2;
             rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
             re += r2;
             im += i2;
+            is_multi = true;
         }
         prev_mine = mine;
     }
-    acc[d] = make_double2(re, im);
-    keep[d] = keep_test(re, im, thr);
+    if (is_multi || !DIRECT) {
+        if (!have) rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+        acc[d] = make_double2(re, im);
+        multi[d] = 1;
+        keep[d] = keep_test(re, im, thr);
+    } else if (thr < 0.0) {
+        keep[d] = 1;         // singleton, no threshold: the coefficient is recomputed at compaction
+    } else {
+        rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+        keep[d] = keep_test(re, im, thr);
+    }
 }
 
 // Compaction (emit phase): kept_t[slot] = term index of the survivor, out_c[slot] = its coefficient,
 // so that the row-emission kernel has a two-step dependency chain (kept_t -> rows) only.
-template <bool BY_T>
-__global__ void __launch_bounds__(256) compact_kernel(RecFmt fmt, const uint64_t *__restrict__ sr, const uint8_t *__restrict__ keep,
+template <class Rows, bool BY_T>
+__global__ void __launch_bounds__(256) compact_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr,
+                                                       const uint8_t *__restrict__ keep, const uint8_t *__restrict__ multi,
                                                        const uint32_t *__restrict__ slot, const double2 *__restrict__ acc,
                                                        int64_t T, uint32_t *__restrict__ kept_t, double2 *__restrict__ out_c) {
     int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= T) return;
     if (keep[d]) {
         const uint32_t s = slot[d];
-        kept_t[s] = BY_T ? (uint32_t)d : fmt.t(sr[d]);
-        out_c[s] = acc[d];
+        uint32_t t;
+        int e = 0;
+        if (BY_T) {
+            t = (uint32_t)d;
+        } else {
+            const uint64_t rec = sr[d];
+            t = fmt.t(rec);
+            e = fmt.e(rec);
+        }
+        kept_t[s] = t;
+        if (multi[d]) {
+            out_c[s] = acc[d];
+        } else {   // singleton survivor: its coefficient was never materialised
+            double re, im;
+            rows.coeff(t, e, re, im);
+            out_c[s] = make_double2(re, im);
+        }
     }
 }
 
@@ -166,6 +198,7 @@ size_t dedup_ws_bytes(int64_t T) {
            + arena_need(n, 4)                        // link
            + arena_need(n, 16)                       // acc
            + arena_need(n, 1)                        // keep
+           + arena_need(n, 1)                        // multi
            + arena_need(n, 4)                        // slot
            + arena_need(n, 4)                        // kept
            + arena_need(scan_scratch_elems(T), 4)    // scan scratch
@@ -197,6 +230,7 @@ struct DedupLayout {
     uint32_t *link;
     double2 *acc;
     uint8_t *keep;
+    uint8_t *multi;
     uint32_t *slot;
     uint32_t *kept;
     uint32_t *scratch;
@@ -213,6 +247,7 @@ static DedupLayout dedup_layout(void *ws, size_t ws_bytes, int64_t T) {
     L.link = ar.take<uint32_t>((size_t)T);
     L.acc = ar.take<double2>((size_t)T);
     L.keep = ar.take<uint8_t>((size_t)T);
+    L.multi = ar.take<uint8_t>((size_t)T);
     L.slot = ar.take<uint32_t>((size_t)T);
     L.kept = ar.take<uint32_t>((size_t)T);
     L.scratch = ar.take<uint32_t>(scan_scratch_elems(T));
@@ -246,7 +281,11 @@ static int dedup_plan(uint64_t *recs, int64_t T, RecFmt fmt, const Rows &rows, d
     const unsigned nb = (unsigned)((T + 255) / 256);
     link_kernel<Rows><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link);
     SYM_LAUNCH_OK();
-    sum_kernel<Rows, BY_T><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link, thr, L.acc, L.keep);
+    // singleton survivors skip the acc[] round trip when their coefficient can be recomputed at
+    // compaction: always in sorted order (the record carries t and the phase), and for stored rows
+    constexpr bool DIRECT = !BY_T || std::is_same<Rows, PlainRows>::value;
+    SYM_CUDA_OK(cudaMemsetAsync(L.multi, 0, (size_t)T, st));
+    sum_kernel<Rows, BY_T, DIRECT><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link, thr, L.acc, L.keep, L.multi);
     SYM_LAUNCH_OK();
     SYM_TRY(scan_exclusive_u8(L.keep, L.slot, T, L.total, L.scratch, st));
     if (n_out) {
@@ -275,7 +314,8 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
     const uint32_t chunks = (uint32_t)(rows.words / 2);
     uint4 *o = reinterpret_cast<uint4 *>(out_xz);
     double2 *oc = reinterpret_cast<double2 *>(out_c);
-    compact_kernel<BY_T><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(fmt, sr, L.keep, L.slot, L.acc, T, L.kept, oc);
+    compact_kernel<Rows, BY_T><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(rows, fmt, sr, L.keep, L.multi, L.slot, L.acc, T,
+                                                                           L.kept, oc);
     SYM_LAUNCH_OK();
 #define EMIT_LAUNCH(LW, UN, CS)                                                                   \
     {                                                                                             \
@@ -341,6 +381,15 @@ __global__ void __launch_bounds__(256) plain_records_kernel(const uint64_t *__re
     if (lane == 0) recs[row] = fmt.make(mix64(h) & mask, (uint64_t)row, 0);
 }
 
+__global__ void __launch_bounds__(256) plain_records8_kernel(const uint64_t *__restrict__ xz, int64_t T, int words, uint64_t mask,
+                                                              RecFmt fmt, uint64_t *__restrict__ recs) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
+    const bool ok = row < T;
+    uint64_t h = group8_sketch_row(xz + (ok ? row : 0) * words, words, lane & 7);
+    if (ok && (lane & 7) == 0) recs[row] = fmt.make(mix64(h) & mask, (uint64_t)row, 0);
+}
+
 }  // namespace symb
 
 using namespace symb;
@@ -373,7 +422,10 @@ extern "C" int sym_cleanup_count(const uint64_t *xz, const double *c, int64_t T,
     Arena ar(ws, ws_bytes);
     uint64_t *recs = ar.take<uint64_t>((size_t)T);
     RecFmt fmt{t_bits_for(T)};
-    plain_records_kernel<<<(unsigned)((T * 32 + 255) / 256), 256, 0, st>>>(xz, T, 2 * W, g_key_mask, fmt, recs);
+    if (group8_ok(W))
+        plain_records8_kernel<<<(unsigned)((((T + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, T, 2 * W, g_key_mask, fmt, recs);
+    else
+        plain_records_kernel<<<(unsigned)((T * 32 + 255) / 256), 256, 0, st>>>(xz, T, 2 * W, g_key_mask, fmt, recs);
     SYM_LAUNCH_OK();
     PlainRows rows{xz, c, 2 * W};
     return dedup_plain_plan(recs, T, fmt, rows, zero_threshold, n_out, n_out_host, ar.base + ar.off, ws_bytes - ar.off, st);

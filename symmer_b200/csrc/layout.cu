@@ -60,6 +60,14 @@ __global__ void ycount_kernel(const uint64_t *__restrict__ xz, int64_t M, int W,
     if (lane == 0) y[row] = cnt;
 }
 
+__global__ void sketch8_kernel(const uint64_t *__restrict__ xz, int64_t M, int W, uint64_t *__restrict__ sk) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
+    const bool ok = row < M;
+    uint64_t h = group8_sketch_row(xz + (ok ? row : 0) * 2 * W, 2 * W, lane & 7);
+    if (ok && (lane & 7) == 0) sk[row] = h;
+}
+
 __global__ void sketch_kernel(const uint64_t *__restrict__ xz, int64_t M, int W, uint64_t *__restrict__ sk) {
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -176,7 +184,10 @@ extern "C" int sym_ycount(const uint64_t *xz, int64_t M, int32_t W, int32_t *y, 
 extern "C" int sym_sketch_rows(const uint64_t *xz, int64_t M, int32_t W, uint64_t *sketch, void *stream) {
     SYM_REQUIRE(M >= 0 && W >= 1, "bad size");
     if (M == 0) return SYM_OK;
-    sketch_kernel<<<blocks_for(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, W, sketch);
+    if (group8_ok(W))
+        sketch8_kernel<<<blocks_for(((M + 3) / 4) * 32, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, W, sketch);
+    else
+        sketch_kernel<<<blocks_for(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, W, sketch);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }

@@ -41,6 +41,51 @@ __global__ void __launch_bounds__(256) rotate_info_kernel(const uint64_t *__rest
     }
 }
 
+// fast path (W even, W <= 16): 8 lanes per row, 16-byte loads, 4 rows per warp
+__global__ void __launch_bounds__(256) rotate_info8_kernel(const uint64_t *__restrict__ xz, int64_t M, int W,
+                                                            const uint64_t *__restrict__ q_xz, uint8_t *__restrict__ info) {
+    const int lane = threadIdx.x & 31, g = lane & 7;
+    int64_t row = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
+    const bool ok = row < M;
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(xz + (ok ? row : 0) * 2 * W);
+    const uint4 *q4 = reinterpret_cast<const uint4 *>(q_xz);
+    const int chunks = W >> 1;   // 16-byte chunks per block
+    uint64_t comm = 0, s = 0;
+    int ya = 0, yb = 0, yout = 0;
+#pragma unroll
+    for (int rep = 0; rep < 1; ++rep) {
+        const int c = g;
+        if (c < chunks) {
+            const uint4 xv = r4[c], zv = r4[chunks + c], qx = q4[c], qz = q4[chunks + c];
+            const uint64_t xa[2] = {((uint64_t)xv.y << 32) | xv.x, ((uint64_t)xv.w << 32) | xv.z};
+            const uint64_t za[2] = {((uint64_t)zv.y << 32) | zv.x, ((uint64_t)zv.w << 32) | zv.z};
+            const uint64_t xb[2] = {((uint64_t)qx.y << 32) | qx.x, ((uint64_t)qx.w << 32) | qx.z};
+            const uint64_t zb[2] = {((uint64_t)qz.y << 32) | qz.x, ((uint64_t)qz.w << 32) | qz.z};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                comm ^= (xa[k] & zb[k]) ^ (za[k] & xb[k]);
+                s ^= xa[k] & zb[k];
+                ya += __popcll(xa[k] & za[k]);
+                yb += __popcll(xb[k] & zb[k]);
+                yout += __popcll((xa[k] ^ xb[k]) & (za[k] ^ zb[k]));
+            }
+        }
+    }
+    int par = __popcll(comm) & 1, sg = __popcll(s) & 1;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        par ^= __shfl_xor_sync(0xffffffffu, par, o);
+        sg ^= __shfl_xor_sync(0xffffffffu, sg, o);
+        ya += __shfl_xor_sync(0xffffffffu, ya, o);
+        yb += __shfl_xor_sync(0xffffffffu, yb, o);
+        yout += __shfl_xor_sync(0xffffffffu, yout, o);
+    }
+    if (ok && g == 0) {
+        int e = (3 * (ya + yb) + yout + 2 * sg) & 3;
+        info[row] = (uint8_t)(par | (e << 1));
+    }
+}
+
 __global__ void __launch_bounds__(256) rotate_anti_flag_kernel(const uint8_t *__restrict__ info, int64_t M,
                                                                 uint8_t *__restrict__ anti) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,6 +142,65 @@ __global__ void __launch_bounds__(256) rotate_write_kernel(const uint64_t *__res
     }
 }
 
+// 16-byte form of rotate_write_kernel (words even): LC = log2(chunks per row) or -1 for generic
+template <int LC>
+__global__ void __launch_bounds__(256) rotate_write4_kernel(const uint4 *__restrict__ xz, const double2 *__restrict__ c,
+                                                             int64_t M, uint32_t chunks, const uint4 *__restrict__ q_xz,
+                                                             const uint8_t *__restrict__ info, const uint32_t *__restrict__ rank,
+                                                             double cos_a, double sin_a, int mode, double sign,
+                                                             uint4 *__restrict__ out_xz, double2 *__restrict__ out_c) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t row;
+    uint32_t k;
+    if (LC >= 0) {
+        row = g >> (LC >= 0 ? LC : 0);
+        k = (uint32_t)g & ((1u << (LC >= 0 ? LC : 0)) - 1u);
+    } else {
+        row = g / chunks;
+        k = (uint32_t)(g - row * chunks);
+    }
+    if (row >= (size_t)M) return;
+    const uint8_t inf = info[row];
+    const bool anti = inf & 1;
+    const int e = (inf >> 1) & 3;
+    const uint4 w = xz[g];
+    const uint4 q = q_xz[k];
+    const uint4 wq = make_uint4(w.x ^ q.x, w.y ^ q.y, w.z ^ q.z, w.w ^ q.w);
+    if (mode == 0) {
+        out_xz[g] = w;
+        if (anti) out_xz[((size_t)M + rank[row]) * chunks + k] = wq;
+        if (k == 0) {
+            double2 cc = c[row];
+            if (anti) {
+                out_c[row] = make_double2(cc.x * cos_a, cc.y * cos_a);
+                double re = cc.x, im = cc.y;
+                mul_i_pow(re, im, e);
+                out_c[M + rank[row]] = make_double2(im * sin_a, -re * sin_a);
+            } else {
+                out_c[row] = cc;
+            }
+        }
+    } else if (mode == 1) {
+        out_xz[g] = anti ? wq : w;
+        if (k == 0) {
+            double2 cc = c[row];
+            if (anti) {
+                double re = cc.x, im = cc.y;
+                mul_i_pow(re, im, e + 3);
+                out_c[row] = make_double2(re * sign, im * sign);
+            } else {
+                out_c[row] = cc;
+            }
+        }
+    } else {
+        out_xz[g] = w;
+        if (k == 0) {
+            double2 cc = c[row];
+            out_c[row] = anti ? make_double2(cc.x * sign, cc.y * sign) : cc;
+        }
+    }
+}
+
 __global__ void rotate_count_kernel(const uint32_t *__restrict__ total, int64_t M, int mode, int64_t *__restrict__ n_out) {
     *n_out = (mode == 0) ? M + (int64_t)*total : M;
 }
@@ -130,7 +234,10 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
     uint32_t *rank = ar.take<uint32_t>((size_t)M);
     uint32_t *scratch = ar.take<uint32_t>(scan_scratch_elems(M));
     uint32_t *total = ar.take<uint32_t>(4);
-    rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info);
+    if (group8_ok(W))
+        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info);
+    else
+        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info);
     SYM_LAUNCH_OK();
     if (mode == 0) {
         rotate_anti_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(info, M, anti);
@@ -139,11 +246,27 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
     } else {
         SYM_CUDA_OK(cudaMemsetAsync(total, 0, sizeof(uint32_t), st));
     }
-    int64_t threads = M * 2 * W;
-    rotate_write_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        xz, reinterpret_cast<const double2 *>(c), M, 2 * W, q_xz, info, rank, cos_a, sin_a, mode, sign, out_xz,
-        reinterpret_cast<double2 *>(out_c));
-    SYM_LAUNCH_OK();
+    {
+        const uint32_t chunks = (uint32_t)W;   // 2W words = W 16-byte chunks
+        const size_t threads = (size_t)M * chunks;
+        const unsigned nbw = (unsigned)((threads + 255) / 256);
+        const uint4 *x4 = reinterpret_cast<const uint4 *>(xz);
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(q_xz);
+        const double2 *c2 = reinterpret_cast<const double2 *>(c);
+        uint4 *o4 = reinterpret_cast<uint4 *>(out_xz);
+        double2 *oc2 = reinterpret_cast<double2 *>(out_c);
+#define RW_CASE(LC) rotate_write4_kernel<LC><<<nbw, 256, 0, st>>>(x4, c2, M, chunks, q4, info, rank, cos_a, sin_a, mode, sign, o4, oc2)
+        switch (chunks) {
+            case 1: RW_CASE(0); break;
+            case 2: RW_CASE(1); break;
+            case 4: RW_CASE(2); break;
+            case 8: RW_CASE(3); break;
+            case 16: RW_CASE(4); break;
+            default: RW_CASE(-1); break;
+        }
+#undef RW_CASE
+        SYM_LAUNCH_OK();
+    }
     rotate_count_kernel<<<1, 1, 0, st>>>(total, M, mode, n_out);
     SYM_LAUNCH_OK();
     return SYM_OK;
