@@ -263,3 +263,54 @@ def test_config1_square(sb):
     ref_s, ref_c = po.multiply(sub_s, sub_c, sub_s, sub_c)
     sub = P(sub_s, sub_c)
     same_terms(sub * sub, ref_s, ref_c, scale=np.abs(sub_c).max() ** 2)
+
+
+def test_single_pauli_product_at_a_million_qubits(sb):
+    """README claim #4 of the reference (single Pauli x single Pauli on very wide registers)."""
+    P = sb.PauliwordOp
+    n = 1_000_000
+    rng = np.random.default_rng(0)
+    a = rng.random((1, 2 * n)) < 0.3
+    b = rng.random((1, 2 * n)) < 0.3
+    A, B = P(a, [1.5]), P(b, [2.0j])
+    C = A * B
+    ref_s, ref_c = po.multiply(a, np.array([1.5]), b, np.array([2.0j]))
+    assert C.n_terms == 1 and np.array_equal(C.symp_matrix, ref_s) and np.allclose(C.coeff_vec, ref_c, rtol=1e-14)
+    assert bool(A.commutes_termwise(B)[0, 0]) == bool(po.commutes_termwise(a, b)[0, 0])
+    assert (A + A).n_terms == 1 and np.allclose((A + A).coeff_vec, [3.0])
+
+
+def test_first_occurrence_vs_sorted_hash_switch(sb):
+    """Products just below / above the 2^22 cross-term switch agree as term sets; below it the row
+    order is the reference's first-occurrence order."""
+    P = sb.PauliwordOp
+    np.random.seed(11)
+    A, B = P.random(40, 2048), P.random(40, 2049)
+    lo = A * B[:2047]                                   # 4 192 256 < 2^22
+    hi = B * A                                          # 4 196 352 > 2^22 (B is the larger operand)
+    ref_s, ref_c = po.multiply(A.symp_matrix, A.coeff_vec, B.symp_matrix[:2047], B.coeff_vec[:2047])
+    assert np.array_equal(lo.symp_matrix, ref_s)        # same order as the reference
+    assert np.allclose(lo.coeff_vec, ref_c, rtol=1e-12)
+    ref_s, ref_c = po.multiply(B.symp_matrix, B.coeff_vec, A.symp_matrix, A.coeff_vec)
+    same_terms(hi, ref_s, ref_c, scale=float(np.abs(A.coeff_vec).max() * np.abs(B.coeff_vec).max()))
+
+
+def test_molecular_square_heavy_duplication(sb, hamiltonians):
+    """H*H for H2O: 1.18M cross terms collapse to a few tens of thousands (group sizes ~ 50)."""
+    symp, coeff, _ = hamiltonians("H2O_STO3G")
+    H = sb.PauliwordOp(symp, coeff)
+    H2 = H * H
+    ref_s, ref_c = po.multiply(symp, coeff, symp, coeff)
+    assert H2.n_terms == len(ref_c)
+    same_terms(H2, ref_s, ref_c, scale=float(np.abs(coeff).max() ** 2))
+
+
+def test_zero_qubit_and_empty_operands(sb):
+    P = sb.PauliwordOp
+    Z = P(np.zeros((3, 0), dtype=bool), [1, 2, 3])
+    assert Z.n_qubits == 0 and np.allclose(Z.cleanup().coeff_vec, [6])
+    E = P(np.zeros((0, 8), dtype=bool), [])
+    A = P.from_list(['XYZI'], [1])
+    assert (A * E).n_terms == 0 and (E * A).n_terms == 0
+    assert (A + E) == A
+    assert E.commutes_termwise(A).shape == (0, 1)
