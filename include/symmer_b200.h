@@ -171,6 +171,26 @@ size_t sym_pair_records_ws_bytes(int64_t M_total, int64_t N, int32_t W);
 int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p_begin, int64_t p_end,
                      const uint64_t *b_xz, int64_t N, int32_t W, uint64_t *recs, void *ws,
                      size_t ws_bytes, void *stream);
+/* Records of nblk rectangular blocks A[p0:p1) x B[q0:q1), written back to back in block order
+ * ((q, p) order inside a block); blocks_host: HOST int64[nblk][4] = {p0, p1, q0, q1}. t = q*M_total + p
+ * with the global row indices. `recs` must hold the sum of the block sizes. */
+int sym_pair_records_blocks(const uint64_t *a_xz, int64_t M_total, const uint64_t *b_xz, int64_t N,
+                            int32_t W, const int64_t *blocks_host, int32_t nblk, uint64_t *recs,
+                            void *ws, size_t ws_bytes, void *stream);
+/* Exchange-free ownership for sharded products. owner(row) = log2_parts parity bits of the row's
+ * GF(2)-linear sketch, hence owner(A[p] ^ B[q]) = owner(A[p]) ^ owner(B[q]): with both operands
+ * grouped by owner class, rank r generates exactly the cross terms it owns (blocks A_a x B_{a^r},
+ * sym_pair_records_blocks) and no record crosses NVLink.
+ * sym_owner_classes: cls[i] = owner class of row i (ws >= 8*M bytes, rounded up to 256).
+ * sym_class_partition: stable grouping of an operator by class: out rows/coefficients in class
+ * order (input order inside a class), perm[i] = source row of output row i (may be NULL),
+ * counts: device int64[1 << log2_parts] class sizes. c/out_c may be NULL. */
+int sym_owner_classes(const uint64_t *xz, int64_t M, int32_t W, int32_t log2_parts, uint8_t *cls,
+                      void *ws, size_t ws_bytes, void *stream);
+size_t sym_class_partition_ws_bytes(int64_t M);
+int sym_class_partition(const uint64_t *xz, const double *c, int64_t M, int32_t W, int32_t log2_parts,
+                        uint64_t *out_xz, double *out_c, int32_t *perm, int64_t *counts, void *ws,
+                        size_t ws_bytes, void *stream);
 /* Stable partition of records by owner = rec >> (64 - log2_parts); counts: device int64[parts]. */
 size_t sym_partition_ws_bytes(int64_t T);
 int sym_partition_records(const uint64_t *recs, int64_t T, int32_t log2_parts, uint64_t *out_recs,

@@ -48,6 +48,10 @@ SIGNATURES = {
     "sym_unpack_matrix": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     "sym_pair_records_ws_bytes": (c_sz, [c_i64, c_i64, c_i32]),
     "sym_pair_records": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
+    "sym_pair_records_blocks": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_i32, c_p, c_p, c_sz, c_p]),
+    "sym_owner_classes": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_p, c_p, c_sz, c_p]),
+    "sym_class_partition_ws_bytes": (c_sz, [c_i64]),
+    "sym_class_partition": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "sym_partition_ws_bytes": (c_sz, [c_i64]),
     "sym_partition_records": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_sz, c_p]),
     "sym_dedup_records_ws_bytes": (c_sz, [c_i64, c_i32]),

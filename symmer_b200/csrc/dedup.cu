@@ -103,11 +103,49 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
         acc[d] = make_double2(re, im);
         multi[d] = 1;
         keep[d] = keep_test(re, im, thr);
-    } else if (thr < 0.0) {
-        keep[d] = 1;         // singleton, no threshold: the coefficient is recomputed at compaction
+    } else if (thr < 0.0 || rows.all_pass()) {
+        keep[d] = 1;         // singleton that cannot fail the threshold: the coefficient is computed once, at emission
     } else {
         rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
         keep[d] = keep_test(re, im, thr);
+    }
+}
+
+// pass_all flag of a product: min|a| * min|b| clears the threshold with a 4x margin (the rounded
+// product of any single pair is within a few ulp of |a||b|), so no singleton cross term can fail
+// |c| > thr and the sum kernel need not gather coefficients for them. One block; M + N is small.
+__global__ void __launch_bounds__(1024) min_abs_flag_kernel(const double2 *__restrict__ a, int64_t M,
+                                                             const double2 *__restrict__ b, int64_t N, double thr,
+                                                             uint32_t *__restrict__ flag) {
+    __shared__ double sa[32], sb[32];
+    double ma = INFINITY, mb = INFINITY;
+    for (int64_t i = threadIdx.x; i < M; i += 1024) {
+        double h = hypot(a[i].x, a[i].y);
+        if (!(h >= 0.0)) h = 0.0;   // NaN
+        ma = fmin(ma, h);
+    }
+    for (int64_t i = threadIdx.x; i < N; i += 1024) {
+        double h = hypot(b[i].x, b[i].y);
+        if (!(h >= 0.0)) h = 0.0;
+        mb = fmin(mb, h);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ma = fmin(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+        mb = fmin(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sa[threadIdx.x >> 5] = ma;
+        sb[threadIdx.x >> 5] = mb;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) {
+            ma = fmin(ma, sa[w]);
+            mb = fmin(mb, sb[w]);
+        }
+        const double prod = ma * mb;
+        *flag = (isfinite(prod) && prod > 4.0 * thr) ? 1u : 0u;
     }
 }
 
@@ -148,7 +186,7 @@ __global__ void total_to_i64_kernel(const uint32_t *__restrict__ total, int64_t 
 // 2*EMIT_UN independent 16-byte loads are in flight per thread (the kernel is latency-bound
 // otherwise). Stores are streaming (st.global.cs): the output is never re-read, and A/B must stay
 // L2-resident. LW: chunks per row = 1 << LW.
-int g_emit_variant = 1;  // tuning knob 1: 8 records per thread, plain stores (measured best on B200)
+int g_emit_variant = 1;  // tuning knob 1: 1 = fused compaction + emission (default), 0 = two kernels
 
 __device__ __forceinline__ void store_streaming(uint4 *p, const uint4 &v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -187,6 +225,71 @@ __global__ void __launch_bounds__(256) emit_generic_kernel(Rows rows, const uint
     const uint32_t c = (uint32_t)(g - (size_t)rec * chunks);
     if (rec >= U) return;
     out_xz[g] = rows.chunk(kept_t[rec], (int)c);
+}
+
+// Fused compaction + row emission (the dominant kernel of a large product: HBM-write bound).
+// A CTA owns D = ROWS_PP*UN consecutive dedup positions; because slot[] is an exclusive scan of the
+// keep flags, its survivors occupy the contiguous output range [slot[d0], slot[d0] + count).
+// Phase 1 (first D threads): survivor -> term id into shared memory, final coefficient straight to
+// out_c (consecutive survivors write consecutive 16-byte slots). Phase 2 (all threads): thread =
+// (row, 16-byte chunk), UN rows in flight per thread, A[p]^B[q] gathered from the L2-resident
+// operands, 16-byte stores. No kept_t round trip through HBM and no separate compaction launch.
+template <class Rows, bool BY_T, int LW, int UN>
+__global__ void __launch_bounds__(256) emit_fused_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr,
+                                                          const uint8_t *__restrict__ keep, const uint8_t *__restrict__ multi,
+                                                          const uint32_t *__restrict__ slot, const double2 *__restrict__ acc,
+                                                          int64_t T, uint4 *__restrict__ out_xz, double2 *__restrict__ out_c) {
+    constexpr uint32_t ROWS_PP = 256u >> LW;
+    constexpr uint32_t D = ROWS_PP * UN;
+    static_assert(D <= 256, "one thread per position in phase 1");
+    __shared__ uint2 s_h[D];
+    __shared__ uint32_t s_count;
+    const int64_t d0 = (int64_t)blockIdx.x * D;
+    const uint32_t base = slot[d0];
+    if (threadIdx.x < D) {
+        const int64_t d = d0 + threadIdx.x;
+        uint8_t k = 0;
+        uint32_t s = 0;
+        if (d < T) {
+            k = keep[d];
+            s = slot[d];
+            if (k) {
+                uint32_t t;
+                int e = 0;
+                if (BY_T) {
+                    t = (uint32_t)d;
+                } else {
+                    const uint64_t rec = sr[d];
+                    t = fmt.t(rec);
+                    e = fmt.e(rec);
+                }
+                s_h[s - base] = rows.locate(t);
+                if (multi[d]) {
+                    out_c[s] = acc[d];
+                } else {   // singleton survivor: its coefficient was never materialised
+                    double re, im;
+                    rows.coeff(t, e, re, im);
+                    out_c[s] = make_double2(re, im);
+                }
+            }
+        }
+        if (d < T && (threadIdx.x == D - 1 || d == T - 1)) s_count = s + (uint32_t)k - base;
+    }
+    __syncthreads();
+    const uint32_t count = s_count;
+    const uint32_t r_in = threadIdx.x >> LW;
+    const uint32_t c = threadIdx.x & ((1u << LW) - 1u);
+    uint4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+        const uint32_t r = u * ROWS_PP + r_in;
+        if (r < count) v[u] = rows.chunk_at(s_h[r], (int)c);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+        const uint32_t r = u * ROWS_PP + r_in;
+        if (r < count) out_xz[(((size_t)base + r) << LW) + c] = v[u];
+    }
 }
 
 size_t dedup_ws_bytes(int64_t T) {
@@ -285,7 +388,18 @@ static int dedup_plan(uint64_t *recs, int64_t T, RecFmt fmt, const Rows &rows, d
     // compaction: always in sorted order (the record carries t and the phase), and for stored rows
     constexpr bool DIRECT = !BY_T || std::is_same<Rows, PlainRows>::value;
     SYM_CUDA_OK(cudaMemsetAsync(L.multi, 0, (size_t)T, st));
-    sum_kernel<Rows, BY_T, DIRECT><<<nb, 256, 0, st>>>(rows, fmt, sr, T, begin, L.flag, L.link, thr, L.acc, L.keep, L.multi);
+    Rows rows_sum = rows;
+    if constexpr (std::is_same<Rows, ProductRows>::value && !BY_T) {
+        if (thr >= 0.0 && rows.N > 0) {
+            min_abs_flag_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
+                                                    reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr,
+                                                    L.total + 2);
+            SYM_LAUNCH_OK();
+            rows_sum.pass_all = L.total + 2;
+        }
+    }
+    sum_kernel<Rows, BY_T, DIRECT><<<nb, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, L.flag, L.link, thr, L.acc, L.keep,
+                                                      L.multi);
     SYM_LAUNCH_OK();
     SYM_TRY(scan_exclusive_u8(L.keep, L.slot, T, L.total, L.scratch, st));
     if (n_out) {
@@ -314,6 +428,25 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
     const uint32_t chunks = (uint32_t)(rows.words / 2);
     uint4 *o = reinterpret_cast<uint4 *>(out_xz);
     double2 *oc = reinterpret_cast<double2 *>(out_c);
+#define EMIT_FUSED(LW, UN)                                                                                      \
+    {                                                                                                           \
+        constexpr int64_t Dp = (int64_t)(256 >> LW) * UN;                                                       \
+        emit_fused_kernel<Rows, BY_T, LW, UN><<<(unsigned)((T + Dp - 1) / Dp), 256, 0, st>>>(                   \
+            rows, fmt, sr, L.keep, L.multi, L.slot, L.acc, T, o, oc);                                           \
+    }
+    if (g_emit_variant == 1 && (chunks == 1 || chunks == 2 || chunks == 4 || chunks == 8 || chunks == 16)) {
+        switch (chunks) {
+            case 1: EMIT_FUSED(0, 1); break;
+            case 2: EMIT_FUSED(1, 2); break;
+            case 4: EMIT_FUSED(2, 4); break;
+            case 8: EMIT_FUSED(3, 8); break;
+            default: EMIT_FUSED(4, 8); break;
+        }
+        SYM_LAUNCH_OK();
+        return SYM_OK;
+    }
+#undef EMIT_FUSED
+    // two-kernel form (tuning knob 1 = 0, and the generic chunk counts): compaction, then row emission
     compact_kernel<Rows, BY_T><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(rows, fmt, sr, L.keep, L.multi, L.slot, L.acc, T,
                                                                            L.kept, oc);
     SYM_LAUNCH_OK();
@@ -323,27 +456,17 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
         const unsigned nbe = (unsigned)((U + rows_per_block - 1) / rows_per_block);               \
         emit_kernel<Rows, LW, UN, CS><<<nbe, 256, 0, st>>>(rows, L.kept, (uint32_t)U, o);         \
     }
-#define EMIT_CASE(LW)                                       \
-    switch (g_emit_variant) {                               \
-        case 1: EMIT_LAUNCH(LW, 8, false); break;           \
-        case 2: EMIT_LAUNCH(LW, 8, true); break;            \
-        case 3: EMIT_LAUNCH(LW, 4, false); break;           \
-        case 4: EMIT_LAUNCH(LW, 2, false); break;           \
-        case 5: EMIT_LAUNCH(LW, 1, true); break;            \
-        default: EMIT_LAUNCH(LW, 1, false); break;          \
-    }
     switch (chunks) {
-        case 1: EMIT_CASE(0); break;
-        case 2: EMIT_CASE(1); break;
-        case 4: EMIT_CASE(2); break;
-        case 8: EMIT_CASE(3); break;
-        case 16: EMIT_CASE(4); break;
+        case 1: EMIT_LAUNCH(0, 8, false); break;
+        case 2: EMIT_LAUNCH(1, 8, false); break;
+        case 4: EMIT_LAUNCH(2, 8, false); break;
+        case 8: EMIT_LAUNCH(3, 8, false); break;
+        case 16: EMIT_LAUNCH(4, 8, false); break;
         default: {
             const size_t threads = (size_t)U * chunks;
             emit_generic_kernel<Rows><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(rows, L.kept, (uint32_t)U, chunks, o);
         } break;
     }
-#undef EMIT_CASE
 #undef EMIT_LAUNCH
     SYM_LAUNCH_OK();
     return SYM_OK;

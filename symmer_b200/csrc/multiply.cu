@@ -29,7 +29,8 @@ template <int WT>
 __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
     const uint64_t *__restrict__ a_xz, const uint64_t *__restrict__ a_sk, const int32_t *__restrict__ a_y, uint32_t M_total,
     uint32_t p_begin, uint32_t p_end, const uint64_t *__restrict__ b_xz, const uint64_t *__restrict__ b_sk,
-    const int32_t *__restrict__ b_y, uint32_t N, int W, uint64_t key_mask, RecFmt fmt, uint64_t *__restrict__ recs) {
+    const int32_t *__restrict__ b_y, uint32_t N, uint32_t q_off, int W, uint64_t key_mask, RecFmt fmt,
+    uint64_t *__restrict__ recs) {
     // B tile: QCH rows, (x_w, z_w) interleaved so one 16-byte shared load feeds a word step
     __shared__ ulonglong2 sb[PAIR_QCH][WT];
     __shared__ uint64_t sb_sk[PAIR_QCH];
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
         }
         const int e = finish_phase(ya, sb_y[qi], s, c0, c1);
         const size_t j = (size_t)(q0 + qi) * m_blk + p_local;
-        recs[j] = fmt.make(mix64(ska ^ sb_sk[qi]) & key_mask, (uint64_t)(q0 + qi) * M_total + p, e);
+        recs[j] = fmt.make(mix64(ska ^ sb_sk[qi]) & key_mask, (uint64_t)(q_off + q0 + qi) * M_total + p, e);
     }
 }
 
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
 __global__ void __launch_bounds__(256) pair_records_generic_kernel(
     const uint64_t *__restrict__ a_xz, const uint64_t *__restrict__ a_sk, const int32_t *__restrict__ a_y, uint32_t M_total,
     uint32_t p_begin, uint32_t p_end, const uint64_t *__restrict__ b_xz, const uint64_t *__restrict__ b_sk,
-    const int32_t *__restrict__ b_y, uint32_t N, int W, uint64_t key_mask, RecFmt fmt, uint64_t *__restrict__ recs) {
+    const int32_t *__restrict__ b_y, uint32_t N, uint32_t q_off, int W, uint64_t key_mask, RecFmt fmt,
+    uint64_t *__restrict__ recs) {
     const uint32_t m_blk = p_end - p_begin;
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (size_t)m_blk * N) return;
@@ -111,19 +113,21 @@ __global__ void __launch_bounds__(256) pair_records_generic_kernel(
         c0 ^= v;
     }
     int e = finish_phase(a_y[p], b_y[q], s, c0, c1);
-    recs[j] = fmt.make(mix64(a_sk[p] ^ b_sk[q]) & key_mask, (uint64_t)q * M_total + p, e);
+    recs[j] = fmt.make(mix64(a_sk[p] ^ b_sk[q]) & key_mask, (uint64_t)(q_off + q) * M_total + p, e);
 }
 
 static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const int32_t *a_y, int64_t M_total,
                                int64_t p_begin, int64_t p_end, const uint64_t *b_xz, const uint64_t *b_sk,
-                               const int32_t *b_y, int64_t N, int W, RecFmt fmt, uint64_t *recs, cudaStream_t st) {
+                               const int32_t *b_y, int64_t N, int W, RecFmt fmt, uint64_t *recs, cudaStream_t st,
+                               int64_t q_off = 0) {
+    // b_xz / b_sk / b_y point at B row q_off; N rows from there. t uses the global index q_off + q.
     const int64_t m_blk = p_end - p_begin;
     if (m_blk <= 0 || N <= 0) return SYM_OK;
     dim3 grid((unsigned)((m_blk + PAIR_THREADS - 1) / PAIR_THREADS), (unsigned)((N + PAIR_QCH - 1) / PAIR_QCH));
 #define PAIR_CASE(WT)                                                                                               \
     pair_records_kernel<WT><<<grid, PAIR_THREADS, 0, st>>>(a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin,   \
-                                                           (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N, W,        \
-                                                           g_key_mask, fmt, recs)
+                                                           (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N,           \
+                                                           (uint32_t)q_off, W, g_key_mask, fmt, recs)
     if (grid.y > 65535) {
         set_error("too many B rows for one launch (N=%lld)", (long long)N);
         return SYM_E_UNSUPPORTED;
@@ -136,8 +140,8 @@ static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const
     else {
         int64_t total = m_blk * N;
         pair_records_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin, (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N, W,
-            g_key_mask, fmt, recs);
+            a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin, (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N,
+            (uint32_t)q_off, W, g_key_mask, fmt, recs);
     }
 #undef PAIR_CASE
     SYM_LAUNCH_OK();
@@ -245,6 +249,37 @@ extern "C" int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p
     return launch_pair_records(a_xz, a_sk, a_y, M_total, p_begin, p_end, b_xz, b_sk, b_y, N, W, fmt, recs, st);
 }
 
+extern "C" int sym_pair_records_blocks(const uint64_t *a_xz, int64_t M_total, const uint64_t *b_xz, int64_t N, int32_t W,
+                                       const int64_t *blocks_host, int32_t nblk, uint64_t *recs, void *ws,
+                                       size_t ws_bytes, void *stream) {
+    SYM_REQUIRE(M_total >= 0 && N >= 0 && W >= 1 && nblk >= 0, "bad size");
+    SYM_REQUIRE(M_total * N < (int64_t)4000000000LL, "M_total*N must be < 4e9");
+    for (int b = 0; b < nblk; ++b) {
+        const int64_t *q = blocks_host + 4 * b;
+        SYM_REQUIRE(0 <= q[0] && q[0] <= q[1] && q[1] <= M_total, "bad A row block");
+        SYM_REQUIRE(0 <= q[2] && q[2] <= q[3] && q[3] <= N, "bad B row block");
+    }
+    if (ws_bytes < sym_pair_records_ws_bytes(M_total, N, W)) {
+        set_error("workspace too small");
+        return SYM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ar(ws, ws_bytes);
+    uint64_t *a_sk, *b_sk;
+    int32_t *a_y, *b_y;
+    SYM_TRY(prepare_operand_tables(a_xz, M_total, b_xz, N, W, ar, a_sk, b_sk, a_y, b_y, st));
+    RecFmt fmt{t_bits_for(M_total * N)};
+    size_t off = 0;
+    for (int b = 0; b < nblk; ++b) {
+        const int64_t p0 = blocks_host[4 * b], p1 = blocks_host[4 * b + 1], q0 = blocks_host[4 * b + 2],
+                      q1 = blocks_host[4 * b + 3];
+        SYM_TRY(launch_pair_records(a_xz, a_sk, a_y, M_total, p0, p1, b_xz + (size_t)q0 * 2 * W, b_sk + q0, b_y + q0,
+                                    q1 - q0, W, fmt, recs + off, st, q0));
+        off += (size_t)(p1 - p0) * (size_t)(q1 - q0);
+    }
+    return SYM_OK;
+}
+
 extern "C" size_t sym_partition_ws_bytes(int64_t T) {
     if (T < 1) T = 1;
     return arena_need(record_hist_elems(T), 4) + 1024;
@@ -275,7 +310,7 @@ extern "C" int sym_dedup_records_count(uint64_t *recs, int64_t T, const uint64_t
     SYM_REQUIRE(T >= 0 && T < (int64_t)4000000000LL, "T out of range");
     SYM_REQUIRE(M_total >= 1 && N >= 1 && W >= 1, "bad size");
     SYM_REQUIRE(M_total * N < (int64_t)4000000000LL, "M_total*N must be < 4e9");
-    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W};
+    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
     RecFmt fmt{t_bits_for(M_total * N)};
     return dedup_product_plan(recs, T, fmt, rows, false, zero_threshold, n_out, n_out_host, ws, ws_bytes,
                               (cudaStream_t)stream);
@@ -286,7 +321,7 @@ extern "C" int sym_dedup_records_emit(const uint64_t *recs, int64_t T, const uin
                                       int64_t U, uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, void *stream) {
     SYM_REQUIRE(T >= 0 && U >= 0 && U <= T, "bad counts");
     SYM_REQUIRE(M_total >= 1 && N >= 1 && W >= 1, "bad size");
-    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W};
+    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
     RecFmt fmt{t_bits_for(M_total * N)};
     return dedup_product_emit(recs, T, fmt, rows, false, U, out_xz, out_c, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -395,7 +430,7 @@ extern "C" int sym_mul_cleanup_count(const uint64_t *a_xz, const double *a_c, in
     SYM_TRY(sym_ycount(b_xz, N, W, P.b_y, st));
     RecFmt fmt{t_bits_for(T)};
     SYM_TRY(launch_pair_records(a_xz, P.a_sk, P.a_y, M, 0, M, b_xz, P.b_sk, P.b_y, N, W, fmt, P.recs, st));
-    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W};
+    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W, (uint32_t)N};
     return dedup_product_plan(P.recs, T, fmt, rows, T <= g_by_t_limit, zero_threshold, n_out, n_out_host, P.rest,
                               P.rest_bytes, st);
 }
@@ -407,7 +442,7 @@ extern "C" int sym_mul_cleanup_emit(const uint64_t *a_xz, const double *a_c, int
     const int64_t T = M * N;
     if (T == 0 || U == 0) return SYM_OK;
     MulPlan P = mul_plan_layout(ws, ws_bytes, M, N);
-    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W};
+    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W, (uint32_t)N};
     RecFmt fmt{t_bits_for(T)};
     return dedup_product_emit(P.recs, T, fmt, rows, T <= g_by_t_limit, U, out_xz, out_c, P.rest, P.rest_bytes,
                               (cudaStream_t)stream);

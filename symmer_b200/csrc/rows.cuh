@@ -32,6 +32,10 @@ struct ProductRows {
     const double *__restrict__ Bc;
     uint32_t M;  // rows of A (divisor of t)
     int words;   // 2*W
+    uint32_t N = 0;                                // rows of B (0 = unknown)
+    const uint32_t *__restrict__ pass_all = nullptr;  // device flag: every single cross term passes |c| > thr
+
+    __device__ __forceinline__ bool all_pass() const { return pass_all != nullptr && *pass_all != 0u; }
 
     __device__ __forceinline__ void split(uint32_t t, uint32_t &p, uint32_t &q) const {
         q = t / M;
@@ -42,6 +46,17 @@ struct ProductRows {
         split(t, p, q);
         const uint4 a = reinterpret_cast<const uint4 *>(A + (size_t)p * words)[c];
         const uint4 b = reinterpret_cast<const uint4 *>(B + (size_t)q * words)[c];
+        return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w);
+    }
+    // (p, q) handle of a term, so that the 16 chunk-threads of a row do not each redo the division
+    __device__ __forceinline__ uint2 locate(uint32_t t) const {
+        uint2 h;
+        split(t, h.x, h.y);
+        return h;
+    }
+    __device__ __forceinline__ uint4 chunk_at(uint2 h, int c) const {
+        const uint4 a = reinterpret_cast<const uint4 *>(A + (size_t)h.x * words)[c];
+        const uint4 b = reinterpret_cast<const uint4 *>(B + (size_t)h.y * words)[c];
         return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w);
     }
     __device__ __forceinline__ bool equal(uint32_t t1, uint32_t t2) const {
@@ -68,9 +83,12 @@ struct PlainRows {
     const double *__restrict__ C;
     int words;
 
+    __device__ __forceinline__ bool all_pass() const { return false; }
     __device__ __forceinline__ uint4 chunk(uint32_t t, int c) const {
         return reinterpret_cast<const uint4 *>(X + (size_t)t * words)[c];
     }
+    __device__ __forceinline__ uint2 locate(uint32_t t) const { return make_uint2(t, 0u); }
+    __device__ __forceinline__ uint4 chunk_at(uint2 h, int c) const { return chunk(h.x, c); }
     __device__ __forceinline__ bool equal(uint32_t t1, uint32_t t2) const {
         const uint64_t *r1 = X + (size_t)t1 * words, *r2 = X + (size_t)t2 * words;
         for (int k = 0; k < words; ++k)

@@ -1,10 +1,14 @@
 """Multi-GPU paths (one process per GPU, torch.distributed over NCCL/NVLink) — SURVEY.md §8e.
 
-* product + cleanup: the larger operand's rows are sharded by term blocks; every rank generates the
-  8-byte dedup records of its block, routes each record to the rank that owns its hash range with
-  one variable-size all-to-all, and the owner dedups locally and rebuilds rows from its replicas of
-  the (small) operands. Only records cross NVLink (8 B per cross term instead of a 272 B row).
-  The result stays hash-partitioned across ranks.
+* product + cleanup: the larger operand's rows are sharded by term blocks and all-gathered once
+  (25.6 MB at C5). Default path ("owner"): the owner of a row is a GF(2)-linear function of it, so
+  owner(A[p]^B[q]) = class(A[p]) ^ class(B[q]) and every rank generates exactly the cross terms it
+  owns — duplicates meet on one rank and nothing but the operands ever crosses NVLink.
+  Alternative ("alltoall"): every rank generates the 8-byte dedup records of its block, routes each
+  record to the rank that owns its hash range with one variable-size all-to-all, and the owner
+  dedups locally (8 B per cross term on NVLink instead of a 272 B row).
+  Either way the owner rebuilds rows from its replicas of the operands and the result stays
+  hash-partitioned across ranks.
 * commute / adjacency: row blocks of the output, no collective.
 * expval: the 2^n basis is sharded by row range, one all-reduce of a complex scalar at the end.
 
@@ -78,15 +82,76 @@ def exchange_records(part: torch.Tensor, counts: torch.Tensor, group=None) -> to
     return out
 
 
+def all_gather_operator(xz: torch.Tensor, c: torch.Tensor, group=None):
+    """All-gather an operator whose rows are sharded by blocks: (xz_full, c_full, offsets). One size
+    exchange for both tensors; equal blocks (the common case) gather straight into the result."""
+    rank, world = _world(group)
+    if world == 1:
+        return xz, c, [0, xz.shape[0]]
+    n_local = torch.tensor([xz.shape[0]], dtype=torch.int64, device=xz.device)
+    sizes_t = torch.empty(world, dtype=torch.int64, device=xz.device)
+    dist.all_gather_into_tensor(sizes_t, n_local, group=group)
+    sizes = [int(v) for v in sizes_t.cpu().tolist()]
+    offsets = [0]
+    for sz in sizes:
+        offsets.append(offsets[-1] + sz)
+    if min(sizes) == max(sizes):
+        xz_full = torch.empty((offsets[-1],) + tuple(xz.shape[1:]), dtype=xz.dtype, device=xz.device)
+        c_real = torch.view_as_real(c.contiguous())
+        c_full = torch.empty((offsets[-1], 2), dtype=c_real.dtype, device=c.device)
+        dist.all_gather_into_tensor(xz_full, xz.contiguous(), group=group)
+        dist.all_gather_into_tensor(c_full, c_real, group=group)
+        return xz_full, torch.view_as_complex(c_full), offsets
+    xz_full, _ = all_gather_rows(xz, group)
+    c_full, _ = all_gather_rows(c, group)
+    return xz_full, c_full, offsets
+
+
+def owner_blocks(a_counts: List[int], b_counts: List[int], owner: int) -> List[Tuple[int, int, int, int]]:
+    """Row blocks (p0, p1, q0, q1) of the class-grouped operands whose cross terms `owner` owns:
+    class a of A against class a ^ owner of B (owner(A[p] ^ B[q]) = class(A[p]) ^ class(B[q]))."""
+    parts = len(a_counts)
+    assert len(b_counts) == parts and 0 <= owner < parts
+    a_off, b_off = [0], [0]
+    for n in a_counts:
+        a_off.append(a_off[-1] + int(n))
+    for n in b_counts:
+        b_off.append(b_off[-1] + int(n))
+    return [(a_off[a], a_off[a + 1], b_off[a ^ owner], b_off[(a ^ owner) + 1]) for a in range(parts)]
+
+
+def owned_product(a_xz: torch.Tensor, a_c: torch.Tensor, b_xz: torch.Tensor, b_c: torch.Tensor, log2_parts: int,
+                  owner: int, zero_threshold: Optional[float] = 1e-15):
+    """The part of (A * B).cleanup() owned by `owner` out of 2**log2_parts, computed locally from the
+    full operands with no exchange. Returns (xz, c, info)."""
+    a_p, a_cp, _, a_counts = ops.class_partition(a_xz, a_c, log2_parts)
+    b_p, b_cp, _, b_counts = ops.class_partition(b_xz, b_c, log2_parts)
+    counts = torch.stack([a_counts, b_counts]).cpu().tolist()      # one small device->host read
+    blocks = owner_blocks(counts[0], counts[1], owner)
+    recs = ops.pair_records_blocks(a_p, b_p, blocks)
+    n_recs = int(recs.numel())
+    out_xz, out_c = ops.dedup_records(recs, a_p, a_cp, b_p, b_cp, zero_threshold)
+    return out_xz, out_c, {"cross_terms_generated": n_recs, "records_owned": n_recs, "rows_total_a": int(a_xz.shape[0])}
+
+
 def sharded_product(a_block_xz: torch.Tensor, a_block_c: torch.Tensor, b_xz: torch.Tensor, b_c: torch.Tensor,
-                    zero_threshold: Optional[float] = 1e-15, group=None):
+                    zero_threshold: Optional[float] = 1e-15, group=None, method: str = "owner"):
     """(A * B).cleanup() with A's rows sharded over the ranks (this rank holds a_block) and B
     replicated. Returns this rank's hash partition of the result as (xz, c) device tensors plus a
-    dict of sizes. Rows are unique across ranks."""
+    dict of sizes. Rows are unique across ranks.
+
+    method="owner" (default): exchange-free. Ownership is a GF(2)-linear function of the row, so
+      after one all-gather of A (25.6 MB at config C5) every rank generates exactly the cross
+      terms it owns (sym_class_partition + sym_pair_records_blocks) — no record crosses NVLink.
+    method="alltoall": every rank generates the records of its own block of A, partitions them by
+      owner (top hash bits) and routes them with one variable-size all-to-all (8 B per cross term)."""
     rank, world = _world(group)
     lg = log2_exact(world)
-    a_full, offsets = all_gather_rows(a_block_xz, group)
-    a_c_full, _ = all_gather_rows(a_block_c, group)
+    a_full, a_c_full, offsets = all_gather_operator(a_block_xz, a_block_c, group)
+    if method == "owner":
+        return owned_product(a_full, a_c_full, b_xz, b_c, lg, rank, zero_threshold)
+    if method != "alltoall":
+        raise ValueError(f"unknown method {method!r}")
     recs = ops.pair_records(a_full, offsets[rank], offsets[rank + 1], b_xz)
     if world > 1:
         part, counts = ops.partition_records(recs, lg)

@@ -374,6 +374,48 @@ def pair_records(a_xz, p_begin, p_end, b_xz):
     return recs
 
 
+def pair_records_blocks(a_xz, b_xz, blocks):
+    """Records of the rectangular blocks [(p0, p1, q0, q1), ...] of A x B, back to back in block order."""
+    M, W = _rows(a_xz)
+    N, _ = _rows(b_xz)
+    blocks = [tuple(int(v) for v in blk) for blk in blocks]
+    T = sum((p1 - p0) * (q1 - q0) for p0, p1, q0, q1 in blocks)
+    recs = torch.empty(T, dtype=torch.int64, device=a_xz.device)
+    if T == 0:
+        return recs
+    flat = (ctypes.c_int64 * (4 * len(blocks)))(*[v for blk in blocks for v in blk])
+    L = lib()
+    ws = workspace(L.sym_pair_records_ws_bytes(M, N, W))
+    _cabi.check(L.sym_pair_records_blocks(_p(a_xz), M, _p(b_xz), N, W, flat, len(blocks), _p(recs), _p(ws), ws.numel(),
+                                          _stream()))
+    return recs
+
+
+def owner_classes(xz, log2_parts):
+    """uint8[M]: owner class of every row (GF(2)-linear in the row, so class(a^b) = class(a)^class(b))."""
+    M, W = _rows(xz)
+    cls = torch.empty(M, dtype=torch.uint8, device=xz.device)
+    if M:
+        ws = workspace(8 * M + 512)
+        _cabi.check(lib().sym_owner_classes(_p(xz), M, W, int(log2_parts), _p(cls), _p(ws), ws.numel(), _stream()))
+    return cls
+
+
+def class_partition(xz, c, log2_parts):
+    """Stable grouping of an operator by owner class: (xz', c', perm int32[M], counts int64[parts])."""
+    M, W = _rows(xz)
+    dev = xz.device
+    out_xz = torch.empty_like(xz)
+    out_c = torch.empty_like(c) if c is not None else None
+    perm = torch.empty(M, dtype=torch.int32, device=dev)
+    counts = torch.zeros(1 << int(log2_parts), dtype=torch.int64, device=dev)
+    L = lib()
+    ws = workspace(L.sym_class_partition_ws_bytes(M))
+    _cabi.check(L.sym_class_partition(_p(xz), _p(_coeff(c)) if c is not None else _p(None), M, W, int(log2_parts),
+                                      _p(out_xz), _p(out_c), _p(perm), _p(counts), _p(ws), ws.numel(), _stream()))
+    return out_xz, out_c, perm, counts
+
+
 def partition_records(recs, log2_parts):
     """Stable partition by owner (top log2_parts bits); returns (recs_by_owner, counts int64[parts])."""
     T = recs.numel()

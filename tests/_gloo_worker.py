@@ -70,6 +70,46 @@ def main():
     ref_s, ref_c = po.multiply_by_operator(a_s, a_c, b_s, b_c)
     ok, why = po.compare_term_sets(all_s, all_c, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
     assert ok, why
+    # 4. operator all-gather (equal blocks gather straight into the result; ragged blocks are padded)
+    for sizes in ([5, 5], [4, 7]):
+        xz_blk = torch.full((sizes[rank], 6), rank + 1, dtype=torch.int64)
+        c_blk = torch.full((sizes[rank],), complex(rank, -rank), dtype=torch.complex128)
+        xz_full, c_full, offs = sdist.all_gather_operator(xz_blk, c_blk)
+        assert offs == [0, sizes[0], sizes[0] + sizes[1]]
+        assert bool((xz_full[:sizes[0]] == 1).all()) and bool((xz_full[sizes[0]:] == 2).all())
+        assert bool((c_full[:sizes[0]] == 0).all()) and bool((c_full[sizes[0]:] == complex(1, -1)).all())
+
+    # 5. exchange-free owner partition (the default product path) with the oracle standing in for the
+    #    kernels: class = a GF(2)-linear functional of the row, rank r multiplies class a of A with
+    #    class a^r of B; the union over ranks must equal the plain product with disjoint owners.
+    functional = np.random.default_rng(9).integers(0, 2, size=(2 * n, lg)).astype(np.int64)
+
+    def classes(symp):
+        bits = (symp.astype(np.int64) @ functional) & 1
+        return (bits << np.arange(lg)).sum(axis=1)
+
+    a_cls, b_cls = classes(a_s), classes(b_s)
+    a_ord, b_ord = np.argsort(a_cls, kind="stable"), np.argsort(b_cls, kind="stable")
+    a_p, a_cp, b_p, b_cp = a_s[a_ord], a_c[a_ord], b_s[b_ord], b_c[b_ord]
+    blocks = sdist.owner_blocks(np.bincount(a_cls, minlength=world).tolist(), np.bincount(b_cls, minlength=world).tolist(),
+                                rank)
+    assert sum((p1 - p0) * (q1 - q0) for p0, p1, q0, q1 in blocks) > 0
+    rows_l, coeff_l = [], []
+    for p0, p1, q0, q1 in blocks:
+        if p1 > p0 and q1 > q0:
+            r_, c_ = po.cross_terms(a_p[p0:p1], a_cp[p0:p1], b_p[q0:q1], b_cp[q0:q1])
+            assert np.all(classes(r_) == rank)                    # every generated term is mine
+            rows_l.append(r_)
+            coeff_l.append(c_)
+    loc_s, loc_c = po.symplectic_cleanup(np.vstack(rows_l), np.hstack(coeff_l), 1e-15)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (loc_s, loc_c, sum(len(r_) for r_ in rows_l)))
+    all_s = np.vstack([g[0] for g in gathered])
+    all_c = np.hstack([g[1] for g in gathered])
+    assert sum(g[2] for g in gathered) == M * N                   # every cross term generated exactly once
+    assert len(np.unique(all_s, axis=0)) == len(all_s)
+    ok, why = po.compare_term_sets(all_s, all_c, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
+    assert ok, why
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")

@@ -28,18 +28,20 @@ def main():
         a_blk_c = torch.from_numpy(a_c[lo:hi].copy()).to(dev)
         b = ops.pack(torch.from_numpy(b_s), n)
         bc = torch.from_numpy(b_c).to(dev)
-        xz, c, info = sdist.sharded_product(a_blk, a_blk_c, b, bc)
-        assert info["rows_total_a"] == M
-        loc = (ops.unpack(xz, n).cpu().numpy(), c.cpu().numpy())
-        gathered = [None] * world
-        dist.all_gather_object(gathered, loc)
-        if rank == 0:
-            s = np.vstack([g[0] for g in gathered])
-            cc = np.hstack([g[1] for g in gathered])
-            assert len(np.unique(s, axis=0)) == len(s), "owners overlap"
-            ref_s, ref_c = po.multiply_by_operator(a_s, a_c, b_s, b_c)
-            ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
-            assert ok, why
+        for method in ("owner", "alltoall"):
+            xz, c, info = sdist.sharded_product(a_blk, a_blk_c, b, bc, method=method)
+            assert info["rows_total_a"] == M
+            loc = (ops.unpack(xz, n).cpu().numpy(), c.cpu().numpy(), info["cross_terms_generated"])
+            gathered = [None] * world
+            dist.all_gather_object(gathered, loc)
+            if rank == 0:
+                s = np.vstack([g[0] for g in gathered])
+                cc = np.hstack([g[1] for g in gathered])
+                assert sum(g[2] for g in gathered) == M * N, method
+                assert len(np.unique(s, axis=0)) == len(s), "owners overlap"
+                ref_s, ref_c = po.multiply_by_operator(a_s, a_c, b_s, b_c)
+                ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
+                assert ok, (method, why)
         # commute row blocks
         a_full = ops.pack(torch.from_numpy(a_s), n)
         blk, row0 = sdist.sharded_commute(a_full, b)

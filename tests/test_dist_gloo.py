@@ -25,6 +25,15 @@ def test_block_bounds_and_log2():
         sdist.log2_exact(6)
 
 
+def test_owner_blocks():
+    blocks = sdist.owner_blocks([2, 0, 3, 1], [1, 1, 1, 4], 2)
+    # class a of A against class a ^ 2 of B
+    assert blocks == [(0, 2, 2, 3), (2, 2, 3, 7), (2, 5, 0, 1), (5, 6, 1, 2)]
+    total = sum(sum((p1 - p0) * (q1 - q0) for p0, p1, q0, q1 in sdist.owner_blocks([2, 0, 3, 1], [1, 1, 1, 4], r))
+                for r in range(4))
+    assert total == 6 * 7                                          # the owners tile the whole product
+
+
 def test_single_process_passthrough():
     import torch
     t = torch.arange(6, dtype=torch.int64)

@@ -328,3 +328,59 @@ def test_record_exchange_blocks_single_gpu(ops, log2g):
     assert len(np.unique(s, axis=0)) == len(s)            # owners hold disjoint rows
     ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
     assert ok, why
+
+
+def test_owner_classes_are_linear_and_partition_is_stable(ops):
+    """Ownership must be GF(2)-linear in the row (class(a^b) = class(a)^class(b)) and the class
+    grouping a stable permutation with the right counts."""
+    rng = np.random.default_rng(5)
+    for n in [3, 64, 200, 1000, 2100]:
+        a = rng.random((300, 2 * n)) < 0.3
+        b = rng.random((300, 2 * n)) < 0.3
+        for lg in [0, 1, 3, 8]:
+            ca = ops.owner_classes(ops.pack(torch.from_numpy(a), n), lg).cpu().numpy()
+            cb = ops.owner_classes(ops.pack(torch.from_numpy(b), n), lg).cpu().numpy()
+            cab = ops.owner_classes(ops.pack(torch.from_numpy(a ^ b), n), lg).cpu().numpy()
+            assert np.array_equal(ca ^ cb, cab)
+            assert ca.max(initial=0) < (1 << lg)
+        if n >= 64:
+            assert len(np.unique(ca)) > 100                           # 8 bits of 300 random rows: well spread
+        coeff = rng.standard_normal(300) + 1j * rng.standard_normal(300)
+        xz, c = dev_op(ops, a, coeff)
+        cls = ops.owner_classes(xz, 3).cpu().numpy()
+        p_xz, p_c, perm, counts = ops.class_partition(xz, c, 3)
+        order = np.argsort(cls, kind="stable")
+        assert np.array_equal(perm.cpu().numpy(), order)
+        assert np.array_equal(counts.cpu().numpy(), np.bincount(cls, minlength=8))
+        assert np.array_equal(ops.unpack(p_xz, n).cpu().numpy(), a[order])
+        assert np.array_equal(p_c.cpu().numpy(), coeff[order])
+
+
+@pytest.mark.parametrize("log2g", [0, 1, 2, 3])
+def test_exchange_free_owner_product_single_gpu(ops, log2g):
+    """The default multi-GPU product path on one device: every "rank" computes the part of the
+    product it owns from the full operands, with no exchange. The union over owners must equal the
+    oracle product, every cross term must be generated exactly once, and owners must be disjoint."""
+    from symmer_b200 import dist as sdist
+    for n, M, N in [(70, 96, 41), (1000, 130, 77), (4, 40, 40)]:
+        a_s, a_c = po.random_operator(n, M, seed=21)
+        b_s, b_c = po.random_operator(n, N, seed=22)
+        b_s[:20] = a_s[:20]                                   # duplicates across class blocks
+        ref_s, ref_c = po.multiply_by_operator(a_s, a_c, b_s, b_c)
+        a, ac = dev_op(ops, a_s, a_c)
+        b, bc = dev_op(ops, b_s, b_c)
+        rows, coeffs, generated = [], [], 0
+        for r in range(1 << log2g):
+            xz, c, info = sdist.owned_product(a, ac, b, bc, log2g, r)
+            generated += info["cross_terms_generated"]
+            if xz.shape[0]:
+                assert bool((ops.owner_classes(xz, log2g) == r).all())
+            s, cc = host_op(ops, xz, c, n)
+            rows.append(s)
+            coeffs.append(cc)
+        assert generated == M * N
+        s = np.vstack(rows)
+        cc = np.hstack(coeffs)
+        assert len(np.unique(s, axis=0)) == len(s)
+        ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
+        assert ok, (n, why)
