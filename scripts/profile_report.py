@@ -30,7 +30,7 @@ def launches(path, out, step_index=4):
     seq = read_launches(path)
     starts = [i for i, (n, _) in enumerate(seq) if n.startswith('pair_records_kernel')]
     # a step = from the two sketch/ycount launches before pair_records up to the emit kernel
-    emits = [i for i, (n, _) in enumerate(seq) if n.startswith('emit_kernel')]
+    emits = [i for i, (n, _) in enumerate(seq) if n.startswith('emit_')]
     k = min(step_index, len(starts) - 1)
     lo, hi = starts[k] - 4, emits[k] + 1
     step = seq[lo:hi]

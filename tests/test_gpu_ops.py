@@ -384,3 +384,46 @@ def test_exchange_free_owner_product_single_gpu(ops, log2g):
         assert len(np.unique(s, axis=0)) == len(s)
         ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
         assert ok, (n, why)
+
+
+@pytest.mark.parametrize("n,real", [(11, True), (12, False), (13, True), (14, False)])
+def test_binned_apply_kernel_matches_oracle_and_4row_kernel(ops, n, real):
+    """The Walsh-Hadamard binned kernel (16 / 8 basis rows per thread) against the oracle and against
+    the 4-row kernel, on operators whose x groups hold 1..many terms (molecular-like structure)."""
+    rng = np.random.default_rng(n)
+    n_groups, M = 37, 400
+    xs = rng.random((n_groups, n)) < 0.4
+    xs[0] = False                                               # a diagonal group
+    grp = np.concatenate([np.arange(n_groups), rng.integers(0, n_groups, size=M - n_groups)])
+    symp = np.hstack([xs[grp], rng.random((M, n)) < 0.5])
+    symp = np.unique(symp, axis=0)
+    M = symp.shape[0]
+    if real:   # real phased coefficients: only terms with an even number of Y survive, like a real Hamiltonian
+        symp = symp[(po.y_count(symp) % 2) == 0]
+        M = symp.shape[0]
+        coeff = rng.standard_normal(M).astype(complex)
+    else:
+        coeff = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    ref = po.pauli_apply_dense(symp, coeff, psi)
+    xz, c = dev_op(ops, symp, coeff)
+    xm, zm, cp = ops.term_masks_sorted(xz, c, n)
+    assert bool(ops._is_real(cp)) == real
+    psi_d = torch.from_numpy(psi).cuda()
+    out = {}
+    try:
+        for variant in (1, 0):
+            ops.set_tuning(4, variant)
+            y = ops.apply_dense(xm, zm, cp, n, psi_d).cpu().numpy()
+            assert np.allclose(y, ref, rtol=1e-12, atol=1e-13), variant
+            e = complex(ops.expval_dense(xm, zm, cp, n, psi_d).cpu().numpy())
+            assert np.isclose(e, np.vdot(psi, ref), rtol=1e-12, atol=1e-14), variant
+            quarter = (1 << n) // 4                             # sharded row ranges (multi-GPU expval)
+            parts = sum(complex(ops.expval_dense(xm, zm, cp, n, psi_d, k * quarter, (k + 1) * quarter).cpu().numpy())
+                        for k in range(4))
+            assert np.isclose(parts, e, rtol=1e-12, atol=1e-14), variant
+            out[variant] = y
+    finally:
+        ops.set_tuning(4, 1)
+    assert np.allclose(out[0], out[1], rtol=1e-13, atol=1e-14)
