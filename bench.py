@@ -159,7 +159,7 @@ def run_ours(args):
     def product(a, ac, b, bc):
         if world == 1:
             return ops.mul_cleanup(a, ac, b, bc, 1e-15)
-        xz, c, _ = sdist.sharded_product(a, ac, b, bc, 1e-15)
+        xz, c, _ = sdist.sharded_product(a, ac, b, bc, 1e-15, method=os.environ.get("SYMMER_DIST_METHOD", "owner"))
         return xz, c
 
     def barrier():

@@ -186,7 +186,10 @@ __global__ void total_to_i64_kernel(const uint32_t *__restrict__ total, int64_t 
 // 2*EMIT_UN independent 16-byte loads are in flight per thread (the kernel is latency-bound
 // otherwise). Stores are streaming (st.global.cs): the output is never re-read, and A/B must stay
 // L2-resident. LW: chunks per row = 1 << LW.
-int g_emit_variant = 1;  // tuning knob 1: 1 = fused compaction + emission (default), 0 = two kernels
+// tuning knob 1: 0 = compaction kernel + emission kernel (default; measured fastest on B200: 7.1 ms for 1.25e8
+// rows of 272 B against 8.8 ms for the CTA-fused form, whose barrier between the two phases stalls the block),
+// 1 = CTA-fused, 2 = warp-fused
+int g_emit_variant = 0;
 
 __device__ __forceinline__ void store_streaming(uint4 *p, const uint4 &v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -289,6 +292,66 @@ __global__ void __launch_bounds__(256) emit_fused_kernel(Rows rows, RecFmt fmt, 
     for (int u = 0; u < UN; ++u) {
         const uint32_t r = u * ROWS_PP + r_in;
         if (r < count) out_xz[(((size_t)base + r) << LW) + c] = v[u];
+    }
+}
+
+// Warp-level form of the fused compaction + emission: a warp owns 32 consecutive dedup positions, so
+// there is no CTA barrier and no idle half block. Phase 1: lane = position (survivor -> (p, q) handle
+// in the warp's shared-memory slice, coefficient straight to out_c); phase 2: lane = (row, 16-byte
+// chunk), 8 rows in flight per lane.
+template <class Rows, bool BY_T, int LW>
+__global__ void __launch_bounds__(256) emit_warp_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr,
+                                                         const uint8_t *__restrict__ keep, const uint8_t *__restrict__ multi,
+                                                         const uint32_t *__restrict__ slot, const double2 *__restrict__ acc,
+                                                         int64_t T, uint4 *__restrict__ out_xz, double2 *__restrict__ out_c) {
+    constexpr int RPP = 32 >> LW;            // rows per pass of one warp
+    constexpr int UN = (RPP * 8 <= 32) ? 8 : (32 / RPP);   // passes in flight
+    __shared__ uint2 s_h[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t d0 = ((int64_t)blockIdx.x * 8 + wid) * 32;
+    if (d0 >= T) return;
+    const int64_t d = d0 + lane;
+    const uint8_t k = d < T ? keep[d] : 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, k != 0);
+    if (bal == 0u) return;
+    uint32_t base = lane == 0 ? slot[d0] : 0u;
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (k) {
+        const uint32_t local = __popc(bal & ((1u << lane) - 1u));
+        uint32_t t;
+        int e = 0;
+        if (BY_T) {
+            t = (uint32_t)d;
+        } else {
+            const uint64_t rec = sr[d];
+            t = fmt.t(rec);
+            e = fmt.e(rec);
+        }
+        s_h[wid][local] = rows.locate(t);
+        if (multi[d]) {
+            out_c[base + local] = acc[d];
+        } else {
+            double re, im;
+            rows.coeff(t, e, re, im);
+            out_c[base + local] = make_double2(re, im);
+        }
+    }
+    __syncwarp();
+    const int count = __popc(bal);
+    const int r_in = lane >> LW;
+    const int c = lane & ((1 << LW) - 1);
+    for (int r0 = 0; r0 < count; r0 += RPP * UN) {
+        uint4 v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int r = r0 + u * RPP + r_in;
+            if (r < count) v[u] = rows.chunk_at(s_h[wid][r], c);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int r = r0 + u * RPP + r_in;
+            if (r < count) out_xz[(((size_t)base + r) << LW) + c] = v[u];
+        }
     }
 }
 
@@ -446,6 +509,21 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
         return SYM_OK;
     }
 #undef EMIT_FUSED
+#define EMIT_WARP(LW)                                                                                           \
+    emit_warp_kernel<Rows, BY_T, LW><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(rows, fmt, sr, L.keep, L.multi, L.slot,  \
+                                                                                 L.acc, T, o, oc)
+    if (g_emit_variant == 2 && (chunks == 1 || chunks == 2 || chunks == 4 || chunks == 8 || chunks == 16)) {
+        switch (chunks) {
+            case 1: EMIT_WARP(0); break;
+            case 2: EMIT_WARP(1); break;
+            case 4: EMIT_WARP(2); break;
+            case 8: EMIT_WARP(3); break;
+            default: EMIT_WARP(4); break;
+        }
+        SYM_LAUNCH_OK();
+        return SYM_OK;
+    }
+#undef EMIT_WARP
     // two-kernel form (tuning knob 1 = 0, and the generic chunk counts): compaction, then row emission
     compact_kernel<Rows, BY_T><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(rows, fmt, sr, L.keep, L.multi, L.slot, L.acc, T,
                                                                            L.kept, oc);
