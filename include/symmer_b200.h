@@ -155,6 +155,15 @@ int sym_to_csr(const int64_t *z_masks, const double *c_phased, int64_t M, int32_
 size_t sym_rref_ws_bytes(int64_t R);
 int sym_rref(uint64_t *bits, int64_t R, int64_t C, int64_t Cw, int32_t *pivots, void *ws,
              size_t ws_bytes, void *stream);
+/* Column reduction (_cref_binary / cref_binary, utils.py:337-359; generator_reconstruction,
+ * base.py:523-560) works on the transpose. sym_bit_transpose: in uint64[R][Cw_in] (R rows of
+ * Cw_in*64 bit columns) -> out uint64[Cw_in*64][Cw_out], Cw_out >= ceil(R/64); bits beyond R are 0.
+ * sym_or_rows: out[k] = OR_i bits[rows[i]][k] over n_rows selected rows (rows == NULL: rows 0..n_rows-1)
+ * — the "all remaining columns are zero" test of generator_reconstruction. */
+int sym_bit_transpose(const uint64_t *in, int64_t R, int64_t Cw_in, uint64_t *out, int64_t Cw_out,
+                      void *stream);
+int sym_or_rows(const uint64_t *bits, int64_t Cw, const int32_t *rows, int64_t n_rows, uint64_t *out,
+                void *stream);
 /* bool[R][C] <-> packed uint64[R][Cw] helpers for the GF(2) matrices (any C). */
 int sym_pack_matrix(const uint8_t *m, int64_t R, int64_t C, uint64_t *bits, int64_t Cw, void *stream);
 int sym_unpack_matrix(const uint64_t *bits, int64_t R, int64_t C, int64_t Cw, uint8_t *m, void *stream);
@@ -217,9 +226,16 @@ int sym_dedup_records(uint64_t *recs, int64_t T, const uint64_t *a_xz, const dou
 size_t sym_sort_pairs_ws_bytes(int64_t T);
 int sym_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t T, int32_t begin_bit, void *ws,
                    size_t ws_bytes, void *stream);
-/* Tuning knobs. which = 0: cross-term count up to which sym_mul_cleanup emits in first-occurrence
- * (reference) order instead of sorted-hash order (default 2^22). */
+/* Tuning knobs (A/B switches kept for measurement). which = 0: cross-term count up to which
+ * sym_mul_cleanup emits in first-occurrence (reference) order instead of sorted-hash order (default
+ * 2^22); 1: row emission (0 two kernels, 1 CTA-fused, 2 warp-fused); 2: radix scatter shape;
+ * 3: extra sort bits; 4: apply/expval kernel (1 binned, 0 four-row); 5: GF(2) large path (1 blocked
+ * panels, 0 one pivot per sweep). */
 int sym_set_tuning(int32_t which, int64_t value);
+/* Measurement hook: two cudaEvent_t (as void*, NULL to disable) recorded on the stream immediately
+ * before and after the row-emission kernel (emit_kernel) of the next *_emit calls, so that a
+ * benchmark can time the dominant kernel alone with CUDA events. */
+int sym_set_emit_events(void *before_event, void *after_event);
 /* Test hook: AND every dedup key with this mask (default ~0) to force sketch collisions. */
 int sym_debug_set_key_mask(uint64_t mask);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */

@@ -44,6 +44,8 @@ SIGNATURES = {
     "sym_to_csr": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "sym_rref_ws_bytes": (c_sz, [c_i64]),
     "sym_rref": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
+    "sym_bit_transpose": (ctypes.c_int, [c_p, c_i64, c_i64, c_p, c_i64, c_p]),
+    "sym_or_rows": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p]),
     "sym_pack_matrix": (ctypes.c_int, [c_p, c_i64, c_i64, c_p, c_i64, c_p]),
     "sym_unpack_matrix": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     "sym_pair_records_ws_bytes": (c_sz, [c_i64, c_i64, c_i32]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "sym_dedup_records_emit": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_i64, c_p, c_p,
                                               c_p, c_sz, c_p]),
     "sym_set_tuning": (ctypes.c_int, [c_i32, c_i64]),
+    "sym_set_emit_events": (ctypes.c_int, [c_p, c_p]),
     "sym_sort_pairs_ws_bytes": (c_sz, [c_i64]),
     "sym_sort_pairs": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_sz, c_p]),
     "sym_debug_set_key_mask": (ctypes.c_int, [c_u64]),

@@ -469,15 +469,41 @@ class PauliwordOp:
         return gens
 
     def generator_reconstruction(self, generators: "PauliwordOp", override_independence_check: bool = False):
-        """base.py:523-560: column reduction of [[B],[M]] -> [[I 0],[R F]]."""
-        from .utils import check_independent, cref_binary
+        """base.py:523-560: column reduction of [[B],[M]] -> [[I 0],[R F]]; returns (R as int[M, dim],
+        mask of the rows whose F part is zero).
+
+        Device-resident: the packed rows of [B; M] are bit-transposed (the reference's cref_binary is
+        rref_binary on the transpose, utils.py:349-359), reduced with the bit-exact GF(2) kernel, the
+        pivot rows ordered by pivot column (rref_binary's order, zero rows last), and only R and the
+        mask travel back to the host. Padding bit positions of the packed layout become all-zero
+        rows of the transpose; they never pivot and sort last, so the result is unchanged."""
+        from .utils import check_independent
         if not override_independence_check:
             assert check_independent(generators), 'Supplied generators are algebraically dependent'
-        dim = generators.n_terms
-        stack = np.vstack([generators.symp_matrix, self.symp_matrix])
-        reduced = cref_binary(stack)
-        mask = np.all(~reduced[dim:, dim:], axis=1)
-        return reduced[dim:, :dim].astype(int), mask
+        assert (self.n_qubits == generators.n_qubits), 'Pauliwords defined for different number of qubits'
+        dim, M = generators.n_terms, self.n_terms
+        if M == 0 or self.n_qubits == 0:
+            return np.zeros((M, dim), dtype=int), np.ones(M, dtype=bool)
+        stack = torch.cat([generators._xz, self._xz], dim=0).contiguous()
+        T = ops.bit_transpose(stack)                                  # [2W*64 bit positions][ceil((dim+M)/64)]
+        piv = ops.rref_packed(T, dim + M).cpu().numpy()
+        nz = np.flatnonzero(piv >= 0)
+        order = nz[np.argsort(piv[nz], kind='stable')]                # pivot rows by pivot column
+        dev = T.device
+        recon = np.zeros((M, dim), dtype=int)
+        first = order[:dim]
+        if len(first):
+            sub = T.index_select(0, torch.as_tensor(first, dtype=torch.int64, device=dev)).contiguous()
+            back = ops.bit_transpose(sub)                             # [columns of [B; M]][ceil(len(first)/64)]
+            recon[:, :len(first)] = ops.unpack_matrix(back[dim:dim + M].contiguous(), len(first)).cpu().numpy()
+        rest = order[dim:]
+        if len(rest):
+            used = ops.or_rows(T, torch.as_tensor(rest, dtype=torch.int32, device=dev))
+            used = ops.unpack_matrix(used.reshape(1, -1), dim + M).cpu().numpy()[0, dim:]
+            mask = ~used
+        else:
+            mask = np.ones(M, dtype=bool)
+        return recon, mask
 
 
 def _i_pow(k: torch.Tensor) -> torch.Tensor:

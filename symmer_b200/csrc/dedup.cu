@@ -191,6 +191,13 @@ __global__ void total_to_i64_kernel(const uint32_t *__restrict__ total, int64_t 
 // 1 = CTA-fused, 2 = warp-fused
 int g_emit_variant = 0;
 
+// optional CUDA events recorded around the row-emission kernel (sym_set_emit_events)
+static cudaEvent_t g_emit_ev0 = nullptr, g_emit_ev1 = nullptr;
+void set_emit_events(cudaEvent_t a, cudaEvent_t b) {
+    g_emit_ev0 = a;
+    g_emit_ev1 = b;
+}
+
 __device__ __forceinline__ void store_streaming(uint4 *p, const uint4 &v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -528,6 +535,7 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
     compact_kernel<Rows, BY_T><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(rows, fmt, sr, L.keep, L.multi, L.slot, L.acc, T,
                                                                            L.kept, oc);
     SYM_LAUNCH_OK();
+    if (g_emit_ev0) SYM_CUDA_OK(cudaEventRecord(g_emit_ev0, st));   // bench.py times the row-emission kernel alone
 #define EMIT_LAUNCH(LW, UN, CS)                                                                   \
     {                                                                                             \
         const uint32_t rows_per_block = (256u >> LW) * UN;                                        \
@@ -547,6 +555,7 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
     }
 #undef EMIT_LAUNCH
     SYM_LAUNCH_OK();
+    if (g_emit_ev1) SYM_CUDA_OK(cudaEventRecord(g_emit_ev1, st));
     return SYM_OK;
 }
 

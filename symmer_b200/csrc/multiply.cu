@@ -350,7 +350,7 @@ extern "C" size_t sym_mul_cleanup_ws_bytes(int64_t M, int64_t N, int32_t W) {
 // Below this many cross terms the product is emitted in first-occurrence (reference) order; above,
 // in sorted-hash order, which keeps every pass of the dedup streaming (no T-sized scatters).
 static int64_t g_by_t_limit = (int64_t)1 << 22;
-namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; }
+namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; extern int g_rref_variant; }
 
 extern "C" int sym_set_tuning(int32_t which, int64_t value) {
     if (which == 0) {
@@ -373,8 +373,17 @@ extern "C" int sym_set_tuning(int32_t which, int64_t value) {
         symb::g_apply_variant = (int)value;
         return SYM_OK;
     }
+    if (which == 5) {
+        symb::g_rref_variant = (int)value;
+        return SYM_OK;
+    }
     set_error("unknown tuning knob %d", which);
     return SYM_E_INVALID;
+}
+
+extern "C" int sym_set_emit_events(void *before_event, void *after_event) {
+    symb::set_emit_events((cudaEvent_t)before_event, (cudaEvent_t)after_event);
+    return SYM_OK;
 }
 
 // workspace layout shared by the count and emit phases

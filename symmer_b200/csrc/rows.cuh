@@ -106,6 +106,7 @@ struct PlainRows {
 // 0..T-1 and the output is written in increasing-t (first occurrence) order; otherwise the output
 // is in sorted-hash order.
 size_t dedup_ws_bytes(int64_t T);
+void set_emit_events(cudaEvent_t before, cudaEvent_t after);
 int dedup_product_plan(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, bool by_t, double thr,
                        int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
 int dedup_product_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, bool by_t, int64_t U,

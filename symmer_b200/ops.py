@@ -16,11 +16,21 @@ _ws_cache = {}
 emit_events = None
 
 
+# (start, end) events recorded INSIDE the library around the row-emission kernel alone
+emit_kernel_events = None
+
+
 def _emit_begin():
     if emit_events is None:
         return None
     e = torch.cuda.Event(enable_timing=True)
     e.record()
+    if emit_kernel_events is not None:
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()          # instantiates the cudaEvent_t handles; the library re-records them
+        k1.record()
+        _cabi.check(lib().sym_set_emit_events(ctypes.c_void_p(k0.cuda_event), ctypes.c_void_p(k1.cuda_event)))
+        emit_kernel_events.append((k0, k1))
     return e
 
 
@@ -29,6 +39,8 @@ def _emit_end(start):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         emit_events.append((start, e))
+        if emit_kernel_events is not None:
+            _cabi.check(lib().sym_set_emit_events(None, None))
 
 
 def lib():
@@ -344,6 +356,25 @@ def rref_packed(bits, C):
     ws = workspace(L.sym_rref_ws_bytes(R))
     _cabi.check(L.sym_rref(_p(bits), R, C, Cw, _p(piv), _p(ws), ws.numel(), _stream()))
     return piv
+
+
+def bit_transpose(bits):
+    """int64[R, Cw] bit matrix (Cw*64 columns) -> int64[Cw*64, ceil(R/64)]."""
+    assert bits.is_cuda and bits.dtype == torch.int64 and bits.dim() == 2 and bits.is_contiguous()
+    R, Cw = bits.shape
+    Cw_out = max(1, (R + 63) // 64)
+    out = torch.empty((Cw * 64, Cw_out), dtype=torch.int64, device=bits.device)
+    _cabi.check(lib().sym_bit_transpose(_p(bits), R, Cw, _p(out), Cw_out, _stream()))
+    return out
+
+
+def or_rows(bits, rows=None):
+    """int64[Cw]: bitwise OR of the selected rows (int32 device indices; None = all rows)."""
+    R, Cw = bits.shape
+    out = torch.empty(Cw, dtype=torch.int64, device=bits.device)
+    n = R if rows is None else int(rows.numel())
+    _cabi.check(lib().sym_or_rows(_p(bits), Cw, _p(rows), n, _p(out), _stream()))
+    return out
 
 
 # ---------------------------------------------------------------------------------- sort / records

@@ -314,3 +314,31 @@ def test_zero_qubit_and_empty_operands(sb):
     assert (A * E).n_terms == 0 and (E * A).n_terms == 0
     assert (A + E) == A
     assert E.commutes_termwise(A).shape == (0, 1)
+
+
+def test_generator_reconstruction_device_path(sb):
+    """generator_reconstruction (base.py:523-560) on the device: bit-transposed packed rows, blocked
+    GF(2) reduction, R and the mask only travel back. Cases: full span, partial span (mask has False
+    entries and R rows are only partially built), padding bit positions (n not a multiple of 64), a
+    matrix wide enough for the blocked multi-launch path."""
+    rng = np.random.default_rng(12)
+    for n, n_gen, M in [(6, 4, 50), (40, 11, 300), (100, 30, 2000), (300, 25, 3000), (1000, 12, 200)]:
+        gens = rng.random((n_gen, 2 * n)) < 0.3
+        assert po.check_independent(gens)
+        combos = rng.random((M, n_gen)) < 0.4
+        symp = (combos.astype(np.uint8) @ gens.astype(np.uint8) % 2).astype(bool)   # inside the span
+        outside = rng.random(M) < 0.2
+        symp[outside] ^= rng.random((int(outside.sum()), 2 * n)) < 0.05            # mostly outside the span
+        G = sb.PauliwordOp(gens, np.ones(n_gen))
+        P = sb.PauliwordOp(symp, np.ones(M))
+        recon, mask = P.generator_reconstruction(G)
+        ref_recon, ref_mask = po.generator_reconstruction(gens, symp)
+        assert recon.shape == (M, n_gen) and recon.dtype == ref_recon.dtype
+        assert np.array_equal(mask, ref_mask), n
+        assert np.array_equal(recon, ref_recon), n                                   # bit-exact, failed rows included
+        assert mask[~outside].all() and not mask.all()
+        ok = mask
+        assert np.array_equal((recon[ok] @ gens.astype(int)) % 2, symp[ok].astype(int))   # M = R B on the span
+    with pytest.raises(AssertionError):
+        dep = sb.PauliwordOp(np.vstack([gens[:2], gens[0] ^ gens[1]]), np.ones(3))
+        P.generator_reconstruction(dep)

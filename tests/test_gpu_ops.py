@@ -214,12 +214,32 @@ def test_gf2_golden(ops, golden):
         assert np.array_equal(piv.cpu().numpy(), exp_piv), nm
 
 
-def test_gf2_large_path(ops):
-    rng = np.random.default_rng(3)
-    m = rng.random((300, 9000)) < 0.02        # 300 x 141 words > 200 KB: multi-launch path
+def _rref_check(ops, m):
     bits = ops.pack_matrix(torch.from_numpy(m))
-    ops.rref_packed(bits, m.shape[1])
-    assert np.array_equal(ops.unpack_matrix(bits, m.shape[1]).cpu().numpy(), po._rref_binary(m))
+    piv = ops.rref_packed(bits, m.shape[1]).cpu().numpy()
+    ref = po._rref_binary(m)
+    assert np.array_equal(ops.unpack_matrix(bits, m.shape[1]).cpu().numpy(), ref)
+    assert np.array_equal(piv, np.array([np.flatnonzero(r)[0] if r.any() else -1 for r in ref]))
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_gf2_large_path(ops, variant):
+    """Matrices beyond one CTA's shared memory: blocked panels (variant 1, default) and the
+    one-pivot-per-sweep form (variant 0), both bit-exact with the row-driven rule of _rref_binary."""
+    rng = np.random.default_rng(3)
+    try:
+        ops.set_tuning(5, variant)
+        _rref_check(ops, rng.random((300, 9000)) < 0.02)          # wide, sparse: 300 x 141 words
+        _rref_check(ops, rng.random((131, 20000)) < 0.5)          # wide, dense, rows not a multiple of the panel
+        tall = rng.random((3000, 700)) < 0.3                      # tall: rank 700, most rows reduce to zero
+        tall[50:60] = 0                                           # zero rows inside a panel
+        tall[100] = tall[7]                                       # duplicate rows
+        _rref_check(ops, tall)
+        low = (rng.random((400, 12)) < 0.5).astype(np.uint8) @ (rng.random((12, 8000)) < 0.5).astype(np.uint8) % 2
+        _rref_check(ops, low.astype(bool))                        # rank <= 12: panels full of dependent rows
+        _rref_check(ops, rng.random((40, 50000)) < 0.001)         # panels of fewer rows (4 per panel at 782 words)
+    finally:
+        ops.set_tuning(5, 1)
 
 
 def test_apply_expval_csr(ops, golden):
