@@ -168,6 +168,21 @@ int sym_or_rows(const uint64_t *bits, int64_t Cw, const int32_t *rows, int64_t n
 int sym_pack_matrix(const uint8_t *m, int64_t R, int64_t C, uint64_t *bits, int64_t Cw, void *stream);
 int sym_unpack_matrix(const uint64_t *bits, int64_t R, int64_t C, int64_t Cw, uint8_t *m, void *stream);
 
+/* ---- S3Projection._perform_projection (symmer/projection/base.py:44-84) on packed rows.
+ * The S stabilizers are single-qubit Paulis: stab_cols[j] (device int32) is the column of stabilizer
+ * j's single set bit in the [X | Z] symplectic layout (q < n: X_q, n + q: Z_q), stab_eigs[j] (device
+ * double) its +/-1 eigenvalue. Rows anticommuting with any stabilizer are dropped; the coefficient
+ * of a kept row is multiplied by the eigenvalue of every stabilizer whose Pauli appears in it; the
+ * kept rows are written over the n_free free qubits only (free_qubits: device int32, ascending;
+ * output layout uint64[*][2*W'], W' = max(1, ceil(n_free/64))) in input order. out_xz / out_c must
+ * hold M rows. n_out (device int64, may be NULL) / n_out_host (may be NULL; forces one stream
+ * synchronise) receive the number of kept rows. Duplicates are NOT merged: follow with sym_cleanup. */
+size_t sym_project_ws_bytes(int64_t M, int32_t n_free);
+int sym_project(const uint64_t *xz, const double *c, int64_t M, int32_t W, int32_t n_qubits,
+                const int32_t *stab_cols, const double *stab_eigs, int32_t S, const int32_t *free_qubits,
+                int32_t n_free, uint64_t *out_xz, double *out_c, int64_t *n_out, int64_t *n_out_host,
+                void *ws, size_t ws_bytes, void *stream);
+
 /* ---- multi-GPU building blocks: the product path split at its exchange point.
  * A record is one 64-bit word  [ hash : 62-tb bits | t : tb bits | e : 2 bits ]  with
  * hash = top bits of mix64(sketch(A[p]) ^ sketch(B[q])), t = global flattened cross-term index

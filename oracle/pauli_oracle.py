@@ -505,6 +505,39 @@ def generator_reconstruction(gen_symp: np.ndarray, op_symp: np.ndarray):
 
 
 # ----------------------------------------------------------------------------------------------
+# f2  stabilizer-subspace projection                                  projection/base.py:44-84
+# ----------------------------------------------------------------------------------------------
+
+def project_onto_stabilizers(symp, coeff, stab_symp, stab_coeff, free_qubits):
+    """S3Projection._perform_projection (projection/base.py:44-84) on plain arrays: `symp` is the
+    operator AFTER the stabilizer rotations, `stab_symp`/`stab_coeff` the rotated single-qubit
+    stabilizers with their +/-1 eigenvalues, `free_qubits` the qubit positions that survive."""
+    symp = np.asarray(symp, dtype=bool)
+    coeff = np.asarray(coeff, dtype=complex)
+    stab_symp = np.asarray(stab_symp, dtype=bool)
+    n = symp.shape[1] // 2
+    keep = np.all(commutes_termwise(symp, stab_symp), axis=1)            # :63
+    kept_s, kept_c = symp[keep], coeff[keep]                             # :64-65
+    idx = np.where(stab_symp)[1]                                         # :69
+    eig = kept_s[:, idx] * np.asarray(stab_coeff)                        # :70
+    eig[eig == 0] = 1                                                    # :71
+    kept_c = kept_c * np.prod(eig, axis=1).T                             # :72
+    free = np.asarray(free_qubits, dtype=int)
+    proj = kept_s[:, np.hstack([free, free + n])]                        # :75-77
+    if proj.shape[1]:
+        return cleanup(proj, kept_c)                                     # :82
+    return np.zeros((1, 0), dtype=bool), np.array([np.sum(kept_c)])      # :84
+
+
+def taper(symp, coeff, rotations, stab_symp, stab_coeff, free_qubits):
+    """S3Projection.perform_projection (projection/base.py:116-124) given the rotation list and the
+    rotated stabilizers: Clifford rotations (angle None = pi/2), then the projection."""
+    if len(rotations):
+        symp, coeff = perform_rotations(symp, coeff, [(r, None) for r in rotations])
+    return project_onto_stabilizers(symp, coeff, stab_symp, stab_coeff, free_qubits)
+
+
+# ----------------------------------------------------------------------------------------------
 # a2  benchmark input generator                                       base.py:82-107, utils.py:281-290
 # ----------------------------------------------------------------------------------------------
 

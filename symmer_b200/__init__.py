@@ -6,7 +6,7 @@ owns the memory) and every kernel is reached through the C ABI of include/symmer
 """
 from . import _cabi  # noqa: F401  (raises if the CUDA library is missing and cannot be built)
 
-__all__ = ["PauliwordOp", "QuantumState", "IndependentOp"]
+__all__ = ["PauliwordOp", "QuantumState", "IndependentOp", "QubitTapering", "S3Projection"]
 
 
 def __getattr__(name):
@@ -16,4 +16,7 @@ def __getattr__(name):
     if name == "IndependentOp":
         from .independent_op import IndependentOp
         return IndependentOp
+    if name in ("QubitTapering", "S3Projection"):
+        from . import projection
+        return getattr(projection, name)
     raise AttributeError(name)

@@ -588,6 +588,10 @@ class QuantumState:
         return QuantumState._from_x_rows(self.state_op._xz, c / torch.linalg.vector_norm(c), self.n_qubits,
                                          self.vec_type)
 
+    def _is_normalized(self) -> bool:
+        """base.py:1964-1976."""
+        return bool(np.isclose(np.sum(abs(self.state_op.coeff_vec) ** 2), 1))
+
     def _bit_keys(self):
         """(sketch keys, packed X rows) used to join two states on equal bit strings."""
         W = self.state_op._xz.shape[1] // 2

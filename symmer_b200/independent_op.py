@@ -1,11 +1,12 @@
 """IndependentOp with the reference's API (symmer/operators/independent_op.py) on the B200 engine:
 algebraically independent stabilizer sets and the symmetry-generator search (config C2)."""
 import warnings
+from typing import List, Tuple, Union
 
 import numpy as np
 
-from .base import PauliwordOp
-from .utils import _cref_binary, check_independent
+from .base import PauliwordOp, QuantumState, single_term_expval
+from .utils import _cref_binary, check_independent, symplectic_to_string
 
 
 class IndependentOp(PauliwordOp):
@@ -69,3 +70,127 @@ class IndependentOp(PauliwordOp):
             keep = sorted(groups[0])
             warnings.warn('Greedy method may identify non-optimal commuting symmetry terms; might be able to taper again.')
         return cls(S.symp_matrix[keep], np.ones(len(keep), dtype=complex))
+
+    # ------------------------------------------------------------------ container behaviour
+    def __str__(self) -> str:
+        return ' \n'.join(f'{c} {symplectic_to_string(row)}' for row, c in zip(self.symp_matrix, self.coeff_vec))
+
+    def __repr__(self) -> str:
+        return str(self)
+
+    def __add__(self, Pword: "IndependentOp") -> "IndependentOp":
+        return self.from_PauliwordOp(PauliwordOp.__add__(self, Pword))
+
+    def __getitem__(self, key) -> "IndependentOp":
+        """independent_op.py:316-350: indexing re-validates the selection as an IndependentOp."""
+        sub = PauliwordOp.__getitem__(self, key)
+        return IndependentOp(sub.symp_matrix, sub.coeff_vec)
+
+    def __iter__(self):
+        return iter([self[i] for i in range(self.n_terms)])
+
+    # ------------------------------------------------------------------ Clifford rotations onto single-qubit Paulis
+    def _rotate_by_single_Pword(self, Pword: PauliwordOp, angle: float = None) -> "IndependentOp":
+        """independent_op.py:186-190. The rotation search below picks pivots by row position, so the
+        row order of the reference's Clifford branch (anticommuting rows first, then the commuting
+        ones; base.py:1151-1154) is reproduced here — these operators have at most n rows, the
+        reordering is a host-side gather."""
+        rotated = PauliwordOp._rotate_by_single_Pword(self, Pword, angle)
+        multiple = (np.pi / 2 if angle is None else complex(angle).real) * 2 / np.pi
+        if rotated.n_terms == self.n_terms and abs(round(multiple) - multiple) <= 1e-18:
+            commutes = self.commutes_termwise(Pword)[:, 0]
+            if not commutes.all():
+                # the reference forms the anticommuting part with `*`, whose cleanup drops zero coefficients
+                anti = np.flatnonzero(~commutes & (abs(self.coeff_vec) > 1e-15))
+                rotated = rotated._take(np.concatenate([anti, np.flatnonzero(commutes)]))
+        return self.from_PauliwordOp(rotated)
+
+    def perform_rotations(self, rotations: List[Tuple[PauliwordOp, float]]) -> "IndependentOp":
+        """independent_op.py:192-204 (a dedup after every rotation, like base.py:1184-1185)."""
+        op = self
+        for generator, angle in rotations:
+            op = self.from_PauliwordOp(op._rotate_by_single_Pword(generator, angle).cleanup())
+        return self.from_PauliwordOp(op) if op is self else op
+
+    def _recursive_rotations(self, basis: "IndependentOp") -> None:
+        """independent_op.py:204-241. Peel off the rows that already are single-qubit Paulis, then
+        rotate the lightest remaining row onto a single-qubit Pauli on its least-supported unused
+        qubit, and repeat on the rotated remainder."""
+        n = self.n_qubits
+        symp, coeff = basis.symp_matrix, basis.coeff_vec
+        weight = symp.sum(axis=1)
+        single = weight == 1
+        # the reference finds the single-qubit rows as `basis - rest`, whose cleanup drops zero coefficients
+        done = np.flatnonzero(single & (abs(coeff) > 1e-15))
+        qubits = np.array([np.flatnonzero(symp[i])[0] % n for i in done], dtype=int)
+        self.used_indices += np.append(qubits, qubits + n).tolist()
+        rest_symp, rest_coeff = symp[~single], coeff[~single]
+        if rest_symp.shape[0] == 0:
+            return None
+        rest = IndependentOp(rest_symp, rest_coeff)
+        pivot_row = rest_symp[np.argsort(rest_symp.sum(axis=1))][0]
+        candidates = np.setdiff1d(np.flatnonzero(pivot_row), np.array(self.used_indices))
+        support = pivot_row * rest_symp.sum(axis=0)
+        pivot_point = candidates[np.argmin(support[candidates])]
+        # rotate onto the OTHER Pauli type of that qubit: X column q -> Z_q, Z column n+q -> X_q
+        target = np.zeros(2 * n, dtype=bool)
+        target[pivot_point + n if pivot_point < n else pivot_point - n] = True
+        rotation = PauliwordOp(target ^ pivot_row, [1])
+        self.stabilizer_rotations.append((rotation, None))
+        return self._recursive_rotations(rest._rotate_by_single_Pword(rotation))
+
+    def generate_stabilizer_rotations(self) -> None:
+        """independent_op.py:243-273: the pi/2 rotations mapping this set onto single-qubit Paulis of
+        type target_sqp."""
+        assert (self.n_terms <= self.n_qubits), 'Too many terms in basis to reduce to single-qubit Paulis'
+        assert (np.all(self.adjacency_matrix)), 'The basis is not commuting, hence the rotation is not possible'
+        self.stabilizer_rotations = []
+        self.used_indices = []
+        basis = self.copy()
+        basis = IndependentOp(basis.symp_matrix, basis.coeff_vec)
+        self._recursive_rotations(basis)
+        rotated = basis.perform_rotations(self.stabilizer_rotations)
+        n = self.n_qubits
+        for row in rotated.symp_matrix:
+            q = np.flatnonzero(row)[0] % n
+            target = np.zeros(2 * n, dtype=bool)
+            target[q] = self.target_sqp in ['X', 'Y']
+            target[q + n] = self.target_sqp in ['Y', 'Z']
+            fix = target ^ row
+            if fix.any():                                   # already the target Pauli otherwise
+                self.stabilizer_rotations.append((PauliwordOp(fix, [1]), None))
+
+    def rotate_onto_single_qubit_paulis(self) -> "IndependentOp":
+        """independent_op.py:299-314: the stabilizers after the rotations, in their original order
+        (the device Clifford kernel rewrites rows in place, so one pass keeps the order that the
+        reference obtains by rotating the stabilizers one at a time)."""
+        self.generate_stabilizer_rotations()
+        if not self.stabilizer_rotations:
+            return self
+        op = PauliwordOp._from_device(self.device_rows, self.device_coeffs, self.n_qubits)
+        for generator, angle in self.stabilizer_rotations:
+            op, _ = op._rotation_step(generator, angle)
+        keep = np.flatnonzero(abs(op.coeff_vec) > 1e-15)    # the per-stabilizer cleanup of the reference
+        return IndependentOp(op.symp_matrix[keep], op.coeff_vec[keep])
+
+    # ------------------------------------------------------------------ sector assignment
+    def update_sector(self, ref_state: Union[List[int], np.ndarray, QuantumState], threshold: float = 0.5) -> None:
+        """independent_op.py:275-297: measure every stabilizer on the reference state; +/-1 when the
+        expectation value is decisive, 0 otherwise (with a warning)."""
+        if not isinstance(ref_state, QuantumState):
+            ref_state = QuantumState(ref_state)
+        assert ref_state._is_normalized(), 'Reference state is not normalized.'
+        self.coeff_vec = np.array(assign_value(self, ref_state), dtype=complex)
+        if np.any(self.coeff_vec == 0):
+            zero = [symplectic_to_string(r) for r in self.symp_matrix[self.coeff_vec == 0]]
+            warnings.warn(f'The stabilizers {zero} were assigned zero values - bad reference state.')
+
+
+def assign_value(S: PauliwordOp, ref_state: QuantumState, threshold: float = 0.5) -> List[int]:
+    """independent_op.py:364-383, evaluated term by term on the device (never through
+    process.parallelize: no fork after CUDA initialisation)."""
+    values = []
+    for i in range(S.n_terms):
+        e = single_term_expval(PauliwordOp.__getitem__(S, i), ref_state)
+        values.append(int(np.sign(e)) if abs(e) > threshold else 0)
+    return values

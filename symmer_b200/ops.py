@@ -263,6 +263,29 @@ def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0):
     return out_xz, out_c
 
 
+# -------------------------------------------------------------------------------------- projection
+def project(xz, c, n_qubits, stab_cols, stab_eigs, free_qubits):
+    """Stabilizer-subspace projection of rotated rows (no duplicate merge): returns (xz', c') over the
+    free qubits, rows that anticommute with a single-qubit stabilizer dropped, signs fixed."""
+    M, W = _rows(xz)
+    dev = xz.device
+    cols = torch.as_tensor(stab_cols, dtype=torch.int32, device=dev).contiguous()
+    eigs = torch.as_tensor(stab_eigs, dtype=torch.float64, device=dev).contiguous()
+    free = torch.as_tensor(free_qubits, dtype=torch.int32, device=dev).contiguous()
+    n_free = int(free.numel())
+    Wo = max(1, (n_free + 63) // 64)
+    out_xz = torch.empty((M, 2 * Wo), dtype=torch.int64, device=dev)
+    out_c = torch.empty(M, dtype=torch.complex128, device=dev)
+    if M == 0:
+        return out_xz, out_c
+    L = lib()
+    ws = workspace(L.sym_project_ws_bytes(M, n_free))
+    U = ctypes.c_int64(0)
+    _cabi.check(L.sym_project(_p(xz), _p(_coeff(c)), M, W, int(n_qubits), _p(cols), _p(eigs), int(cols.numel()), _p(free),
+                              n_free, _p(out_xz), _p(out_c), None, ctypes.byref(U), _p(ws), ws.numel(), _stream()))
+    return out_xz[:U.value], out_c[:U.value]
+
+
 # ------------------------------------------------------------------------------------- matrix-free
 def term_masks_sorted(xz, c, n_qubits):
     """Basis-index masks and phased coefficients of every term, sorted by x mask."""

@@ -44,6 +44,20 @@ def golden():
     return cases
 
 
+@pytest.fixture(scope="session")
+def taper_golden():
+    """Tapering workflow vectors produced by the real reference (tests/golden/make_golden_taper.py)."""
+    data = np.load(os.path.join(ROOT, "tests", "golden", "taper_vectors.npz"))
+    cases = {}
+    for key in data.files:
+        name, field = key.split("/", 1)
+        cases.setdefault(name, {})[field] = data[key]
+    for g in cases.values():
+        nq = int(g["n_out_qubits"][0])
+        g["out_symp"] = np.unpackbits(g["out_symp"], axis=1)[:, :2 * nq].astype(bool)
+    return cases
+
+
 def load_hamiltonian(tag):
     d = np.load(os.path.join(ROOT, "tests", "golden", "hamiltonians", tag + ".npz"))
     n = int(d["n_qubits"][0])

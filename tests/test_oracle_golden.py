@@ -158,3 +158,16 @@ def test_pack_unpack_roundtrip():
         assert np.array_equal(po.unpack_bits(xz, n), symp)
         q = n - 1
         assert bool((xz[0, q // 64] >> np.uint64(q % 64)) & np.uint64(1)) == bool(symp[0, q])
+
+
+def test_projection_oracle_against_reference_tapering(taper_golden, hamiltonians):
+    """The oracle's rotations + stabilizer-subspace projection reproduce the real reference's
+    QubitTapering.taper_it outputs (H2O, Be, NH3; target Pauli Z and X)."""
+    for tag in ["H2O_STO3G", "Be_STO3G", "NH3_STO3G"]:
+        symp, coeff, _ = hamiltonians(tag)
+        for sqp in ["Z", "X"]:
+            g = taper_golden[f"taper_{tag}_{sqp}"]
+            s, c = po.taper(symp, coeff, g["rotations"], g["rotated_symp"], g["rotated_coeff"], g["free"])
+            assert s.shape == g["out_symp"].shape, (tag, sqp)
+            ok, why = po.compare_term_sets(s, c, g["out_symp"], g["out_coeff"], scale=np.abs(coeff).max())
+            assert ok, (tag, sqp, why)
