@@ -137,10 +137,23 @@ int sym_apply(const int64_t *x_masks, const int64_t *z_masks, const double *c_ph
               int32_t n_qubits, const double *psi, double *y, int64_t row_begin, int64_t row_end,
               int32_t real_coeffs, void *stream);
 /* partial[0..1] += sum_{r in [row_begin,row_end)} conj(psi[r]) * (H psi)[r]  (device double[2],
- * zero it first). The 2^n basis shards over ranks by row range; all-reduce the two doubles. */
+ * zero it first). The 2^n basis shards over ranks by row range; all-reduce the two doubles.
+ * real_coeffs: 0 complex, 1 all phased coefficients real, 2 symmetric mode (see sym_expval_prepare_sym). */
 int sym_expval(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
                int32_t n_qubits, const double *psi, double *partial, int64_t row_begin, int64_t row_end,
                int32_t real_coeffs, void *stream);
+/* Symmetric expectation-value mode for Hermitian operators whose phased coefficients are all real
+ * (every term has an even number of Y and a real coefficient: molecular Hamiltonians). The pair of
+ * basis rows (r, r ^ x) contributes a complex-conjugate pair, so a group of terms whose x mask has
+ * its highest set bit h >= 11 is evaluated only on the rows with bit h clear, with doubled
+ * coefficients: half the work. sym_expval_prepare_sym builds that table once per operator
+ * (z_sym = z | (h+1) << 56, c_sym = 2c for those groups, copies otherwise; x_masks unchanged); pass
+ * it to sym_expval with real_coeffs = 2 and row ranges aligned to 2048. partial[0] receives the
+ * (real) expectation value, partial[1] is left untouched (exactly zero for a Hermitian operator).
+ * Row-range partial sums are no longer the sums over those rows, but they still add up to the total
+ * when every range uses this mode (the 2^n basis shards over ranks as before). */
+int sym_expval_prepare_sym(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased,
+                           int64_t M, int64_t *z_sym, double *c_sym, void *stream);
 /* CSR emitter for small n (parity with to_sparse_matrix): G distinct x masks (x_groups, ascending),
  * terms sorted by x with group g spanning [group_start[g], group_start[g+1]). Every row gets exactly
  * G entries sorted by column (explicit zeros kept). data: double[2^n*G][2], indices: int64[2^n*G],

@@ -41,6 +41,7 @@ SIGNATURES = {
     "sym_term_masks": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_p, c_p, c_p]),
     "sym_apply": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i64, c_i64, c_i32, c_p]),
     "sym_expval": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i64, c_i64, c_i32, c_p]),
+    "sym_expval_prepare_sym": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p]),
     "sym_to_csr": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
     "sym_rref_ws_bytes": (c_sz, [c_i64]),
     "sym_rref": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p, c_sz, c_p]),

@@ -139,9 +139,11 @@ __global__ void __launch_bounds__(RREF_THREADS) rref_panel_kernel(uint64_t *__re
         if (piv != 0x7fffffff) {
             if (tid < kk) s_hit[tid] = (tid != j) && ((sm[(int64_t)tid * Cw + (piv >> 6)] >> (piv & 63)) & 1ull);
             __syncthreads();
-            for (int64_t c = tid; c < total; c += nt) {
-                const int r = (int)(c / Cw);
-                if (s_hit[r]) sm[c] ^= sm[(int64_t)j * Cw + (c - (int64_t)r * Cw)];
+            const uint64_t *src = sm + (int64_t)j * Cw;
+            for (int r = 0; r < kk; ++r) {          // uniform over the CTA: no per-cell division
+                if (!s_hit[r]) continue;
+                uint64_t *dst = sm + (int64_t)r * Cw;
+                for (int64_t k = tid; k < Cw; k += nt) dst[k] ^= src[k];
             }
         }
         __syncthreads();

@@ -238,7 +238,7 @@ __device__ __forceinline__ void wht_inplace(double (&B)[1 << NB]) {
     }
 }
 
-template <bool EXPVAL, bool REAL, int NB, int TH, int MINB>
+template <bool EXPVAL, bool REAL, int NB, int TH, int MINB, bool SYM>
 __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restrict__ xm, const int64_t *__restrict__ zm,
                                                                    const double2 *__restrict__ cp, int64_t M,
                                                                    const double2 *__restrict__ psi, double2 *__restrict__ y,
@@ -259,6 +259,12 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
         Bi[k] = 0.0;
     }
     int64_t xcur = -1;
+    // SYM (Hermitian operator with real phased coefficients, expectation value only): the pair (r, r^x)
+    // contributes a complex-conjugate pair, so a group whose x has its highest set bit h above the
+    // CTA's row span is evaluated only by the CTAs whose rows have bit h clear, with doubled
+    // coefficients (sym_expval_prepare_sym stores h+1 in bits 56..62 of z and doubles c).
+    const uint64_t block_rows = (uint64_t)(row_begin + (int64_t)blockIdx.x * (R * TH));
+    bool dirty = false;   // the current group has received at least one term
     auto finish_group = [&]() {
         wht_inplace<NB>(Br);
         if constexpr (!REAL) wht_inplace<NB>(Bi);
@@ -288,19 +294,25 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
         for (int i = 0; i < nt; ++i) {
             const int64_t x = tile.x[i];
             if (x != xcur) {  // uniform across the CTA
-                if (xcur >= 0) finish_group();
+                if (dirty) finish_group();
+                dirty = false;
                 xcur = x;
             }
             const uint64_t z = (uint64_t)tile.z[i];
+            if constexpr (SYM) {
+                const uint32_t hb = (uint32_t)(z >> 56) & 0x7fu;          // uniform across the CTA
+                if (hb != 0u && ((block_rows >> (hb - 1u)) & 1ull)) continue;   // the partner rows own this group
+            }
             const double2 c = tile.c[i];
             const int flip = (int)((__popcll((uint64_t)r0 & z) & 1u) << 31);
             const uint32_t zeta = (uint32_t)(z >> SH) & (uint32_t)(R - 1);
+            dirty = true;
             bin_add<NB>(Br, zeta, __hiloint2double(__double2hiint(c.x) ^ flip, __double2loint(c.x)));
             if constexpr (!REAL)
                 bin_add<NB>(Bi, zeta, __hiloint2double(__double2hiint(c.y) ^ flip, __double2loint(c.y)));
         }
     }
-    if (xcur >= 0) finish_group();
+    if (dirty) finish_group();
     if (!EXPVAL) {
 #pragma unroll
         for (int k = 0; k < R; ++k) y[r0 + (int64_t)k * TH - row_begin] = make_double2(ar[k], ai[k]);
@@ -332,8 +344,30 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
             si += red[1][w];
         }
         atomicAdd(&partial[0], sr);
-        atomicAdd(&partial[1], si);
+        if (!SYM) atomicAdd(&partial[1], si);   // Hermitian: the conjugate pairs cancel the imaginary part exactly
     }
+}
+
+// z' = z | (h+1) << 56 and c' = 2c for the groups whose x has its highest set bit h >= min_bit (the
+// symmetric expectation-value mode of applyw_kernel); other terms are copied.
+__global__ void __launch_bounds__(256) prepare_sym_kernel(const int64_t *__restrict__ xm, const int64_t *__restrict__ zm,
+                                                           const double2 *__restrict__ cp, int64_t M, int min_bit,
+                                                           int64_t *__restrict__ z_out, double2 *__restrict__ c_out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    const uint64_t x = (uint64_t)xm[t];
+    uint64_t z = (uint64_t)zm[t];
+    double2 c = cp[t];
+    if (x != 0ull) {
+        const int h = 63 - __clzll((long long)x);
+        if (h >= min_bit) {
+            z |= (uint64_t)(h + 1) << 56;
+            c.x *= 2.0;
+            c.y *= 2.0;
+        }
+    }
+    z_out[t] = (int64_t)z;
+    c_out[t] = c;
 }
 
 // CSR emitter for small n: thread per (row, group); value = sum over the group's terms, position =
@@ -371,7 +405,7 @@ using namespace symb;
 
 static int apply_common(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M, int32_t n,
                         const double *psi, double *y, double *partial, int64_t row_begin, int64_t row_end, bool expval,
-                        bool real_coeffs, cudaStream_t st) {
+                        bool real_coeffs, cudaStream_t st, bool sym_mode = false) {
     SYM_REQUIRE(n >= 1 && n <= 40, "n_qubits out of range for the dense-state path");
     SYM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= ((int64_t)1 << n), "bad row range");
     const int64_t rows = row_end - row_begin;
@@ -381,14 +415,22 @@ static int apply_common(const int64_t *x_masks, const int64_t *z_masks, const do
     double2 *y2 = reinterpret_cast<double2 *>(y);
     // binned kernel: 16 rows per thread for real coefficients, 8 for complex ones (register budget)
     const int64_t span_w = real_coeffs ? 16 * 128 : 8 * 256;
+    if (sym_mode) {
+        SYM_REQUIRE(expval && real_coeffs, "symmetric mode is for expectation values with real phased coefficients");
+        SYM_REQUIRE(rows % span_w == 0 && row_begin % span_w == 0, "symmetric mode needs row ranges aligned to 2048");
+        applyw_kernel<true, true, 4, 128, 3, true><<<(unsigned)(rows / span_w), 128, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr,
+                                                                                          row_begin, partial);
+        SYM_LAUNCH_OK();
+        return SYM_OK;
+    }
     if (g_apply_variant == 1 && rows % span_w == 0 && row_begin % span_w == 0) {
         const unsigned nbw = (unsigned)(rows / span_w);
         if (expval) {
-            if (real_coeffs) applyw_kernel<true, true, 4, 128, 3><<<nbw, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
-            else applyw_kernel<true, false, 3, 256, 2><<<nbw, 256, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
+            if (real_coeffs) applyw_kernel<true, true, 4, 128, 3, false><<<nbw, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
+            else applyw_kernel<true, false, 3, 256, 2, false><<<nbw, 256, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
         } else {
-            if (real_coeffs) applyw_kernel<false, true, 4, 128, 3><<<nbw, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
-            else applyw_kernel<false, false, 3, 256, 2><<<nbw, 256, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
+            if (real_coeffs) applyw_kernel<false, true, 4, 128, 3, false><<<nbw, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
+            else applyw_kernel<false, false, 3, 256, 2, false><<<nbw, 256, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
         }
         SYM_LAUNCH_OK();
         return SYM_OK;
@@ -425,7 +467,17 @@ extern "C" int sym_expval(const int64_t *x_masks, const int64_t *z_masks, const 
                           int32_t n_qubits, const double *psi, double *partial, int64_t row_begin, int64_t row_end,
                           int32_t real_coeffs, void *stream) {
     return apply_common(x_masks, z_masks, c_phased, M, n_qubits, psi, nullptr, partial, row_begin, row_end, true,
-                        real_coeffs != 0, (cudaStream_t)stream);
+                        real_coeffs != 0, (cudaStream_t)stream, real_coeffs == 2);
+}
+
+extern "C" int sym_expval_prepare_sym(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
+                                      int64_t *z_sym, double *c_sym, void *stream) {
+    SYM_REQUIRE(M >= 0, "bad size");
+    if (M == 0) return SYM_OK;
+    prepare_sym_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x_masks, z_masks, reinterpret_cast<const double2 *>(c_phased), M, 11, z_sym, reinterpret_cast<double2 *>(c_sym));
+    SYM_LAUNCH_OK();
+    return SYM_OK;
 }
 
 extern "C" int sym_to_csr(const int64_t *z_masks, const double *c_phased, int64_t M, int32_t n_qubits,

@@ -288,7 +288,10 @@ def project(xz, c, n_qubits, stab_cols, stab_eigs, free_qubits):
 
 # ------------------------------------------------------------------------------------- matrix-free
 def term_masks_sorted(xz, c, n_qubits):
-    """Basis-index masks and phased coefficients of every term, sorted by x mask."""
+    """Basis-index masks and phased coefficients of every term, sorted by x mask. The returned
+    coefficient tensor carries two Python attributes used by the kernels' fast paths:
+    `_sym_real` (every phased coefficient is real) and `_sym_hermitian` (additionally every original
+    coefficient is real, i.e. a Hermitian operator whose terms all have an even number of Y)."""
     M, W = _rows(xz)
     assert W == 1 and n_qubits <= 62
     dev = xz.device
@@ -299,15 +302,15 @@ def term_masks_sorted(xz, c, n_qubits):
     _cabi.check(L.sym_term_masks(_p(xz), _p(_coeff(c)), M, int(n_qubits), _p(xm), _p(zm), _p(cp), _stream()))
     order = sort_pairs(xm.clone(), torch.arange(M, dtype=torch.int32, device=dev), begin_bit=0)[1].to(torch.int64)
     cp = cp[order].contiguous()
-    _real_flags[cp.data_ptr()] = bool((cp.imag == 0).all().item())     # one sync, once per operator
+    flags = torch.stack([(cp.imag == 0).all(), (c.imag == 0).all()]).cpu().tolist()    # one sync, once per operator
+    cp._sym_real = bool(flags[0])
+    cp._sym_hermitian = bool(flags[0] and flags[1])
+    cp._sym_table = None
     return xm[order].contiguous(), zm[order].contiguous(), cp
 
 
-_real_flags = {}
-
-
 def _is_real(cp):
-    return 1 if _real_flags.get(cp.data_ptr(), False) else 0
+    return 1 if getattr(cp, "_sym_real", False) else 0
 
 
 def apply_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
@@ -321,15 +324,35 @@ def apply_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
     return y
 
 
+SYM_ALIGN = 2048      # row-range alignment of the symmetric expectation-value mode
+use_symmetric_expval = True
+
+
 def expval_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
-    """Partial <psi|H|psi> over basis rows [row_begin, row_end) as a complex128 device scalar."""
+    """Partial <psi|H|psi> over basis rows [row_begin, row_end) as a complex128 device scalar. For a
+    Hermitian operator with real phased coefficients (see term_masks_sorted) and 2048-aligned row
+    ranges the symmetric mode halves the work: the partial sums of the row ranges then only add up
+    to the total when every range is evaluated this way (they are, for a given operator)."""
     side = 1 << int(n_qubits)
     row_end = side if row_end is None else row_end
     psi = psi.contiguous()
     assert psi.dtype == torch.complex128 and psi.numel() == side
     partial = torch.zeros(2, dtype=torch.float64, device=psi.device)
-    _cabi.check(lib().sym_expval(_p(xm), _p(zm), _p(cp), xm.numel(), int(n_qubits), _p(psi), _p(partial), row_begin,
-                                 row_end, _is_real(cp), _stream()))
+    L = lib()
+    M = xm.numel()
+    if (use_symmetric_expval and getattr(cp, "_sym_hermitian", False) and side % SYM_ALIGN == 0
+            and row_begin % SYM_ALIGN == 0 and row_end % SYM_ALIGN == 0 and M > 0):
+        if cp._sym_table is None:
+            z_sym = torch.empty_like(zm)
+            c_sym = torch.empty_like(cp)
+            _cabi.check(L.sym_expval_prepare_sym(_p(xm), _p(zm), _p(cp), M, _p(z_sym), _p(c_sym), _stream()))
+            cp._sym_table = (z_sym, c_sym)
+        z_sym, c_sym = cp._sym_table
+        _cabi.check(L.sym_expval(_p(xm), _p(z_sym), _p(c_sym), M, int(n_qubits), _p(psi), _p(partial), row_begin, row_end, 2,
+                                 _stream()))
+    else:
+        _cabi.check(L.sym_expval(_p(xm), _p(zm), _p(cp), M, int(n_qubits), _p(psi), _p(partial), row_begin, row_end,
+                                 _is_real(cp), _stream()))
     return torch.view_as_complex(partial)
 
 

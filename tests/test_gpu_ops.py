@@ -406,7 +406,7 @@ def test_exchange_free_owner_product_single_gpu(ops, log2g):
         assert ok, (n, why)
 
 
-@pytest.mark.parametrize("n,real", [(11, True), (12, False), (13, True), (14, False)])
+@pytest.mark.parametrize("n,real", [(11, True), (12, False), (13, True), (14, False), (15, True)])
 def test_binned_apply_kernel_matches_oracle_and_4row_kernel(ops, n, real):
     """The Walsh-Hadamard binned kernel (16 / 8 basis rows per thread) against the oracle and against
     the 4-row kernel, on operators whose x groups hold 1..many terms (molecular-like structure)."""
@@ -447,3 +447,22 @@ def test_binned_apply_kernel_matches_oracle_and_4row_kernel(ops, n, real):
     finally:
         ops.set_tuning(4, 1)
     assert np.allclose(out[0], out[1], rtol=1e-13, atol=1e-14)
+    # symmetric (Hermitian, real phased coefficients) expectation-value mode: on for `real`, never for complex
+    assert bool(getattr(cp, "_sym_hermitian", False)) == real
+    if real:
+        e_ref = np.vdot(psi, ref)
+        assert abs(e_ref.imag) < 1e-12
+        try:
+            ops.use_symmetric_expval = False
+            e_plain = complex(ops.expval_dense(xm, zm, cp, n, psi_d).cpu().numpy())
+        finally:
+            ops.use_symmetric_expval = True
+        e_sym = complex(ops.expval_dense(xm, zm, cp, n, psi_d).cpu().numpy())
+        assert cp._sym_table is not None and e_sym.imag == 0.0
+        assert np.isclose(e_sym.real, e_ref.real, rtol=1e-12, atol=1e-14)
+        assert np.isclose(e_plain, e_ref, rtol=1e-12, atol=1e-14)
+        n_parts = max(1, (1 << n) // 2048)
+        step = (1 << n) // n_parts
+        parts = sum(complex(ops.expval_dense(xm, zm, cp, n, psi_d, k * step, (k + 1) * step).cpu().numpy())
+                    for k in range(n_parts))
+        assert np.isclose(parts.real, e_ref.real, rtol=1e-12, atol=1e-14)      # shards still add up to the total
