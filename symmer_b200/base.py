@@ -151,6 +151,20 @@ class PauliwordOp:
         return cls.from_list(list(pauli_terms), coeff_vec)
 
     @classmethod
+    def from_packed_file(cls, path) -> "PauliwordOp":
+        """Load an operator written by `to_packed_file` (packed uint64 rows + complex128 coefficients)
+        straight into device memory: no string parsing, no bool matrix."""
+        from .utils import load_packed
+        xz, coeff, n, _ = load_packed(path)
+        dev = ops.device()
+        return cls._from_device(torch.from_numpy(xz.view(np.int64).copy()).to(dev),
+                                torch.from_numpy(np.ascontiguousarray(coeff)).to(dev), n)
+
+    def to_packed_file(self, path, **extra) -> None:
+        from .utils import save_packed
+        save_packed(path, self.symp_matrix, self.coeff_vec, **extra)
+
+    @classmethod
     def empty(cls, n_qubits: int) -> "PauliwordOp":
         """base.py:223-236: 0 * I...I."""
         return cls.from_dictionary({'I' * n_qubits: 0})

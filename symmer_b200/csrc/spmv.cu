@@ -238,7 +238,7 @@ __device__ __forceinline__ void wht_inplace(double (&B)[1 << NB]) {
     }
 }
 
-template <bool EXPVAL, bool REAL, int NB, int TH, int MINB, bool SYM>
+template <bool EXPVAL, bool REAL, int NB, int TH, int MINB, bool SYM, bool NARROW>
 __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restrict__ xm, const int64_t *__restrict__ zm,
                                                                    const double2 *__restrict__ cp, int64_t M,
                                                                    const double2 *__restrict__ psi, double2 *__restrict__ y,
@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
     // coefficients (sym_expval_prepare_sym stores h+1 in bits 56..62 of z and doubles c).
     const uint64_t block_rows = (uint64_t)(row_begin + (int64_t)blockIdx.x * (R * TH));
     bool dirty = false;   // the current group has received at least one term
+    int64_t skip_until = 0;   // SYM: global index of the first term after the group being skipped
     auto finish_group = [&]() {
         wht_inplace<NB>(Br);
         if constexpr (!REAL) wht_inplace<NB>(Bi);
@@ -291,20 +292,33 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
             tile.c[i] = cp[base + i];
         }
         __syncthreads();
-        for (int i = 0; i < nt; ++i) {
+        int i = 0;
+        if constexpr (SYM) {   // a skipped group may continue into this tile
+            const int64_t rem = skip_until - base;
+            i = rem <= 0 ? 0 : (rem >= nt ? nt : (int)rem);
+        }
+        for (; i < nt; ++i) {
             const int64_t x = tile.x[i];
+            const uint64_t z = (uint64_t)tile.z[i];
             if (x != xcur) {  // uniform across the CTA
                 if (dirty) finish_group();
                 dirty = false;
                 xcur = x;
-            }
-            const uint64_t z = (uint64_t)tile.z[i];
-            if constexpr (SYM) {
-                const uint32_t hb = (uint32_t)(z >> 56) & 0x7fu;          // uniform across the CTA
-                if (hb != 0u && ((block_rows >> (hb - 1u)) & 1ull)) continue;   // the partner rows own this group
+                if constexpr (SYM) {
+                    // first term of a group: bits 56..62 of z hold h+1, bits 40..55 the group length
+                    const uint32_t hb = (uint32_t)(z >> 56) & 0x7fu;
+                    if (hb != 0u && ((block_rows >> (hb - 1u)) & 1ull)) {       // the partner rows own this group
+                        const int len = (int)((z >> 40) & 0xffffu);
+                        skip_until = base + i + len;
+                        i += len - 1;
+                        xcur = -1;           // re-evaluate at the next term (a capped group continues)
+                        continue;
+                    }
+                }
             }
             const double2 c = tile.c[i];
-            const int flip = (int)((__popcll((uint64_t)r0 & z) & 1u) << 31);
+            const uint32_t par = NARROW ? (uint32_t)__popc((uint32_t)r0 & (uint32_t)z) : (uint32_t)__popcll((uint64_t)r0 & z);
+            const int flip = (int)((par & 1u) << 31);
             const uint32_t zeta = (uint32_t)(z >> SH) & (uint32_t)(R - 1);
             dirty = true;
             bin_add<NB>(Br, zeta, __hiloint2double(__double2hiint(c.x) ^ flip, __double2loint(c.x)));
@@ -361,7 +375,10 @@ __global__ void __launch_bounds__(256) prepare_sym_kernel(const int64_t *__restr
     if (x != 0ull) {
         const int h = 63 - __clzll((long long)x);
         if (h >= min_bit) {
-            z |= (uint64_t)(h + 1) << 56;
+            // remaining terms of the group from here (capped; a longer group is skipped in several hops)
+            int64_t len = 1;
+            while (t + len < M && len < 0xffff && (uint64_t)xm[t + len] == x) ++len;
+            z |= (uint64_t)(h + 1) << 56 | (uint64_t)len << 40;
             c.x *= 2.0;
             c.y *= 2.0;
         }
@@ -415,23 +432,29 @@ static int apply_common(const int64_t *x_masks, const int64_t *z_masks, const do
     double2 *y2 = reinterpret_cast<double2 *>(y);
     // binned kernel: 16 rows per thread for real coefficients, 8 for complex ones (register budget)
     const int64_t span_w = real_coeffs ? 16 * 128 : 8 * 256;
+    const bool narrow = n <= 32;   // basis indices fit 32 bits: one POPC per sign instead of two
     if (sym_mode) {
         SYM_REQUIRE(expval && real_coeffs, "symmetric mode is for expectation values with real phased coefficients");
         SYM_REQUIRE(rows % span_w == 0 && row_begin % span_w == 0, "symmetric mode needs row ranges aligned to 2048");
-        applyw_kernel<true, true, 4, 128, 3, true><<<(unsigned)(rows / span_w), 128, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr,
-                                                                                          row_begin, partial);
+        const unsigned nbs = (unsigned)(rows / span_w);
+        if (narrow) applyw_kernel<true, true, 4, 128, 3, true, true><<<nbs, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
+        else applyw_kernel<true, true, 4, 128, 3, true, false><<<nbs, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
         SYM_LAUNCH_OK();
         return SYM_OK;
     }
     if (g_apply_variant == 1 && rows % span_w == 0 && row_begin % span_w == 0) {
         const unsigned nbw = (unsigned)(rows / span_w);
+#define APPLYW(E, RL, NBITS, THR, MB, OUT, PART)                                                                         \
+    if (narrow) applyw_kernel<E, RL, NBITS, THR, MB, false, true><<<nbw, THR, 0, st>>>(x_masks, z_masks, c2, M, p2, OUT, row_begin, PART); \
+    else applyw_kernel<E, RL, NBITS, THR, MB, false, false><<<nbw, THR, 0, st>>>(x_masks, z_masks, c2, M, p2, OUT, row_begin, PART)
         if (expval) {
-            if (real_coeffs) applyw_kernel<true, true, 4, 128, 3, false><<<nbw, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
-            else applyw_kernel<true, false, 3, 256, 2, false><<<nbw, 256, 0, st>>>(x_masks, z_masks, c2, M, p2, nullptr, row_begin, partial);
+            if (real_coeffs) { APPLYW(true, true, 4, 128, 3, nullptr, partial); }
+            else { APPLYW(true, false, 3, 256, 2, nullptr, partial); }
         } else {
-            if (real_coeffs) applyw_kernel<false, true, 4, 128, 3, false><<<nbw, 128, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
-            else applyw_kernel<false, false, 3, 256, 2, false><<<nbw, 256, 0, st>>>(x_masks, z_masks, c2, M, p2, y2, row_begin, nullptr);
+            if (real_coeffs) { APPLYW(false, true, 4, 128, 3, y2, nullptr); }
+            else { APPLYW(false, false, 3, 256, 2, y2, nullptr); }
         }
+#undef APPLYW
         SYM_LAUNCH_OK();
         return SYM_OK;
     }

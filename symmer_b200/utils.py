@@ -158,3 +158,54 @@ def symplectic_to_string(symp_vec) -> str:
     symp_vec = np.asarray(symp_vec, dtype=bool)
     n = symp_vec.size // 2
     return "".join(_LUT[symp_vec[:n].astype(int) + 2 * symp_vec[n:].astype(int)])
+
+
+# ------------------------------------------------------------------ packed on-disk operators
+PACKED_FORMAT_VERSION = 1
+
+
+def save_packed(path, symp_matrix, coeff_vec, **extra) -> None:
+    """Write an operator as a compressed .npz holding the engine's own layout: uint64[M, 2W] X|Z rows
+    (qubit q = bit q%64 of word q//64 of its block) + complex128[M]. 8x smaller than the bool matrix
+    and ~30x smaller than the reference's JSON dictionaries (tests/hamiltonian_data/*.json); loading
+    needs no per-string parsing and uploads straight into device memory."""
+    symp_matrix = np.asarray(symp_matrix, dtype=bool)
+    M, two_n = symp_matrix.shape
+    n = two_n // 2
+    np.savez_compressed(path, format_version=np.array([PACKED_FORMAT_VERSION]), n_qubits=np.array([n]),
+                        xz=pack_rows_host(symp_matrix), coeff=np.asarray(coeff_vec, dtype=complex),
+                        **{k: np.asarray(v) for k, v in extra.items()})
+
+
+def load_packed(path):
+    """(xz uint64[M, 2W], coeff complex128[M], n_qubits, extra dict) from a file written by save_packed."""
+    d = np.load(path)
+    if int(d["format_version"][0]) != PACKED_FORMAT_VERSION:
+        raise ValueError(f"unsupported packed operator format {int(d['format_version'][0])}")
+    extra = {k: d[k] for k in d.files if k not in ("format_version", "n_qubits", "xz", "coeff")}
+    return d["xz"], d["coeff"], int(d["n_qubits"][0]), extra
+
+
+def pack_rows_host(symp_matrix: np.ndarray) -> np.ndarray:
+    """bool[M, 2n] -> uint64[M, 2W] in the device layout (host-side twin of sym_pack, used for files)."""
+    symp_matrix = np.asarray(symp_matrix, dtype=bool)
+    M, two_n = symp_matrix.shape
+    n = two_n // 2
+    W = max(1, (n + 63) // 64)
+    out = np.zeros((M, 2 * W), dtype=np.uint64)
+    for blk in range(2):
+        bits = np.zeros((M, W * 64), dtype=np.uint8)
+        bits[:, :n] = symp_matrix[:, blk * n:(blk + 1) * n]
+        by = np.packbits(bits.reshape(M, W, 8, 8), axis=-1, bitorder="little").reshape(M, W, 8)
+        out[:, blk * W:(blk + 1) * W] = by.astype(np.uint64).dot(np.uint64(1) << (np.arange(8, dtype=np.uint64) * np.uint64(8)))
+    return out
+
+
+def unpack_rows_host(xz: np.ndarray, n_qubits: int) -> np.ndarray:
+    """uint64[M, 2W] -> bool[M, 2n] (host-side twin of sym_unpack)."""
+    xz = np.asarray(xz, dtype=np.uint64)
+    M, two_w = xz.shape
+    W = two_w // 2
+    by = (xz[:, :, None] >> (np.arange(8, dtype=np.uint64) * np.uint64(8))).astype(np.uint8)      # little-endian bytes
+    bits = np.unpackbits(by, axis=-1, bitorder="little").reshape(M, 2, W * 64)
+    return np.hstack([bits[:, 0, :n_qubits], bits[:, 1, :n_qubits]]).astype(bool)
