@@ -204,37 +204,30 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply4_kernel(const int64_t *__
 }
 
 // 2^NB basis rows per thread (r0 + k*TH, k = 0 .. 2^NB-1, TH = block size; the block base is aligned to
-// TH*2^NB so the rows of a thread differ only in bits SH .. SH+NB-1, SH = log2 TH). For a term with z mask z the sign of row k is
-//   s0 * (-1)^{popcount(k & zeta)},   s0 = (-1)^{popcount(r0 & z)},   zeta = (z >> SH) & (2^NB - 1),
-// so instead of one add per (row, term) the thread adds s0*c into ONE of 2^NB bins (zeta is uniform
-// across the CTA: a uniform switch, no divergence) and turns the bins into the 2^NB row weights with
-// a Walsh-Hadamard butterfly when the x group ends: NB adds per (row, group) instead of one add and
-// one sign flip per (row, term), and the per-term overhead (3 shared loads, AND + POPC, loop) is
-// spread over 2^NB rows. HOOH STO-3G (24 q, 14 905 terms in 2 767 groups): 3x fewer issued
-// instructions than the 4-row kernel. FP64-add / issue bound; psi gathers are coalesced.
+// TH*2^NB so the rows of a thread differ only in bits SH .. SH+NB-1, SH = log2 TH). For a term with z mask
+// z the sign of row k is
+//   s0 * (-1)^{popcount(k & zeta)},   s0 = (-1)^{popcount(r0 & z)},   zeta = (z >> SH) & (2^NB - 1).
+// zeta is uniform across the CTA, so a uniform switch selects one of 2^NB straight-line blocks in which
+// the sign of every row is a compile-time constant: the block is 2^NB FP64 adds with the negation folded
+// into the instruction (DADD with a negated operand) — no per-row sign arithmetic at all. One AND + POPC
+// + shared-memory fetch per (thread, term) is spread over 2^NB rows, so the kernel sits on the FP64 add
+// rate: 1 DADD per (row, term) for real coefficients, 2 for complex ones. psi gathers are coalesced.
 template <int NB>
-__device__ __forceinline__ void bin_add(double (&B)[1 << NB], uint32_t zeta, double v) {
+__device__ __forceinline__ void signed_add(double (&w)[1 << NB], uint32_t zeta, double v) {
     switch (zeta) {
-#define BIN_CASE(Z) case Z: if (Z < (1 << NB)) B[Z < (1 << NB) ? Z : 0] += v; break;
-        BIN_CASE(0) BIN_CASE(1) BIN_CASE(2) BIN_CASE(3) BIN_CASE(4) BIN_CASE(5) BIN_CASE(6) BIN_CASE(7)
-        BIN_CASE(8) BIN_CASE(9) BIN_CASE(10) BIN_CASE(11) BIN_CASE(12) BIN_CASE(13) BIN_CASE(14) BIN_CASE(15)
-#undef BIN_CASE
+#define SIGN_CASE(Z)                                                       \
+    case Z:                                                                \
+        if (Z < (1 << NB)) {                                               \
+            _Pragma("unroll") for (int k = 0; k < (1 << NB); ++k) {        \
+                if (__builtin_popcount(k & Z) & 1) w[k] -= v;              \
+                else w[k] += v;                                            \
+            }                                                              \
+        }                                                                  \
+        break;
+        SIGN_CASE(0) SIGN_CASE(1) SIGN_CASE(2) SIGN_CASE(3) SIGN_CASE(4) SIGN_CASE(5) SIGN_CASE(6) SIGN_CASE(7)
+        SIGN_CASE(8) SIGN_CASE(9) SIGN_CASE(10) SIGN_CASE(11) SIGN_CASE(12) SIGN_CASE(13) SIGN_CASE(14) SIGN_CASE(15)
+#undef SIGN_CASE
         default: break;
-    }
-}
-
-template <int NB>
-__device__ __forceinline__ void wht_inplace(double (&B)[1 << NB]) {
-#pragma unroll
-    for (int h = 1; h < (1 << NB); h <<= 1) {
-#pragma unroll
-        for (int i = 0; i < (1 << NB); ++i) {
-            if ((i & h) == 0) {
-                const double a = B[i], b = B[i + h];
-                B[i] = a + b;
-                B[i + h] = a - b;
-            }
-        }
     }
 }
 
@@ -266,9 +259,7 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
     const uint64_t block_rows = (uint64_t)(row_begin + (int64_t)blockIdx.x * (R * TH));
     bool dirty = false;   // the current group has received at least one term
     int64_t skip_until = 0;   // SYM: global index of the first term after the group being skipped
-    auto finish_group = [&]() {
-        wht_inplace<NB>(Br);
-        if constexpr (!REAL) wht_inplace<NB>(Bi);
+    auto finish_group = [&]() {   // Br/Bi hold the row weights w_g(r) of the finished x group
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const double2 p = psi[(r0 + (int64_t)k * TH) ^ xcur];
@@ -321,9 +312,9 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
             const int flip = (int)((par & 1u) << 31);
             const uint32_t zeta = (uint32_t)(z >> SH) & (uint32_t)(R - 1);
             dirty = true;
-            bin_add<NB>(Br, zeta, __hiloint2double(__double2hiint(c.x) ^ flip, __double2loint(c.x)));
+            signed_add<NB>(Br, zeta, __hiloint2double(__double2hiint(c.x) ^ flip, __double2loint(c.x)));
             if constexpr (!REAL)
-                bin_add<NB>(Bi, zeta, __hiloint2double(__double2hiint(c.y) ^ flip, __double2loint(c.y)));
+                signed_add<NB>(Bi, zeta, __hiloint2double(__double2hiint(c.y) ^ flip, __double2loint(c.y)));
         }
     }
     if (dirty) finish_group();
@@ -414,7 +405,7 @@ __global__ void __launch_bounds__(256) csr_kernel(const int64_t *__restrict__ zm
     if (g == 0) indptr[r] = r * G;
 }
 
-int g_apply_variant = 1;  // tuning knob 4: 1 = binned Walsh-Hadamard kernel (default), 0 = 4-row kernel
+int g_apply_variant = 1;  // tuning knob 4: 1 = 16/8-row static-sign kernel (default), 0 = 4-row kernel
 
 }  // namespace symb
 
@@ -430,7 +421,7 @@ static int apply_common(const int64_t *x_masks, const int64_t *z_masks, const do
     const double2 *c2 = reinterpret_cast<const double2 *>(c_phased);
     const double2 *p2 = reinterpret_cast<const double2 *>(psi);
     double2 *y2 = reinterpret_cast<double2 *>(y);
-    // binned kernel: 16 rows per thread for real coefficients, 8 for complex ones (register budget)
+    // static-sign kernel: 16 rows per thread for real coefficients, 8 for complex ones (register budget)
     const int64_t span_w = real_coeffs ? 16 * 128 : 8 * 256;
     const bool narrow = n <= 32;   // basis indices fit 32 bits: one POPC per sign instead of two
     if (sym_mode) {
