@@ -79,6 +79,23 @@ def main():
         assert bool((xz_full[:sizes[0]] == 1).all()) and bool((xz_full[sizes[0]:] == 2).all())
         assert bool((c_full[:sizes[0]] == 0).all()) and bool((c_full[sizes[0]:] == complex(1, -1)).all())
 
+    # 4b. row exchange (sharded_cleanup's collective): rows grouped by destination, order preserved
+    n_rows = 6 + rank
+    dest = (np.arange(n_rows) + rank) % world
+    order_r = np.argsort(dest, kind="stable")
+    xz_rows = torch.from_numpy((np.arange(n_rows, dtype=np.int64)[:, None] * 10 + rank + np.zeros((1, 4), np.int64))[order_r])
+    c_rows = torch.from_numpy((np.arange(n_rows) + 1j * rank).astype(complex)[order_r])
+    cnt = torch.from_numpy(np.bincount(dest, minlength=world).astype(np.int64))
+    got_xz, got_c = sdist.exchange_rows(xz_rows, c_rows, cnt)
+    assert got_xz.shape[0] == got_c.shape[0] and got_xz.shape[1] == 4
+    src_rank = got_xz[:, 0].numpy() % 10
+    serial = got_xz[:, 0].numpy() // 10
+    assert np.all((serial + src_rank) % world == rank)           # everything I received was addressed to me
+    assert np.array_equal(got_c.numpy().real, serial) and np.array_equal(got_c.numpy().imag, src_rank)
+    tot = torch.tensor([got_xz.shape[0]], dtype=torch.int64)
+    dist.all_reduce(tot)
+    assert int(tot) == 6 + 7
+
     # 5. exchange-free owner partition (the default product path) with the oracle standing in for the
     #    kernels: class = a GF(2)-linear functional of the row, rank r multiplies class a of A with
     #    class a^r of B; the union over ranks must equal the plain product with disjoint owners.

@@ -42,6 +42,35 @@ def main():
                 ref_s, ref_c = po.multiply_by_operator(a_s, a_c, b_s, b_c)
                 ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
                 assert ok, (method, why)
+        # term-sharded cleanup and rotations: every rank holds an arbitrary slice of a list with duplicates
+        dup_s = np.vstack([a_s, a_s[::3], b_s[:N // 2]]) if a_s.shape[1] == b_s.shape[1] else a_s
+        dup_c = np.hstack([a_c, -a_c[::3] * (np.arange(len(a_c[::3])) % 2), b_c[:N // 2]])
+        sl = slice(rank, None, world)
+        loc_xz = ops.pack(torch.from_numpy(dup_s[sl].copy()), n)
+        loc_c = torch.from_numpy(dup_c[sl].copy()).to(dev)
+        cxz, cc_ = sdist.sharded_cleanup(loc_xz, loc_c)
+        q_row = b_s[0]
+        q_xz = ops.pack(torch.from_numpy(q_row.reshape(1, -1).copy()), n)
+        rxz, rc = sdist.sharded_rotation(cxz, cc_, q_xz, 0.37)
+        kxz, kc = sdist.sharded_rotation(cxz, cc_, q_xz, None)
+        parts = [None] * world
+        dist.all_gather_object(parts, tuple(t.cpu().numpy() for t in (ops.unpack(cxz, n), cc_, ops.unpack(rxz, n), rc,
+                                                                    ops.unpack(kxz, n), kc)))
+        if rank == 0:
+            cs, ccs = np.vstack([p_[0] for p_ in parts]), np.hstack([p_[1] for p_ in parts])
+            assert len(np.unique(cs, axis=0)) == len(cs), "cleanup owners overlap"
+            ref_s, ref_c = po.cleanup(dup_s, dup_c)
+            ok, why = po.compare_term_sets(cs, ccs, ref_s, ref_c, scale=np.abs(dup_c).max())
+            assert ok, ("sharded_cleanup", why)
+            rs, rcs = np.vstack([p_[2] for p_ in parts]), np.hstack([p_[3] for p_ in parts])
+            assert len(np.unique(rs, axis=0)) == len(rs), "rotation owners overlap"
+            ref_rs, ref_rc = po.perform_rotations(ref_s, ref_c, [(q_row, 0.37)])
+            ok, why = po.compare_term_sets(rs, rcs, ref_rs, ref_rc, scale=np.abs(dup_c).max())
+            assert ok, ("sharded_rotation", why)
+            ks, kcs = np.vstack([p_[4] for p_ in parts]), np.hstack([p_[5] for p_ in parts])
+            ref_ks, ref_kc = po.perform_rotations(ref_s, ref_c, [(q_row, None)])
+            ok, why = po.compare_term_sets(ks, kcs, ref_ks, ref_kc, scale=np.abs(dup_c).max())
+            assert ok, ("sharded Clifford rotation", why)
         # commute row blocks
         a_full = ops.pack(torch.from_numpy(a_s), n)
         blk, row0 = sdist.sharded_commute(a_full, b)
