@@ -145,9 +145,11 @@ int sym_expval(const int64_t *x_masks, const int64_t *z_masks, const double *c_p
 /* Symmetric expectation-value mode for Hermitian operators whose phased coefficients are all real
  * (every term has an even number of Y and a real coefficient: molecular Hamiltonians). The pair of
  * basis rows (r, r ^ x) contributes a complex-conjugate pair, so a group of terms whose x mask has
- * its highest set bit h >= 11 is evaluated only on the rows with bit h clear, with doubled
+ * its highest set bit h >= 11 is evaluated only on one half of the rows (bit h clear or set, a
+ * pseudo-random choice per group that keeps CTAs and row shards balanced), with doubled
  * coefficients: half the work. sym_expval_prepare_sym builds that table once per operator
- * (z_sym = z | (h+1) << 56, c_sym = 2c for those groups, copies otherwise; x_masks unchanged); pass
+ * (z_sym = z | side << 63 | (h+1) << 56 | group_length << 40, c_sym = 2c for those groups, copies
+ * otherwise; x_masks unchanged); pass
  * it to sym_expval with real_coeffs = 2 and row ranges aligned to 2048. partial[0] receives the
  * (real) expectation value, partial[1] is left untouched (exactly zero for a Hermitian operator).
  * Row-range partial sums are no longer the sums over those rows, but they still add up to the total

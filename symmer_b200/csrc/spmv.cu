@@ -254,8 +254,9 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
     int64_t xcur = -1;
     // SYM (Hermitian operator with real phased coefficients, expectation value only): the pair (r, r^x)
     // contributes a complex-conjugate pair, so a group whose x has its highest set bit h above the
-    // CTA's row span is evaluated only by the CTAs whose rows have bit h clear, with doubled
-    // coefficients (sym_expval_prepare_sym stores h+1 in bits 56..62 of z and doubles c).
+    // CTA's row span is evaluated only by the CTAs whose rows have bit h equal to the group's side bit,
+    // with doubled coefficients (sym_expval_prepare_sym stores h+1 in bits 56..62 of z, the group length
+    // in bits 40..55, the side in bit 63, and doubles c).
     const uint64_t block_rows = (uint64_t)(row_begin + (int64_t)blockIdx.x * (R * TH));
     bool dirty = false;   // the current group has received at least one term
     int64_t skip_until = 0;   // SYM: global index of the first term after the group being skipped
@@ -298,7 +299,9 @@ __global__ void __launch_bounds__(TH, MINB) applyw_kernel(const int64_t *__restr
                 if constexpr (SYM) {
                     // first term of a group: bits 56..62 of z hold h+1, bits 40..55 the group length
                     const uint32_t hb = (uint32_t)(z >> 56) & 0x7fu;
-                    if (hb != 0u && ((block_rows >> (hb - 1u)) & 1ull)) {       // the partner rows own this group
+                    // bit 63 of z says which half of the pairs (bit h of the row clear or set) evaluates this
+                    // group; it alternates pseudo-randomly between groups so CTAs and row shards stay balanced
+                    if (hb != 0u && (((block_rows >> (hb - 1u)) & 1ull) != (z >> 63))) {   // the partner rows own this group
                         const int len = (int)((z >> 40) & 0xffffu);
                         skip_until = base + i + len;
                         i += len - 1;
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(256) prepare_sym_kernel(const int64_t *__restr
             // remaining terms of the group from here (capped; a longer group is skipped in several hops)
             int64_t len = 1;
             while (t + len < M && len < 0xffff && (uint64_t)xm[t + len] == x) ++len;
-            z |= (uint64_t)(h + 1) << 56 | (uint64_t)len << 40;
+            z |= (uint64_t)(h + 1) << 56 | (uint64_t)len << 40 | ((mix64(x) >> 17) & 1ull) << 63;
             c.x *= 2.0;
             c.y *= 2.0;
         }
