@@ -141,6 +141,12 @@ def run_ours(args):
     dev = ops.device()
     if os.environ.get("SYMMER_EMIT_VARIANT"):                      # A/B knob: 0 = two-kernel compaction + emission
         ops.set_tuning(1, int(os.environ["SYMMER_EMIT_VARIANT"]))
+    tuning = {}
+    for kv in filter(None, os.environ.get("SYMMER_TUNING", "").split(",")):   # A/B knobs, e.g. "6=0,7=32"
+        k, v = kv.split("=")
+        tuning[int(k)] = int(v)
+        ops.set_tuning(int(k), int(v))
+    tile_mode = tuning.get(6, 1) != 0                              # ordered-tile mode (default) vs sorted-hash order
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -272,12 +278,14 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         U_local = state["U"]
-        row_only = 16 * ((N_QUBITS + 63) // 64)                        # the emission kernel writes the 256 B row;
-        emit_bytes = U_local * row_only                                # the 16 B coefficient leaves in compact_kernel
+        row_only = 16 * ((N_QUBITS + 63) // 64)
+        # tile_emit_kernel writes row + coefficient (272 B per survivor); in the sorted-hash path emit_kernel
+        # writes the 256 B row and the coefficient leaves in compact_kernel
+        emit_bytes = U_local * (ROW_BYTES if tile_mode else row_only)
         achieved = emit_bytes / (kern_mean * 1e-3) / 1e9 if kern_mean > 0 else None
         phase_gbs = U_local * ROW_BYTES / (emit_mean * 1e-3) / 1e9 if emit_mean > 0 else None
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "emit_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "tile_emit_traffic.json" if tile_mode else "emit_traffic.json")
         if os.path.exists(tpath):
             traffic = float(json.load(open(tpath))["dram_bytes_per_row"]) * U_local
         path_bytes = T_local * (2 * ROW_BYTES + (U_local / T_local) * ROW_BYTES)   # SURVEY §8d model: 816 B/ct at U=T
@@ -303,12 +311,16 @@ def run_ours(args):
                             "coefficient checksum are read back"},
             "gpu_launches": int(launches),
             "clocks": clock_info,
-            "roofline": {"bound": "hbm", "kernel": "emit_kernel (row emission of the survivors: 256 B per row, one launch per step)",
+            "roofline": {"bound": "hbm", "kernel": ("tile_emit_kernel (rows + coefficients of the survivors in cross-term order: "
+                                                    "272 B per survivor, one launch per block)") if tile_mode else
+                                                   "emit_kernel (row emission of the survivors: 256 B per row, one launch per step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": kern_mean, "kernel_share_of_step": kern_mean / step_ms if step_ms else None,
                          "emit_phase_ms": emit_mean, "emit_phase_gbs": phase_gbs,
-                         "emit_phase_note": "compact_kernel + emit_kernel: 272 B (row + coefficient) per survivor",
+                         "emit_phase_note": ("tile_emit_kernel + fix-up of group sums" if tile_mode else
+                                             "compact_kernel + emit_kernel") + ": 272 B (row + coefficient) per survivor",
+                         "tuning": tuning,
                          "path_model_bytes_per_step": path_bytes,
                          "path_achieved_gbs": path_bytes / (step_ms * 1e-3) / 1e9,
                          "path_frac": path_bytes / (step_ms * 1e-3) / 1e9 / peak},

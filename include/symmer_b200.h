@@ -60,9 +60,12 @@ int sym_cross_mul(const uint64_t *a_xz, const double *a_c, int64_t M, const uint
 /* Fused product + cleanup (base.py:764-794 followed by utils.py:230-279) that never materialises
  * the M*N cross terms: dedup runs on 64-bit keys derived from the row sketches, rows are only
  * written for the survivors. zero_threshold < 0 disables the |c| > threshold filter (the
- * reference's `None`). Output rows are unique; order is first-occurrence (the reference's) for
- * products up to 2^22 cross terms and sorted-hash order above (parity is defined on canonically
- * sorted term sets).
+ * reference's `None`). Output rows are unique and leave in first-occurrence order of the
+ * reference's flattened cross-term index t = q*M + p (base.py:783-792) at every size: small
+ * products scatter by t, large ones (> 2^22 cross terms) run the ordered-tile mode (drop bit per
+ * cross term, survivors streamed tile by tile); only rows wider than 1024 qubits or with a word
+ * count that is not a power of two fall back to sorted-hash order above 2^22 cross terms (parity
+ * is defined on canonically sorted term sets).
  * n_out: device int64[1], receives the number of surviving terms. out_capacity: rows available in
  * out_xz/out_c; on overflow returns SYM_E_CAPACITY after a stream synchronise.
  * This call synchronises the stream once (it needs the survivor count to size the emit launch). */
@@ -80,6 +83,21 @@ int sym_mul_cleanup(const uint64_t *a_xz, const double *a_c, int64_t M, const ui
                     const double *b_c, int64_t N, int32_t W, double zero_threshold, uint64_t *out_xz,
                     double *out_c, int64_t out_capacity, int64_t *n_out, int64_t *n_out_host,
                     void *ws, size_t ws_bytes, void *stream);
+
+/* Same product + cleanup restricted to nblk disjoint rectangular blocks A[p0:p1) x B[q0:q1) of the
+ * cross-term grid (blocks_host: HOST int64[nblk][4] = {p0, p1, q0, q1}, nblk <= 256); one block
+ * {0, M_total, 0, N} is sym_mul_cleanup. This is the exchange-free sharded product of SURVEY.md
+ * §8e: with both operands grouped by owner class (sym_class_partition) rank r passes the blocks
+ * A_a x B_{a^r} and gets exactly the part of (A*B).cleanup() it owns. Survivors leave block by
+ * block, in (q, p) order inside a block. Same two-phase contract as sym_mul_cleanup_count/_emit. */
+size_t sym_mul_blocks_ws_bytes(int64_t M_total, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk);
+int sym_mul_blocks_count(const uint64_t *a_xz, const double *a_c, int64_t M_total, const uint64_t *b_xz,
+                         const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
+                         double zero_threshold, int64_t *n_out, int64_t *n_out_host, void *ws,
+                         size_t ws_bytes, void *stream);
+int sym_mul_blocks_emit(const uint64_t *a_xz, const double *a_c, int64_t M_total, const uint64_t *b_xz,
+                        const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
+                        int64_t U, uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- a5 cleanup: symplectic_cleanup (utils.py:230-279) / PauliwordOp.cleanup (base.py:617-638)
  * Unique rows with duplicates' coefficients summed in input order, then |c| > zero_threshold.
@@ -257,10 +275,10 @@ size_t sym_sort_pairs_ws_bytes(int64_t T);
 int sym_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t T, int32_t begin_bit, void *ws,
                    size_t ws_bytes, void *stream);
 /* Tuning knobs (A/B switches kept for measurement). which = 0: cross-term count up to which
- * sym_mul_cleanup emits in first-occurrence (reference) order instead of sorted-hash order (default
- * 2^22); 1: row emission (0 two kernels, 1 CTA-fused, 2 warp-fused); 2: radix scatter shape;
+ * sym_mul_cleanup scatters by t (above it: knob 6; default 2^22); 1: row emission (0 two kernels, 1 CTA-fused, 2 warp-fused); 2: radix scatter shape;
  * 3: extra sort bits; 4: apply/expval kernel (1 binned, 0 four-row); 5: GF(2) large path (1 blocked
- * panels, 0 one pivot per sweep). */
+ * panels, 0 one pivot per sweep); 6: large products in ordered-tile mode (1, default) or sorted-hash
+ * order (0); 7: B rows per CTA of the tiled row emission (default 16). */
 int sym_set_tuning(int32_t which, int64_t value);
 /* Measurement hook: two cudaEvent_t (as void*, NULL to disable) recorded on the stream immediately
  * before and after the row-emission kernel (emit_kernel) of the next *_emit calls, so that a

@@ -8,6 +8,7 @@
 //   2. link: every sorted position finds its nearest earlier twin inside its sort bucket (exact row compare)
 //   3. sum: each head adds the coefficients of its group in input (t) order and applies |c| > thr
 //   4. exclusive scan of keep flags -> output slots ; compact ; emit rows with 16-byte stores
+#include <algorithm>
 #include <type_traits>
 
 #include "rows.cuh"
@@ -25,10 +26,8 @@ constexpr uint8_t FLAG_HEAD = 0, FLAG_PREV = 1, FLAG_LINK = 2;
 // (full hash match, then exact word-by-word compare): none -> HEAD, the immediate predecessor ->
 // PREV, further back -> LINK (position stored in link[]).
 template <class Rows>
-__global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                    int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
+__device__ __forceinline__ void link_one(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t i,
+                                         int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
     uint8_t f = FLAG_HEAD;
     if (i > 0) {
         const uint64_t ri = sr[i];
@@ -50,6 +49,24 @@ __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const 
     flag[i] = f;
 }
 
+template <class Rows>
+__global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                                    int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    link_one(rows, fmt, sr, i, sort_shift, flag, link);
+}
+
+// the same over a worklist of sorted positions (ordered-tile mode: only records of non-singleton buckets)
+template <class Rows>
+__global__ void __launch_bounds__(256) link_work_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int sort_shift,
+                                                         const uint32_t *__restrict__ work, const uint32_t *__restrict__ n_work,
+                                                         uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
+    const uint32_t n = *n_work;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        link_one(rows, fmt, sr, (int64_t)work[k], sort_shift, flag, link);
+}
+
 __device__ __forceinline__ uint8_t keep_test(double re, double im, double thr) {
     return (thr < 0.0) ? 1 : (hypot(re, im) > thr ? 1 : 0);
 }
@@ -61,17 +78,20 @@ __device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_
 
 // sum: each HEAD walks forward through its bucket and adds the coefficients of the records whose
 // chain leads back to it, in input (t) order like np.add.at — deterministic, no atomics.
-template <class Rows, bool BY_T, bool DIRECT>
-__global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                   int sort_shift, const uint8_t *__restrict__ flag,
-                                                   const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
-                                                   uint8_t *__restrict__ keep, uint8_t *__restrict__ multi) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
+// TILE (ordered-tile mode, see rows.cuh): nothing is written for a record that survives as a
+// singleton; a record that does not survive sets its drop bit, and a surviving group head leaves
+// its sum in acc[i] with multi[i] = 1 for the fix-up pass after the row emission.
+template <class Rows, bool BY_T, bool DIRECT, bool TILE>
+__device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                        int64_t i, int sort_shift, const uint8_t *__restrict__ flag,
+                                        const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
+                                        uint8_t *__restrict__ keep, uint8_t *__restrict__ multi, const TileMap &tm) {
     const uint64_t r0 = sr[i];
     const int64_t d = BY_T ? (int64_t)fmt.t(r0) : i;
+    if (TILE) multi[d] = 0;
     if (flag[i] != FLAG_HEAD) {
-        keep[d] = 0;
+        if (TILE) tm.mark_dropped(fmt.t(r0));
+        else keep[d] = 0;
         return;
     }
     double re = 0.0, im = 0.0;
@@ -98,6 +118,20 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
         }
         prev_mine = mine;
     }
+    if (TILE) {
+        if (is_multi) {
+            if (keep_test(re, im, thr)) {
+                acc[d] = make_double2(re, im);
+                multi[d] = 1;
+            } else {
+                tm.mark_dropped(fmt.t(r0));
+            }
+        } else if (!(thr < 0.0 || rows.all_pass())) {
+            rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+            if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r0));
+        }
+        return;
+    }
     if (is_multi || !DIRECT) {
         if (!have) rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
         acc[d] = make_double2(re, im);
@@ -109,6 +143,57 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
         rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
         keep[d] = keep_test(re, im, thr);
     }
+}
+
+template <class Rows, bool BY_T, bool DIRECT>
+__global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                                   int sort_shift, const uint8_t *__restrict__ flag,
+                                                   const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
+                                                   uint8_t *__restrict__ keep, uint8_t *__restrict__ multi) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    sum_one<Rows, BY_T, DIRECT, false>(rows, fmt, sr, T, i, sort_shift, flag, link, thr, acc, keep, multi, TileMap());
+}
+
+// ordered-tile mode: the reduction over the worklist (records of non-singleton buckets)
+template <class Rows>
+__global__ void __launch_bounds__(256) sum_work_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                                        int sort_shift, const uint32_t *__restrict__ work,
+                                                        const uint32_t *__restrict__ n_work, const uint8_t *__restrict__ flag,
+                                                        const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
+                                                        uint8_t *__restrict__ multi, TileMap tm) {
+    const uint32_t n = *n_work;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        sum_one<Rows, false, true, true>(rows, fmt, sr, T, (int64_t)work[k], sort_shift, flag, link, thr, acc, nullptr, multi, tm);
+}
+
+// Ordered-tile mode, first pass over the sorted records: a record whose sort bucket holds nothing
+// else is a singleton survivor (or fails the threshold on its own) — no link, no sum, nothing
+// written. Only the records of shared buckets go on the worklist for link / sum / fix-up.
+template <class Rows>
+__global__ void __launch_bounds__(256) tile_classify_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                                             int sort_shift, double thr, TileMap tm,
+                                                             uint32_t *__restrict__ work, uint32_t *__restrict__ n_work) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool shared_bucket = false;
+    if (i < T) {
+        const uint64_t r = sr[i];
+        const bool same_prev = i > 0 && ((r ^ sr[i - 1]) >> sort_shift) == 0;
+        const bool same_next = i + 1 < T && ((r ^ sr[i + 1]) >> sort_shift) == 0;
+        shared_bucket = same_prev || same_next;
+        if (!shared_bucket && !(thr < 0.0 || rows.all_pass())) {
+            double re, im;
+            rows.coeff(fmt.t(r), fmt.e(r), re, im);
+            if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r));
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, shared_bucket);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(n_work, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (shared_bucket) work[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
 }
 
 // pass_all flag of a product: min|a| * min|b| clears the threshold with a 4x margin (the rounded
@@ -556,6 +641,212 @@ static int dedup_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const Rows &r
 #undef EMIT_LAUNCH
     SYM_LAUNCH_OK();
     if (g_emit_ev1) SYM_CUDA_OK(cudaEventRecord(g_emit_ev1, st));
+    return SYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered-tile mode (rows.cuh): survivors in cross-term order, tiled streaming row emission
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ TileBlock tile_block_of_segment(const TileMap &tm, uint32_t s) {
+    TileBlock blk = tm.first;
+    for (int b = 1; b < tm.nblk; ++b) {
+        const TileBlock nb = tm.blocks[b];
+        if (s < nb.seg_base) break;
+        blk = nb;
+    }
+    return blk;
+}
+
+// survivors per segment = valid rows whose drop bit is clear
+__global__ void __launch_bounds__(256) seg_count_kernel(TileMap tm) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= tm.n_seg) return;
+    const TileBlock blk = tile_block_of_segment(tm, s);
+    const uint32_t ptile = (s - blk.seg_base) % blk.ptiles;
+    const uint4 d = reinterpret_cast<const uint4 *>(tm.drop)[s];
+    tm.segoff[s] = __popc(tile_valid_word(blk.m_blk, ptile, 0) & ~d.x) + __popc(tile_valid_word(blk.m_blk, ptile, 1) & ~d.y) +
+                   __popc(tile_valid_word(blk.m_blk, ptile, 2) & ~d.z) + __popc(tile_valid_word(blk.m_blk, ptile, 3) & ~d.w);
+}
+
+// Row + coefficient emission of one block, CTA = (tile of TILE_ROWS rows of A) x (QG rows of B).
+// Thread = (row, 16-byte chunk); the A chunks of its UN rows stay in registers for the whole q loop,
+// the B row is one broadcast 16-byte load per q, so the only traffic that scales with the output
+// is the output itself: consecutive survivors of a segment go to consecutive 16-byte slots
+// (streaming stores). The first TILE_ROWS threads also write the survivors' coefficients
+// a[p]*b[q]*i^e (e from the bit planes); group sums overwrite theirs in the fix-up pass.
+template <int LW>
+__global__ void __launch_bounds__((TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256)
+    tile_emit_kernel(const uint4 *__restrict__ A, const double2 *__restrict__ Ac, const uint4 *__restrict__ B,
+                     const double2 *__restrict__ Bc, TileBlock blk, uint32_t qg, const uint32_t *__restrict__ drop,
+                     const uint2 *__restrict__ e01, const uint32_t *__restrict__ segoff, uint4 *__restrict__ out_xz,
+                     double2 *__restrict__ out_c) {
+    constexpr int TH = (TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256;
+    constexpr int CH = 1 << LW;
+    constexpr int RP = TH >> LW;          // rows per pass
+    constexpr int UN = TILE_ROWS / RP;    // passes per segment
+    const uint32_t ptile = blockIdx.x;
+    const uint32_t r_in = threadIdx.x >> LW, c = threadIdx.x & (CH - 1);
+    const uint32_t pl0 = ptile * TILE_ROWS;
+
+    uint4 a[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+        const uint32_t pl = pl0 + u * RP + r_in;
+        a[u] = pl < blk.m_blk ? A[((size_t)(blk.p0 + pl) << LW) + c] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const bool coeff_thread = threadIdx.x < TILE_ROWS;
+    double2 ac = make_double2(0.0, 0.0);
+    if (coeff_thread && pl0 + threadIdx.x < blk.m_blk) ac = Ac[blk.p0 + pl0 + threadIdx.x];
+    uint32_t vm[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) vm[w] = tile_valid_word(blk.m_blk, ptile, w);
+
+    const uint32_t q_lo = blockIdx.y * qg;
+    const uint32_t q_hi = min(blk.nq, q_lo + qg);
+    for (uint32_t ql = q_lo; ql < q_hi; ++ql) {
+        const uint32_t s = blk.seg_base + ql * blk.ptiles + ptile;
+        const uint4 d = reinterpret_cast<const uint4 *>(drop)[s];
+        const uint32_t base = segoff[s];
+        const uint4 b = B[((size_t)(blk.q0 + ql) << LW) + c];
+        uint32_t k[4] = {vm[0] & ~d.x, vm[1] & ~d.y, vm[2] & ~d.z, vm[3] & ~d.w};
+        uint32_t pre[4];
+        pre[0] = base;
+        pre[1] = pre[0] + __popc(k[0]);
+        pre[2] = pre[1] + __popc(k[1]);
+        pre[3] = pre[2] + __popc(k[2]);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const uint32_t j = u * RP + r_in;
+            const uint32_t kw = k[j >> 5], bit = j & 31;
+            if ((kw >> bit) & 1u) {
+                const uint32_t slot = pre[j >> 5] + __popc(kw & ((1u << bit) - 1u));
+                store_streaming(out_xz + (((size_t)slot) << LW) + c,
+                                make_uint4(a[u].x ^ b.x, a[u].y ^ b.y, a[u].z ^ b.z, a[u].w ^ b.w));
+            }
+        }
+        if (coeff_thread) {
+            const uint32_t j = threadIdx.x;
+            const uint32_t kw = k[j >> 5], bit = j & 31;
+            if ((kw >> bit) & 1u) {
+                const uint32_t slot = pre[j >> 5] + __popc(kw & ((1u << bit) - 1u));
+                const uint2 ep = e01[4 * (size_t)s + (j >> 5)];
+                const int e = (int)((ep.x >> bit) & 1u) | (int)(((ep.y >> bit) & 1u) << 1);
+                const double2 bc = Bc[blk.q0 + ql];
+                double re, im;
+                cmul(ac.x, ac.y, bc.x, bc.y, re, im);
+                mul_i_pow(re, im, e);
+                out_c[slot] = make_double2(re, im);
+            }
+        }
+    }
+}
+
+// group sums of the surviving heads -> their output slots (after tile_emit_kernel wrote a[p]*b[q]*i^e there)
+__global__ void __launch_bounds__(256) tile_fixup_kernel(TileMap tm, RecFmt fmt, const uint64_t *__restrict__ sr,
+                                                          const uint32_t *__restrict__ work, const uint32_t *__restrict__ n_work,
+                                                          const uint8_t *__restrict__ multi, const double2 *__restrict__ acc,
+                                                          double2 *__restrict__ out_c) {
+    const uint32_t n = *n_work;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t i = work[k];
+        if (!multi[i]) continue;
+        const uint32_t slot = tm.slot_of(fmt.t(sr[i]));
+        if (slot != 0xffffffffu) out_c[slot] = acc[i];
+    }
+}
+
+int g_tile_qgroup = 16;   // tuning knob 7: B rows per CTA of tile_emit_kernel
+
+int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, double thr,
+                             int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < dedup_ws_bytes(T)) {
+        set_error("workspace too small: need %zu bytes, got %zu", dedup_ws_bytes(T), ws_bytes);
+        return SYM_E_WORKSPACE;
+    }
+    DedupLayout L = dedup_layout(ws, ws_bytes, T);
+    if (!L.ok) {
+        set_error("workspace arena exhausted");
+        return SYM_E_WORKSPACE;
+    }
+    const int begin = sort_begin_bit(T, fmt);
+    uint64_t *sr = nullptr;
+    SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
+    const unsigned nb = (unsigned)((T + 255) / 256);
+    ProductRows rows_sum = rows;
+    if (thr >= 0.0 && rows.N > 0) {
+        min_abs_flag_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
+                                                reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr, L.total + 2);
+        SYM_LAUNCH_OK();
+        rows_sum.pass_all = L.total + 2;
+    }
+    // worklist of the records that share a sort bucket (L.slot is free in this mode), counter in L.total[1]
+    uint32_t *work = L.slot, *n_work = L.total + 1;
+    SYM_CUDA_OK(cudaMemsetAsync(n_work, 0, sizeof(uint32_t), st));
+    tile_classify_kernel<ProductRows><<<nb, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, thr, tm, work, n_work);
+    SYM_LAUNCH_OK();
+    const unsigned nbw = (unsigned)std::min<int64_t>((int64_t)nb, (int64_t)num_sms() * 16);
+    link_work_kernel<ProductRows><<<nbw, 256, 0, st>>>(rows, fmt, sr, begin, work, n_work, L.flag, L.link);
+    SYM_LAUNCH_OK();
+    sum_work_kernel<ProductRows><<<nbw, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, work, n_work, L.flag, L.link, thr, L.acc,
+                                                      L.multi, tm);
+    SYM_LAUNCH_OK();
+    seg_count_kernel<<<(tm.n_seg + 255) / 256, 256, 0, st>>>(tm);
+    SYM_LAUNCH_OK();
+    SYM_TRY(scan_exclusive_u32(tm.segoff, tm.segoff, (int64_t)tm.n_seg, L.total, L.scratch, st));
+    if (n_out) {
+        total_to_i64_kernel<<<1, 1, 0, st>>>(L.total, n_out);
+        SYM_LAUNCH_OK();
+    }
+    uint32_t U32 = 0;
+    SYM_CUDA_OK(cudaMemcpyAsync(&U32, L.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SYM_CUDA_OK(cudaStreamSynchronize(st));
+    if (n_out_host) *n_out_host = (int64_t)U32;
+    return SYM_OK;
+}
+
+int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
+                             const TileBlock *blocks_host, int64_t U, uint64_t *out_xz, double *out_c, void *ws,
+                             size_t ws_bytes, cudaStream_t st) {
+    if (T == 0 || U == 0) return SYM_OK;
+    DedupLayout L = dedup_layout(ws, ws_bytes, T);
+    if (!L.ok) {
+        set_error("workspace arena exhausted");
+        return SYM_E_WORKSPACE;
+    }
+    const uint64_t *sr = (T > 1 && sorted_in_alt(sort_begin_bit(T, fmt))) ? L.alt : recs;
+    const int chunks = rows.words / 2;
+    const uint4 *A4 = reinterpret_cast<const uint4 *>(rows.A), *B4 = reinterpret_cast<const uint4 *>(rows.B);
+    const double2 *Ac = reinterpret_cast<const double2 *>(rows.Ac), *Bc = reinterpret_cast<const double2 *>(rows.Bc);
+    uint4 *o = reinterpret_cast<uint4 *>(out_xz);
+    double2 *oc = reinterpret_cast<double2 *>(out_c);
+    const uint32_t qg = (uint32_t)(g_tile_qgroup < 1 ? 1 : g_tile_qgroup);
+    if (g_emit_ev0) SYM_CUDA_OK(cudaEventRecord(g_emit_ev0, st));
+    for (int b = 0; b < tm.nblk; ++b) {
+        const TileBlock blk = blocks_host[b];
+        if (blk.m_blk == 0 || blk.nq == 0) continue;
+        dim3 grid(blk.ptiles, (blk.nq + qg - 1) / qg);
+        if (grid.y > 65535) {
+            set_error("too many B rows for one tile launch");
+            return SYM_E_UNSUPPORTED;
+        }
+#define TILE_EMIT(LW) \
+    tile_emit_kernel<LW><<<grid, (TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256, 0, st>>>(A4, Ac, B4, Bc, blk, qg, tm.drop, \
+                                                                                        tm.e01, tm.segoff, o, oc)
+        switch (chunks) {
+            case 1: TILE_EMIT(0); break;
+            case 2: TILE_EMIT(1); break;
+            case 4: TILE_EMIT(2); break;
+            case 8: TILE_EMIT(3); break;
+            case 16: TILE_EMIT(4); break;
+            default: set_error("ordered-tile mode needs 1, 2, 4, 8 or 16 chunks per row"); return SYM_E_UNSUPPORTED;
+        }
+#undef TILE_EMIT
+        SYM_LAUNCH_OK();
+    }
+    if (g_emit_ev1) SYM_CUDA_OK(cudaEventRecord(g_emit_ev1, st));
+    const unsigned nbw = (unsigned)std::min<int64_t>((T + 255) / 256, (int64_t)num_sms() * 16);
+    tile_fixup_kernel<<<nbw, 256, 0, st>>>(tm, fmt, sr, L.slot, L.total + 1, L.multi, L.acc, oc);
+    SYM_LAUNCH_OK();
     return SYM_OK;
 }
 

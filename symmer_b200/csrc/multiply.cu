@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
     const uint64_t *__restrict__ a_xz, const uint64_t *__restrict__ a_sk, const int32_t *__restrict__ a_y, uint32_t M_total,
     uint32_t p_begin, uint32_t p_end, const uint64_t *__restrict__ b_xz, const uint64_t *__restrict__ b_sk,
     const int32_t *__restrict__ b_y, uint32_t N, uint32_t q_off, int W, uint64_t key_mask, RecFmt fmt,
-    uint64_t *__restrict__ recs) {
+    uint64_t *__restrict__ recs, uint2 *__restrict__ e01, uint32_t seg_base, uint32_t ptiles) {
     // B tile: QCH rows, (x_w, z_w) interleaved so one 16-byte shared load feeds a word step
     __shared__ ulonglong2 sb[PAIR_QCH][WT];
     __shared__ uint64_t sb_sk[PAIR_QCH];
@@ -72,10 +72,14 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
         for (int w = 0; w < WT; ++w) xa[w] = za[w] = 0ull;
     }
     __syncthreads();
-    if (!active) return;
+    // whole warps stay alive for the ballots of the phase bit planes (ordered-tile mode)
+    if (!__any_sync(0xffffffffu, active)) return;
 
     const uint32_t m_blk = p_end - p_begin;
     const uint32_t p_local = p - p_begin;
+    // word of the warp's 32 rows in the segment bit planes (rows.cuh): 256 rows per CTA = 2 tiles
+    const uint32_t ew_tile = blockIdx.x * (PAIR_THREADS / TILE_ROWS) + (threadIdx.x / TILE_ROWS);
+    const uint32_t ew_word = (threadIdx.x % TILE_ROWS) >> 5;
     for (uint32_t qi = 0; qi < nq; ++qi) {
         uint64_t s = 0, c0 = 0, c1 = 0;
 #pragma unroll
@@ -86,9 +90,14 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
             c1 ^= c0 & v;
             c0 ^= v;
         }
-        const int e = finish_phase(ya, sb_y[qi], s, c0, c1);
+        const int e = active ? finish_phase(ya, sb_y[qi], s, c0, c1) : 0;
         const size_t j = (size_t)(q0 + qi) * m_blk + p_local;
-        recs[j] = fmt.make(mix64(ska ^ sb_sk[qi]) & key_mask, (uint64_t)(q_off + q0 + qi) * M_total + p, e);
+        if (active) recs[j] = fmt.make(mix64(ska ^ sb_sk[qi]) & key_mask, (uint64_t)(q_off + q0 + qi) * M_total + p, e);
+        if (e01 != nullptr) {
+            const uint32_t e_lo = __ballot_sync(0xffffffffu, e & 1), e_hi = __ballot_sync(0xffffffffu, e & 2);
+            if ((threadIdx.x & 31) == 0)
+                e01[4 * ((size_t)seg_base + (size_t)(q0 + qi) * ptiles + ew_tile) + ew_word] = make_uint2(e_lo, e_hi);
+        }
     }
 }
 
@@ -119,7 +128,7 @@ __global__ void __launch_bounds__(256) pair_records_generic_kernel(
 static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const int32_t *a_y, int64_t M_total,
                                int64_t p_begin, int64_t p_end, const uint64_t *b_xz, const uint64_t *b_sk,
                                const int32_t *b_y, int64_t N, int W, RecFmt fmt, uint64_t *recs, cudaStream_t st,
-                               int64_t q_off = 0) {
+                               int64_t q_off = 0, uint2 *e01 = nullptr, uint32_t seg_base = 0, uint32_t ptiles = 0) {
     // b_xz / b_sk / b_y point at B row q_off; N rows from there. t uses the global index q_off + q.
     const int64_t m_blk = p_end - p_begin;
     if (m_blk <= 0 || N <= 0) return SYM_OK;
@@ -127,7 +136,7 @@ static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const
 #define PAIR_CASE(WT)                                                                                               \
     pair_records_kernel<WT><<<grid, PAIR_THREADS, 0, st>>>(a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin,   \
                                                            (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N,           \
-                                                           (uint32_t)q_off, W, g_key_mask, fmt, recs)
+                                                           (uint32_t)q_off, W, g_key_mask, fmt, recs, e01, seg_base, ptiles)
     if (grid.y > 65535) {
         set_error("too many B rows for one launch (N=%lld)", (long long)N);
         return SYM_E_UNSUPPORTED;
@@ -341,16 +350,13 @@ extern "C" int sym_dedup_records(uint64_t *recs, int64_t T, const uint64_t *a_xz
     return sym_dedup_records_emit(recs, T, a_xz, a_c, M_total, b_xz, b_c, N, W, U, out_xz, out_c, ws, ws_bytes, stream);
 }
 
-extern "C" size_t sym_mul_cleanup_ws_bytes(int64_t M, int64_t N, int32_t W) {
-    int64_t T = M * N;
-    if (T < 1) T = 1;
-    return sym_pair_records_ws_bytes(M, N, W) + arena_need((size_t)T, 8) + dedup_ws_bytes(T) + 1024;
-}
-
 // Below this many cross terms the product is emitted in first-occurrence (reference) order; above,
 // in sorted-hash order, which keeps every pass of the dedup streaming (no T-sized scatters).
 static int64_t g_by_t_limit = (int64_t)1 << 22;
-namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; extern int g_rref_variant; }
+// tuning knob 6: 1 (default) = products above the limit use the ordered-tile mode (first-occurrence
+// order at every size, streaming tiled row emission); 0 = the sorted-hash order path
+static int g_ordered_tiles = 1;
+namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; extern int g_rref_variant; extern int g_tile_qgroup; }
 
 extern "C" int sym_set_tuning(int32_t which, int64_t value) {
     if (which == 0) {
@@ -377,6 +383,14 @@ extern "C" int sym_set_tuning(int32_t which, int64_t value) {
         symb::g_rref_variant = (int)value;
         return SYM_OK;
     }
+    if (which == 6) {
+        g_ordered_tiles = (int)value;
+        return SYM_OK;
+    }
+    if (which == 7) {
+        symb::g_tile_qgroup = (int)value;
+        return SYM_OK;
+    }
     set_error("unknown tuning knob %d", which);
     return SYM_E_INVALID;
 }
@@ -386,79 +400,198 @@ extern "C" int sym_set_emit_events(void *before_event, void *after_event) {
     return SYM_OK;
 }
 
-// workspace layout shared by the count and emit phases
-struct MulPlan {
+// ---------------------------------------------------------------------------------------------
+// product + cleanup of a list of rectangular blocks of A x B (one block = the whole product)
+// ---------------------------------------------------------------------------------------------
+enum MulMode { MODE_BY_T = 0, MODE_SORTED = 1, MODE_TILES = 2 };
+
+struct MulBlocksPlan {
+    MulMode mode;
+    int64_t T;
+    int nblk;
+    uint32_t n_seg;
+    TileBlock blocks[256];
+    // workspace slices
     uint64_t *a_sk, *b_sk;
     int32_t *a_y, *b_y;
     uint64_t *recs;
+    TileBlock *d_blocks;
+    uint32_t *drop;
+    uint2 *e01;
+    uint32_t *segoff;
     void *rest;
     size_t rest_bytes;
-    bool ok;
+    size_t need;
 };
 
-static MulPlan mul_plan_layout(void *ws, size_t ws_bytes, int64_t M, int64_t N) {
-    Arena ar(ws, ws_bytes);
-    MulPlan P;
-    const int64_t T = M * N;
-    P.a_sk = ar.take<uint64_t>((size_t)(M > 0 ? M : 1));
-    P.b_sk = ar.take<uint64_t>((size_t)(N > 0 ? N : 1));
-    P.a_y = ar.take<int32_t>((size_t)(M > 0 ? M : 1));
-    P.b_y = ar.take<int32_t>((size_t)(N > 0 ? N : 1));
-    P.recs = ar.take<uint64_t>((size_t)(T > 0 ? T : 1));
-    P.ok = P.recs != nullptr;
-    P.rest = ar.base + ar.off;
-    P.rest_bytes = ws_bytes > ar.off ? ws_bytes - ar.off : 0;
-    return P;
+static int mul_blocks_plan(int64_t M_total, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk, void *ws,
+                           size_t ws_bytes, MulBlocksPlan &P) {
+    SYM_REQUIRE(M_total >= 0 && N >= 0 && W >= 1, "bad size");
+    SYM_REQUIRE(nblk >= 0 && nblk <= 256, "at most 256 blocks");
+    SYM_REQUIRE(M_total * N < (int64_t)4000000000LL, "M_total*N must be < 4e9 cross terms per call");
+    SYM_REQUIRE(nblk == 0 || blocks_host != nullptr, "blocks_host is NULL");
+    P.nblk = nblk;
+    P.T = 0;
+    int64_t segs = 0;
+    for (int b = 0; b < nblk; ++b) {
+        const int64_t *q = blocks_host + 4 * b;
+        SYM_REQUIRE(0 <= q[0] && q[0] <= q[1] && q[1] <= M_total, "bad A row block");
+        SYM_REQUIRE(0 <= q[2] && q[2] <= q[3] && q[3] <= N, "bad B row block");
+        for (int o = 0; o < b; ++o) {   // rectangles must not overlap: every cross term is generated once
+            const int64_t *r = blocks_host + 4 * o;
+            const bool disjoint = q[1] <= r[0] || r[1] <= q[0] || q[3] <= r[2] || r[3] <= q[2] || q[0] == q[1] ||
+                                  q[2] == q[3] || r[0] == r[1] || r[2] == r[3];
+            SYM_REQUIRE(disjoint, "blocks overlap");
+        }
+        TileBlock &tb = P.blocks[b];
+        tb.p0 = (uint32_t)q[0];
+        tb.m_blk = (uint32_t)(q[1] - q[0]);
+        tb.q0 = (uint32_t)q[2];
+        tb.nq = (uint32_t)(q[3] - q[2]);
+        tb.ptiles = (tb.m_blk + TILE_ROWS - 1) / TILE_ROWS;
+        tb.seg_base = (uint32_t)segs;
+        segs += (int64_t)tb.nq * tb.ptiles;
+        P.T += (int64_t)tb.m_blk * tb.nq;
+    }
+    const bool whole = nblk == 1 && P.blocks[0].p0 == 0 && P.blocks[0].q0 == 0 && P.blocks[0].m_blk == M_total &&
+                       P.blocks[0].nq == N;
+    const bool tiles_ok = g_ordered_tiles != 0 && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16) &&
+                          segs * TILE_ROWS <= 4 * P.T + 4096 && segs < (int64_t)1 << 31;
+    if (whole && P.T <= g_by_t_limit) P.mode = MODE_BY_T;
+    else if (tiles_ok) P.mode = MODE_TILES;
+    else P.mode = MODE_SORTED;
+    P.n_seg = P.mode == MODE_TILES ? (uint32_t)segs : 0u;
+
+    Arena ar(ws, ws ? ws_bytes : 0);
+    const size_t m = (size_t)(M_total > 0 ? M_total : 1), n = (size_t)(N > 0 ? N : 1), t = (size_t)(P.T > 0 ? P.T : 1);
+    size_t need = arena_need(m, 8) + arena_need(n, 8) + arena_need(m, 4) + arena_need(n, 4) + arena_need(t, 8);
+    P.a_sk = ar.take<uint64_t>(m);
+    P.b_sk = ar.take<uint64_t>(n);
+    P.a_y = ar.take<int32_t>(m);
+    P.b_y = ar.take<int32_t>(n);
+    P.recs = ar.take<uint64_t>(t);
+    P.d_blocks = nullptr;
+    P.drop = nullptr;
+    P.e01 = nullptr;
+    P.segoff = nullptr;
+    if (P.mode == MODE_TILES) {
+        const size_t sg = (size_t)P.n_seg;
+        need += arena_need(256, sizeof(TileBlock)) + arena_need(4 * sg, 4) + arena_need(4 * sg, 8) + arena_need(sg + 1, 4);
+        P.d_blocks = ar.take<TileBlock>(256);
+        P.drop = ar.take<uint32_t>(4 * sg);
+        P.e01 = ar.take<uint2>(4 * sg);
+        P.segoff = ar.take<uint32_t>(sg + 1);
+    }
+    P.rest = ws ? (void *)(ar.base + ar.off) : nullptr;
+    P.rest_bytes = (ws && ws_bytes > ar.off) ? ws_bytes - ar.off : 0;
+    P.need = need + dedup_ws_bytes(P.T) + 1024;
+    return SYM_OK;
 }
 
-static int mul_check(int64_t M, int64_t N, int32_t W, size_t ws_bytes) {
-    SYM_REQUIRE(M >= 0 && N >= 0 && W >= 1, "bad size");
-    SYM_REQUIRE(M * N < (int64_t)4000000000LL, "M*N must be < 4e9 cross terms per call");
-    if (M * N > 0 && ws_bytes < sym_mul_cleanup_ws_bytes(M, N, W)) {
-        set_error("workspace too small: need %zu", sym_mul_cleanup_ws_bytes(M, N, W));
+static TileMap tile_map_of(const MulBlocksPlan &P, int64_t M_total) {
+    TileMap tm;
+    tm.first = P.blocks[0];
+    tm.blocks = P.d_blocks;
+    tm.nblk = P.nblk;
+    tm.M = (uint32_t)M_total;
+    tm.n_seg = P.n_seg;
+    tm.drop = P.drop;
+    tm.e01 = P.e01;
+    tm.segoff = P.segoff;
+    return tm;
+}
+
+extern "C" size_t sym_mul_blocks_ws_bytes(int64_t M_total, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk) {
+    MulBlocksPlan P;
+    if (mul_blocks_plan(M_total, N, W, blocks_host, nblk, nullptr, 0, P) != SYM_OK) return 0;
+    return P.need;
+}
+
+extern "C" int sym_mul_blocks_count(const uint64_t *a_xz, const double *a_c, int64_t M_total, const uint64_t *b_xz,
+                                    const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
+                                    double zero_threshold, int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes,
+                                    void *stream) {
+    MulBlocksPlan P;
+    SYM_TRY(mul_blocks_plan(M_total, N, W, blocks_host, nblk, ws, ws_bytes, P));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P.T == 0) {
+        if (n_out) SYM_CUDA_OK(cudaMemsetAsync(n_out, 0, sizeof(int64_t), st));
+        if (n_out_host) *n_out_host = 0;
+        return SYM_OK;
+    }
+    if (ws == nullptr || ws_bytes < P.need) {
+        set_error("workspace too small: need %zu bytes, got %zu", P.need, ws_bytes);
         return SYM_E_WORKSPACE;
     }
-    return SYM_OK;
+    SYM_TRY(sym_sketch_rows(a_xz, M_total, W, P.a_sk, st));
+    SYM_TRY(sym_sketch_rows(b_xz, N, W, P.b_sk, st));
+    SYM_TRY(sym_ycount(a_xz, M_total, W, P.a_y, st));
+    SYM_TRY(sym_ycount(b_xz, N, W, P.b_y, st));
+    RecFmt fmt{t_bits_for(M_total * N)};
+    if (P.mode == MODE_TILES) {
+        if (P.nblk > 1)   // block 0 travels inside the TileMap kernel argument
+            SYM_CUDA_OK(cudaMemcpyAsync(P.d_blocks, P.blocks, sizeof(TileBlock) * (size_t)P.nblk, cudaMemcpyHostToDevice, st));
+        SYM_CUDA_OK(cudaMemsetAsync(P.drop, 0, sizeof(uint32_t) * 4 * (size_t)P.n_seg, st));
+    }
+    size_t off = 0;
+    for (int b = 0; b < P.nblk; ++b) {
+        const TileBlock &tb = P.blocks[b];
+        SYM_TRY(launch_pair_records(a_xz, P.a_sk, P.a_y, M_total, tb.p0, (int64_t)tb.p0 + tb.m_blk,
+                                    b_xz + (size_t)tb.q0 * 2 * W, P.b_sk + tb.q0, P.b_y + tb.q0, tb.nq, W, fmt, P.recs + off,
+                                    st, tb.q0, P.e01, tb.seg_base, tb.ptiles));
+        off += (size_t)tb.m_blk * tb.nq;
+    }
+    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
+    if (P.mode == MODE_TILES)
+        return dedup_product_plan_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), zero_threshold, n_out, n_out_host,
+                                        P.rest, P.rest_bytes, st);
+    return dedup_product_plan(P.recs, P.T, fmt, rows, P.mode == MODE_BY_T, zero_threshold, n_out, n_out_host, P.rest,
+                              P.rest_bytes, st);
+}
+
+extern "C" int sym_mul_blocks_emit(const uint64_t *a_xz, const double *a_c, int64_t M_total, const uint64_t *b_xz,
+                                   const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
+                                   int64_t U, uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, void *stream) {
+    MulBlocksPlan P;
+    SYM_TRY(mul_blocks_plan(M_total, N, W, blocks_host, nblk, ws, ws_bytes, P));
+    if (P.T == 0 || U == 0) return SYM_OK;
+    SYM_REQUIRE(U >= 0 && U <= P.T, "bad survivor count");
+    if (ws == nullptr || ws_bytes < P.need) {
+        set_error("workspace too small: need %zu bytes, got %zu", P.need, ws_bytes);
+        return SYM_E_WORKSPACE;
+    }
+    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
+    RecFmt fmt{t_bits_for(M_total * N)};
+    if (P.mode == MODE_TILES)
+        return dedup_product_emit_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.blocks, U, out_xz, out_c, P.rest,
+                                        P.rest_bytes, (cudaStream_t)stream);
+    return dedup_product_emit(P.recs, P.T, fmt, rows, P.mode == MODE_BY_T, U, out_xz, out_c, P.rest, P.rest_bytes,
+                              (cudaStream_t)stream);
+}
+
+// the whole product = one block
+extern "C" size_t sym_mul_cleanup_ws_bytes(int64_t M, int64_t N, int32_t W) {
+    const int64_t blk[4] = {0, M, 0, N};
+    // sized for either mode, so that a tuning-knob change between calls never invalidates a workspace
+    const int64_t T = M * N > 0 ? M * N : 1;
+    const size_t segs = (size_t)(N > 0 ? N : 1) * (size_t)((M + TILE_ROWS - 1) / TILE_ROWS + 1);
+    (void)blk;
+    return sym_pair_records_ws_bytes(M, N, W) + arena_need((size_t)T, 8) + dedup_ws_bytes(T) +
+           arena_need(256, sizeof(TileBlock)) + arena_need(4 * segs, 4) + arena_need(4 * segs, 8) + arena_need(segs + 1, 4) + 2048;
 }
 
 extern "C" int sym_mul_cleanup_count(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz,
                                      const double *b_c, int64_t N, int32_t W, double zero_threshold, int64_t *n_out,
                                      int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream) {
-    SYM_TRY(mul_check(M, N, W, ws_bytes));
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t T = M * N;
-    if (T == 0) {
-        if (n_out) SYM_CUDA_OK(cudaMemsetAsync(n_out, 0, sizeof(int64_t), st));
-        if (n_out_host) *n_out_host = 0;
-        return SYM_OK;
-    }
-    MulPlan P = mul_plan_layout(ws, ws_bytes, M, N);
-    if (!P.ok) {
-        set_error("workspace arena exhausted");
-        return SYM_E_WORKSPACE;
-    }
-    SYM_TRY(sym_sketch_rows(a_xz, M, W, P.a_sk, st));
-    SYM_TRY(sym_sketch_rows(b_xz, N, W, P.b_sk, st));
-    SYM_TRY(sym_ycount(a_xz, M, W, P.a_y, st));
-    SYM_TRY(sym_ycount(b_xz, N, W, P.b_y, st));
-    RecFmt fmt{t_bits_for(T)};
-    SYM_TRY(launch_pair_records(a_xz, P.a_sk, P.a_y, M, 0, M, b_xz, P.b_sk, P.b_y, N, W, fmt, P.recs, st));
-    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W, (uint32_t)N};
-    return dedup_product_plan(P.recs, T, fmt, rows, T <= g_by_t_limit, zero_threshold, n_out, n_out_host, P.rest,
-                              P.rest_bytes, st);
+    const int64_t blk[4] = {0, M, 0, N};
+    return sym_mul_blocks_count(a_xz, a_c, M, b_xz, b_c, N, W, blk, 1, zero_threshold, n_out, n_out_host, ws, ws_bytes, stream);
 }
 
 extern "C" int sym_mul_cleanup_emit(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz,
                                     const double *b_c, int64_t N, int32_t W, int64_t U, uint64_t *out_xz, double *out_c,
                                     void *ws, size_t ws_bytes, void *stream) {
-    SYM_TRY(mul_check(M, N, W, ws_bytes));
-    const int64_t T = M * N;
-    if (T == 0 || U == 0) return SYM_OK;
-    MulPlan P = mul_plan_layout(ws, ws_bytes, M, N);
-    ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M, 2 * W, (uint32_t)N};
-    RecFmt fmt{t_bits_for(T)};
-    return dedup_product_emit(P.recs, T, fmt, rows, T <= g_by_t_limit, U, out_xz, out_c, P.rest, P.rest_bytes,
-                              (cudaStream_t)stream);
+    const int64_t blk[4] = {0, M, 0, N};
+    return sym_mul_blocks_emit(a_xz, a_c, M, b_xz, b_c, N, W, blk, 1, U, out_xz, out_c, ws, ws_bytes, stream);
 }
 
 extern "C" int sym_mul_cleanup(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz, const double *b_c,

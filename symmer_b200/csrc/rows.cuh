@@ -101,6 +101,75 @@ struct PlainRows {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Ordered-tile mode of a product (large T): the survivors leave in the order of the cross-term
+// index t = q*M + p (the reference's first-occurrence order) and the row emission streams
+// rectangular tiles of A x B instead of gathering rows in sorted-hash order.
+// The cross terms of block b (rows [p0, p0+m_blk) of A against rows [q0, q0+nq) of B) are cut
+// into SEGMENTS of TILE_ROWS consecutive p for one q; segment id
+//   s = seg_base + (q - q0) * ptiles + (p - p0) / TILE_ROWS,  bit = (p - p0) % TILE_ROWS.
+// Per segment: 4 words of drop bits (set by the reduction for every cross term that does not
+// survive), 4 x 2 words of phase-exponent bit planes (written by the pair-record kernel) and one
+// output offset (exclusive scan of the survivor counts).
+constexpr int TILE_ROWS = 128;
+
+struct TileBlock {
+    uint32_t p0, m_blk, q0, nq, ptiles, seg_base;
+};
+
+__host__ __device__ __forceinline__ uint32_t tile_valid_word(uint32_t m_blk, uint32_t ptile, int w) {
+    const int64_t left = (int64_t)m_blk - (int64_t)ptile * TILE_ROWS - 32 * w;
+    return left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+}
+
+struct TileMap {
+    TileBlock first;           // block 0 inline: the single-rectangle product never reads `blocks`
+    const TileBlock *blocks;   // device, nblk entries
+    int nblk;
+    uint32_t M;                // rows of A: t = q*M + p
+    uint32_t n_seg;
+    uint32_t *drop;            // uint32[4 * n_seg]
+    uint2 *e01;                // uint2[4 * n_seg]: bit planes (e & 1, e >> 1)
+    uint32_t *segoff;          // uint32[n_seg + 1]: counts, then their exclusive scan in place
+
+#ifdef __CUDACC__
+    __device__ __forceinline__ bool locate(uint32_t t, TileBlock &blk, uint32_t &s, uint32_t &bit) const {
+        const uint32_t q = t / M, p = t - q * M;
+        blk = first;
+        for (int b = 0;;) {
+            const uint32_t pl = p - blk.p0, ql = q - blk.q0;
+            if (pl < blk.m_blk && ql < blk.nq) {
+                s = blk.seg_base + ql * blk.ptiles + pl / TILE_ROWS;
+                bit = pl % TILE_ROWS;
+                return true;
+            }
+            if (++b >= nblk) return false;
+            blk = blocks[b];
+        }
+    }
+    __device__ __forceinline__ void mark_dropped(uint32_t t) const {
+        TileBlock blk;
+        uint32_t s, bit;
+        if (locate(t, blk, s, bit)) atomicOr(drop + 4 * (size_t)s + (bit >> 5), 1u << (bit & 31));
+    }
+    // output slot of a surviving cross term (valid once segoff holds the scan)
+    __device__ __forceinline__ uint32_t slot_of(uint32_t t) const {
+        TileBlock blk;
+        uint32_t s, bit;
+        if (!locate(t, blk, s, bit)) return 0xffffffffu;
+        const uint32_t ptile = (s - blk.seg_base) % blk.ptiles;
+        uint32_t r = segoff[s];
+        const int wb = (int)(bit >> 5);
+        for (int w = 0; w <= wb; ++w) {
+            uint32_t k = tile_valid_word(blk.m_blk, ptile, w) & ~drop[4 * (size_t)s + w];
+            if (w == wb) k &= (1u << (bit & 31)) - 1u;
+            r += __popc(k);
+        }
+        return r;
+    }
+#endif
+};
+
 // Dedup driver (dedup.cu), split where the survivor count is known so the caller can allocate
 // exact-size outputs. `recs` holds T records (clobbered). by_t: the t fields are a permutation of
 // 0..T-1 and the output is written in increasing-t (first occurrence) order; otherwise the output
@@ -115,5 +184,12 @@ int dedup_plain_plan(uint64_t *recs, int64_t T, RecFmt fmt, const PlainRows &row
                      int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
 int dedup_plain_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const PlainRows &rows, int64_t U, uint64_t *out_xz,
                      double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);
+
+// ordered-tile mode (products only); blocks_host mirrors tm.blocks
+int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, double thr,
+                             int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
+int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
+                             const TileBlock *blocks_host, int64_t U, uint64_t *out_xz, double *out_c, void *ws,
+                             size_t ws_bytes, cudaStream_t st);
 
 }  // namespace symb

@@ -130,9 +130,7 @@ def owned_product(a_xz: torch.Tensor, a_c: torch.Tensor, b_xz: torch.Tensor, b_c
     b_p, b_cp, _, b_counts = ops.class_partition(b_xz, b_c, log2_parts)
     counts = torch.stack([a_counts, b_counts]).cpu().tolist()      # one small device->host read
     blocks = owner_blocks(counts[0], counts[1], owner)
-    recs = ops.pair_records_blocks(a_p, b_p, blocks)
-    n_recs = int(recs.numel())
-    out_xz, out_c = ops.dedup_records(recs, a_p, a_cp, b_p, b_cp, zero_threshold)
+    out_xz, out_c, n_recs = ops.mul_blocks_cleanup(a_p, a_cp, b_p, b_cp, blocks, zero_threshold)
     return out_xz, out_c, {"cross_terms_generated": n_recs, "records_owned": n_recs, "rows_total_a": int(a_xz.shape[0])}
 
 

@@ -181,6 +181,38 @@ def mul_cleanup(a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
     return out_xz, out_c
 
 
+def mul_blocks_cleanup(a_xz, a_c, b_xz, b_c, blocks, zero_threshold=1e-15):
+    """Product + cleanup restricted to disjoint rectangular blocks [(p0, p1, q0, q1), ...] of the
+    cross-term grid A x B (the exchange-free sharded product: rank r passes the blocks it owns).
+    Survivors leave block by block in (q, p) order. Returns (xz[U,2W], c[U], n_cross_terms)."""
+    M, W = _rows(a_xz)
+    N, W2 = _rows(b_xz)
+    assert W == W2
+    dev = a_xz.device
+    blocks = [tuple(int(v) for v in blk) for blk in blocks]
+    T = sum((p1 - p0) * (q1 - q0) for p0, p1, q0, q1 in blocks)
+    if T == 0:
+        return (torch.empty((0, 2 * W), dtype=torch.int64, device=dev),
+                torch.empty(0, dtype=torch.complex128, device=dev), 0)
+    flat = (ctypes.c_int64 * (4 * len(blocks)))(*[v for blk in blocks for v in blk])
+    L = lib()
+    nbytes = L.sym_mul_blocks_ws_bytes(M, N, W, flat, len(blocks))
+    if nbytes == 0:
+        _cabi.check(-1)
+    ws = workspace(nbytes)
+    U = ctypes.c_int64(0)
+    _cabi.check(L.sym_mul_blocks_count(_p(a_xz), _p(_coeff(a_c)), M, _p(b_xz), _p(_coeff(b_c)), N, W, flat, len(blocks),
+                                       _thr(zero_threshold), None, ctypes.byref(U), _p(ws), ws.numel(), _stream()))
+    U = U.value
+    out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
+    out_c = torch.empty(U, dtype=torch.complex128, device=dev)
+    ev = _emit_begin()
+    _cabi.check(L.sym_mul_blocks_emit(_p(a_xz), _p(a_c), M, _p(b_xz), _p(b_c), N, W, flat, len(blocks), U, _p(out_xz),
+                                      _p(out_c), _p(ws), ws.numel(), _stream()))
+    _emit_end(ev)
+    return out_xz, out_c, T
+
+
 def cleanup(xz, c, zero_threshold=1e-15):
     T, W = _rows(xz)
     dev = xz.device

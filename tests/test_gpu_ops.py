@@ -294,10 +294,95 @@ def test_rotations_golden(ops, golden):
         assert ok, (nm, why)
 
 
+@pytest.mark.parametrize("n,m1,m2", [(5, 300, 7), (64, 130, 13), (100, 257, 9), (200, 129, 20), (500, 140, 33),
+                                     (1000, 260, 45), (1000, 100, 3), (1000, 128, 128), (1100, 30, 9), (40, 1, 50)])
+def test_ordered_tile_mode_first_occurrence_order(ops, n, m1, m2):
+    """Force the large-product path on small inputs: the ordered-tile mode must give the reference's
+    first-occurrence order (rows bit-exact IN ORDER), whatever the tile raggedness; widths it does
+    not cover (W = 18 here) fall back to sorted-hash order and still match as a term set."""
+    try:
+        ops.set_tuning(0, 0)
+        tiled = n != 1100 and m1 >= 32      # a one-row A would be > 75 % tile padding: sorted-hash order instead
+        a_s, a_c = po.random_operator(n, m1, seed=5 * n + m1)
+        b_s, b_c = po.random_operator(n, m2, seed=5 * n + m2 + 1)
+        k = min(m1, m2) // 2
+        b_s[:k] = a_s[:k]                              # duplicates: identity terms + repeated products
+        a_s[m1 // 2:] = a_s[: m1 - m1 // 2]            # and duplicated rows inside A
+        for q in (16, 1, 5):
+            ops.set_tuning(7, q)
+            s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, b_s, b_c)
+            if tiled and len(ref_c) == len(cc):
+                assert np.array_equal(s, ref_s)
+        # a threshold that drops some singletons and some group sums
+        s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, b_s, b_c, thr=0.8)
+        s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, b_s, b_c, thr=None)
+        if tiled:
+            assert np.array_equal(s, ref_s)
+    finally:
+        ops.set_tuning(7, 16)
+        ops.set_tuning(0, 1 << 22)
+
+
+def test_ordered_tile_mode_squares_and_forced_collisions(ops):
+    try:
+        ops.set_tuning(0, 0)
+        a_s, a_c = po.random_operator(1000, 150, seed=1)
+        s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, a_s, a_c)
+        comm = po.commutes_termwise(a_s, a_s)
+        assert len(cc) == (np.count_nonzero(comm) - 150) // 2 + 1     # anticommuting pairs cancel exactly
+        a_s, a_c = po.random_operator(100, 90, seed=11)
+        for mask in [0xFFFFFFFFFFFFFFFF, 0xFF00000000000000, 0x0]:
+            ops.set_debug_key_mask(mask)
+            s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, a_s, a_c)
+            if len(ref_c) == len(cc):
+                assert np.array_equal(s, ref_s)
+    finally:
+        ops.set_debug_key_mask(0xFFFFFFFFFFFFFFFF)
+        ops.set_tuning(0, 1 << 22)
+
+
+def test_mul_blocks_cleanup_matches_block_products(ops):
+    """sym_mul_blocks_*: disjoint rectangles of the cross-term grid, survivors block by block in
+    (q, p) order; equal rows in different blocks must merge. Checked against the oracle product of
+    the same set of cross terms."""
+    n, M, N = 1000, 300, 70
+    a_s, a_c = po.random_operator(n, M, seed=31)
+    b_s, b_c = po.random_operator(n, N, seed=32)
+    b_s[:30] = a_s[:30]
+    b_s[30:60] = a_s[150:180]
+    a, ac = dev_op(ops, a_s, a_c)
+    b, bc = dev_op(ops, b_s, b_c)
+    blocks = [(0, 130, 40, 70), (130, 131, 0, 40), (131, 300, 0, 35), (0, 100, 0, 40)]
+    rows, coeffs = [], []
+    for p0, p1, q0, q1 in blocks:          # the same cross terms, in the same order, on the CPU
+        r, c = po.cross_terms(a_s[p0:p1], a_c[p0:p1], b_s[q0:q1], b_c[q0:q1])
+        rows.append(r)
+        coeffs.append(c)
+    ref_s, ref_c = po.symplectic_cleanup(np.vstack(rows), np.hstack(coeffs), 1e-15)
+    try:
+        for limit in (0, 1 << 22):
+            for knob6 in (1, 0):
+                ops.set_tuning(0, limit)
+                ops.set_tuning(6, knob6)
+                xz, c, T = ops.mul_blocks_cleanup(a, ac, b, bc, blocks)
+                assert T == sum((p1 - p0) * (q1 - q0) for p0, p1, q0, q1 in blocks)
+                s, cc = host_op(ops, xz, c, n)
+                ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
+                assert ok, (limit, knob6, why)
+                if knob6 == 1 and len(cc) == len(ref_c):
+                    assert np.array_equal(s, ref_s)            # block-by-block first-occurrence order
+        with pytest.raises(Exception):
+            ops.mul_blocks_cleanup(a, ac, b, bc, [(0, 10, 0, 10), (5, 15, 5, 15)])   # overlapping blocks
+    finally:
+        ops.set_tuning(0, 1 << 22)
+        ops.set_tuning(6, 1)
+
+
 def test_sorted_hash_order_path(ops):
     """Force the large-product path (output in sorted-hash order) on small inputs."""
     try:
         ops.set_tuning(0, 0)
+        ops.set_tuning(6, 0)
         for n, m1, m2 in [(5, 20, 7), (64, 30, 13), (1000, 60, 45)]:
             a_s, a_c = po.random_operator(n, m1, seed=3 * n + m1)
             b_s, b_c = po.random_operator(n, m2, seed=3 * n + m2 + 7)
@@ -310,6 +395,7 @@ def test_sorted_hash_order_path(ops):
     finally:
         ops.set_debug_key_mask(0xFFFFFFFFFFFFFFFF)
         ops.set_tuning(0, 1 << 22)
+        ops.set_tuning(6, 1)
 
 
 @pytest.mark.parametrize("log2g", [0, 1, 2, 3])
