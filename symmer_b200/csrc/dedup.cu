@@ -57,14 +57,24 @@ __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const 
     link_one(rows, fmt, sr, i, sort_shift, flag, link);
 }
 
-// the same over a worklist of sorted positions (ordered-tile mode: only records of non-singleton buckets)
+// Worklist of sorted positions (ordered-tile mode: only the records of non-singleton buckets), kept as
+// `nreg` regions of `cap` entries with one counter each: CTA b of the classify pass appends to region
+// b % nreg, so no counter is hot (one global counter serialises ~2e6 same-address atomics: 1.5 ms)
+// and a region can never overflow (it receives from at most cap records).
+struct WorkList {
+    uint32_t *work;
+    uint32_t *counts;
+    uint32_t nreg, cap;
+};
+#define FOR_EACH_WORK(wl, i)                                                   \
+    for (uint32_t _r = blockIdx.x; _r < (wl).nreg; _r += gridDim.x)            \
+        for (uint32_t _k = threadIdx.x, _n = (wl).counts[_r]; _k < _n; _k += blockDim.x) \
+            if (const uint32_t i = (wl).work[(size_t)_r * (wl).cap + _k]; true)
+
 template <class Rows>
 __global__ void __launch_bounds__(256) link_work_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int sort_shift,
-                                                         const uint32_t *__restrict__ work, const uint32_t *__restrict__ n_work,
-                                                         uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
-    const uint32_t n = *n_work;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-        link_one(rows, fmt, sr, (int64_t)work[k], sort_shift, flag, link);
+                                                         WorkList wl, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
+    FOR_EACH_WORK(wl, i) link_one(rows, fmt, sr, (int64_t)i, sort_shift, flag, link);
 }
 
 __device__ __forceinline__ uint8_t keep_test(double re, double im, double thr) {
@@ -127,7 +137,7 @@ __device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, con
                 tm.mark_dropped(fmt.t(r0));
             }
         } else if (!(thr < 0.0 || rows.all_pass())) {
-            rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+            rows.coeff_unphased(fmt.t(r0), re, im);
             if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r0));
         }
         return;
@@ -158,13 +168,11 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
 // ordered-tile mode: the reduction over the worklist (records of non-singleton buckets)
 template <class Rows>
 __global__ void __launch_bounds__(256) sum_work_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                        int sort_shift, const uint32_t *__restrict__ work,
-                                                        const uint32_t *__restrict__ n_work, const uint8_t *__restrict__ flag,
+                                                        int sort_shift, WorkList wl, const uint8_t *__restrict__ flag,
                                                         const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
                                                         uint8_t *__restrict__ multi, TileMap tm) {
-    const uint32_t n = *n_work;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-        sum_one<Rows, false, true, true>(rows, fmt, sr, T, (int64_t)work[k], sort_shift, flag, link, thr, acc, nullptr, multi, tm);
+    FOR_EACH_WORK(wl, i)
+        sum_one<Rows, false, true, true>(rows, fmt, sr, T, (int64_t)i, sort_shift, flag, link, thr, acc, nullptr, multi, tm);
 }
 
 // Ordered-tile mode, first pass over the sorted records: a record whose sort bucket holds nothing
@@ -172,8 +180,7 @@ __global__ void __launch_bounds__(256) sum_work_kernel(Rows rows, RecFmt fmt, co
 // written. Only the records of shared buckets go on the worklist for link / sum / fix-up.
 template <class Rows>
 __global__ void __launch_bounds__(256) tile_classify_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
-                                                             int sort_shift, double thr, TileMap tm,
-                                                             uint32_t *__restrict__ work, uint32_t *__restrict__ n_work) {
+                                                             int sort_shift, double thr, TileMap tm, WorkList wl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool shared_bucket = false;
     if (i < T) {
@@ -183,17 +190,18 @@ __global__ void __launch_bounds__(256) tile_classify_kernel(Rows rows, RecFmt fm
         shared_bucket = same_prev || same_next;
         if (!shared_bucket && !(thr < 0.0 || rows.all_pass())) {
             double re, im;
-            rows.coeff(fmt.t(r), fmt.e(r), re, im);
+            rows.coeff_unphased(fmt.t(r), re, im);
             if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r));
         }
     }
     const uint32_t m = __ballot_sync(0xffffffffu, shared_bucket);
     if (m == 0u) return;
     const int lane = threadIdx.x & 31;
+    const uint32_t reg = blockIdx.x % wl.nreg;
     uint32_t base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(n_work, (uint32_t)__popc(m));
+    if (lane == __ffs(m) - 1) base = atomicAdd(wl.counts + reg, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (shared_bucket) work[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    if (shared_bucket) wl.work[(size_t)reg * wl.cap + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
 }
 
 // pass_all flag of a product: min|a| * min|b| clears the threshold with a 4x margin (the rounded
@@ -669,34 +677,43 @@ __global__ void __launch_bounds__(256) seg_count_kernel(TileMap tm) {
 }
 
 // Row + coefficient emission of one block, CTA = (tile of TILE_ROWS rows of A) x (QG rows of B).
-// Thread = (row, 16-byte chunk); the A chunks of its UN rows stay in registers for the whole q loop,
-// the B row is one broadcast 16-byte load per q, so the only traffic that scales with the output
-// is the output itself: consecutive survivors of a segment go to consecutive 16-byte slots
-// (streaming stores). The first TILE_ROWS threads also write the survivors' coefficients
-// a[p]*b[q]*i^e (e from the bit planes); group sums overwrite theirs in the fix-up pass.
+// Thread = (row, word c): it holds X word c and Z word c of its UN rows of A in registers for the
+// whole q loop; the B row is two broadcast 8-byte loads per q, so the only traffic that scales
+// with the output is the output itself: consecutive survivors of a segment go to consecutive
+// slots (streaming stores, a warp writes whole 128-byte lines).
+// Holding the X and Z words of the same qubits lets the thread also compute its share of the
+// phase exponent (base.py:785-788): popc((xa^xb)&(za^zb)) + 2*popc(xa&zb) mod 4, packed as one
+// 4-bit field per row and XOR-shuffle-reduced over the W lanes of the row (all UN rows in one
+// word), then 3*(Ya+Yb) is added. Lane u of a row group writes the coefficient a[p]*b[q]*i^e of row
+// u; group sums overwrite theirs in the fix-up pass. The kernel stays HBM-write bound.
 template <int LW>
 __global__ void __launch_bounds__((TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256)
-    tile_emit_kernel(const uint4 *__restrict__ A, const double2 *__restrict__ Ac, const uint4 *__restrict__ B,
-                     const double2 *__restrict__ Bc, TileBlock blk, uint32_t qg, const uint32_t *__restrict__ drop,
-                     const uint2 *__restrict__ e01, const uint32_t *__restrict__ segoff, uint4 *__restrict__ out_xz,
-                     double2 *__restrict__ out_c) {
+    tile_emit_kernel(const uint64_t *__restrict__ A, const double2 *__restrict__ Ac, const int32_t *__restrict__ Ay,
+                     const uint64_t *__restrict__ B, const double2 *__restrict__ Bc, const int32_t *__restrict__ By,
+                     TileBlock blk, uint32_t qg, const uint32_t *__restrict__ drop, const uint32_t *__restrict__ segoff,
+                     uint64_t *__restrict__ out_xz, double2 *__restrict__ out_c) {
     constexpr int TH = (TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256;
-    constexpr int CH = 1 << LW;
+    constexpr int W = 1 << LW;            // words per X (and per Z) block = lanes per row
     constexpr int RP = TH >> LW;          // rows per pass
-    constexpr int UN = TILE_ROWS / RP;    // passes per segment
+    constexpr int UN = TILE_ROWS / RP;    // passes per segment (UN <= W)
+    static_assert(UN <= W && UN <= 8, "one coefficient lane per row, one 4-bit phase field per row");
     const uint32_t ptile = blockIdx.x;
-    const uint32_t r_in = threadIdx.x >> LW, c = threadIdx.x & (CH - 1);
+    const uint32_t r_in = threadIdx.x >> LW, c = threadIdx.x & (W - 1);
     const uint32_t pl0 = ptile * TILE_ROWS;
 
-    uint4 a[UN];
+    uint64_t xa[UN], za[UN];
+    uint32_t ya3 = 0;                     // 3*Ya mod 4 of the UN rows, 4 bits apart
+    double2 ac = make_double2(0.0, 0.0);  // coefficient of row u == c
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
         const uint32_t pl = pl0 + u * RP + r_in;
-        a[u] = pl < blk.m_blk ? A[((size_t)(blk.p0 + pl) << LW) + c] : make_uint4(0u, 0u, 0u, 0u);
+        const bool ok = pl < blk.m_blk;
+        const size_t row = (size_t)(blk.p0 + (ok ? pl : 0u));
+        xa[u] = ok ? A[row * (2 * W) + c] : 0ull;
+        za[u] = ok ? A[row * (2 * W) + W + c] : 0ull;
+        ya3 |= ((3u * (uint32_t)(ok ? Ay[row] : 0)) & 3u) << (4 * u);
+        if ((int)c == u && ok) ac = Ac[row];
     }
-    const bool coeff_thread = threadIdx.x < TILE_ROWS;
-    double2 ac = make_double2(0.0, 0.0);
-    if (coeff_thread && pl0 + threadIdx.x < blk.m_blk) ac = Ac[blk.p0 + pl0 + threadIdx.x];
     uint32_t vm[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) vm[w] = tile_valid_word(blk.m_blk, ptile, w);
@@ -705,54 +722,71 @@ __global__ void __launch_bounds__((TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 
     const uint32_t q_hi = min(blk.nq, q_lo + qg);
     for (uint32_t ql = q_lo; ql < q_hi; ++ql) {
         const uint32_t s = blk.seg_base + ql * blk.ptiles + ptile;
+        const size_t qrow = (size_t)(blk.q0 + ql);
         const uint4 d = reinterpret_cast<const uint4 *>(drop)[s];
         const uint32_t base = segoff[s];
-        const uint4 b = B[((size_t)(blk.q0 + ql) << LW) + c];
-        uint32_t k[4] = {vm[0] & ~d.x, vm[1] & ~d.y, vm[2] & ~d.z, vm[3] & ~d.w};
+        const uint64_t xb = B[qrow * (2 * W) + c], zb = B[qrow * (2 * W) + W + c];
+        const uint32_t yb3 = (3u * (uint32_t)By[qrow]) & 3u;
+        const uint32_t k[4] = {vm[0] & ~d.x, vm[1] & ~d.y, vm[2] & ~d.z, vm[3] & ~d.w};
         uint32_t pre[4];
         pre[0] = base;
         pre[1] = pre[0] + __popc(k[0]);
         pre[2] = pre[1] + __popc(k[1]);
         pre[3] = pre[2] + __popc(k[2]);
+        uint32_t ph = 0, my_slot = 0;
+        bool my_keep = false;
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const uint32_t j = u * RP + r_in;
             const uint32_t kw = k[j >> 5], bit = j & 31;
-            if ((kw >> bit) & 1u) {
-                const uint32_t slot = pre[j >> 5] + __popc(kw & ((1u << bit) - 1u));
-                store_streaming(out_xz + (((size_t)slot) << LW) + c,
-                                make_uint4(a[u].x ^ b.x, a[u].y ^ b.y, a[u].z ^ b.z, a[u].w ^ b.w));
+            const bool kept = (kw >> bit) & 1u;
+            const uint32_t slot = pre[j >> 5] + __popc(kw & ((1u << bit) - 1u));
+            const uint64_t ox = xa[u] ^ xb, oz = za[u] ^ zb;
+            ph |= ((uint32_t)(__popcll(ox & oz) + 2 * __popcll(xa[u] & zb)) & 3u) << (4 * u);
+            if (kept) {
+                uint64_t *o = out_xz + (size_t)slot * (2 * W) + c;
+                __stcs(o, ox);
+                __stcs(o + W, oz);
+            }
+            if ((int)c == u) {
+                my_slot = slot;
+                my_keep = kept;
             }
         }
-        if (coeff_thread) {
-            const uint32_t j = threadIdx.x;
-            const uint32_t kw = k[j >> 5], bit = j & 31;
-            if ((kw >> bit) & 1u) {
-                const uint32_t slot = pre[j >> 5] + __popc(kw & ((1u << bit) - 1u));
-                const uint2 ep = e01[4 * (size_t)s + (j >> 5)];
-                const int e = (int)((ep.x >> bit) & 1u) | (int)(((ep.y >> bit) & 1u) << 1);
-                const double2 bc = Bc[blk.q0 + ql];
-                double re, im;
-                cmul(ac.x, ac.y, bc.x, bc.y, re, im);
-                mul_i_pow(re, im, e);
-                out_c[slot] = make_double2(re, im);
-            }
+#pragma unroll
+        for (int o = W >> 1; o > 0; o >>= 1) ph = (ph + __shfl_xor_sync(0xffffffffu, ph, o)) & 0x33333333u;
+        if ((int)c < UN && my_keep) {
+            const int e = (int)(((ph + ya3) >> (4 * c)) + yb3) & 3;
+            const double2 bc = Bc[qrow];
+            double re, im;
+            cmul(ac.x, ac.y, bc.x, bc.y, re, im);
+            mul_i_pow(re, im, e);
+            out_c[my_slot] = make_double2(re, im);
         }
     }
 }
 
 // group sums of the surviving heads -> their output slots (after tile_emit_kernel wrote a[p]*b[q]*i^e there)
-__global__ void __launch_bounds__(256) tile_fixup_kernel(TileMap tm, RecFmt fmt, const uint64_t *__restrict__ sr,
-                                                          const uint32_t *__restrict__ work, const uint32_t *__restrict__ n_work,
+__global__ void __launch_bounds__(256) tile_fixup_kernel(TileMap tm, RecFmt fmt, const uint64_t *__restrict__ sr, WorkList wl,
                                                           const uint8_t *__restrict__ multi, const double2 *__restrict__ acc,
                                                           double2 *__restrict__ out_c) {
-    const uint32_t n = *n_work;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t i = work[k];
+    FOR_EACH_WORK(wl, i) {
         if (!multi[i]) continue;
         const uint32_t slot = tm.slot_of(fmt.t(sr[i]));
         if (slot != 0xffffffffu) out_c[slot] = acc[i];
     }
+}
+
+// worklist storage: L.slot and L.kept (adjacent, both unused in this mode) hold the regions, the
+// radix histogram buffer (free once the sort is done) holds the counters
+static WorkList tile_worklist(const DedupLayout &L, int64_t T) {
+    const int64_t nb = (T + 255) / 256;
+    WorkList wl;
+    wl.nreg = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(2048, nb / 16));
+    wl.cap = (uint32_t)std::min<int64_t>(((nb + wl.nreg - 1) / wl.nreg) * 256, T);
+    wl.work = L.slot;
+    wl.counts = L.hist;
+    return wl;
 }
 
 int g_tile_qgroup = 16;   // tuning knob 7: B rows per CTA of tile_emit_kernel
@@ -773,22 +807,25 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
     SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
     const unsigned nb = (unsigned)((T + 255) / 256);
     ProductRows rows_sum = rows;
+    rows_sum.lazy_phase = true;   // pair_keys_kernel records carry no phase exponent
     if (thr >= 0.0 && rows.N > 0) {
         min_abs_flag_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
                                                 reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr, L.total + 2);
         SYM_LAUNCH_OK();
         rows_sum.pass_all = L.total + 2;
     }
-    // worklist of the records that share a sort bucket (L.slot is free in this mode), counter in L.total[1]
-    uint32_t *work = L.slot, *n_work = L.total + 1;
-    SYM_CUDA_OK(cudaMemsetAsync(n_work, 0, sizeof(uint32_t), st));
-    tile_classify_kernel<ProductRows><<<nb, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, thr, tm, work, n_work);
+    // worklist of the records that share a sort bucket
+    const WorkList wl = tile_worklist(L, T);
+    if ((size_t)wl.nreg * wl.cap > 2 * (arena_need((size_t)T, 4) / 4)) {
+        set_error("worklist does not fit its arena slice");
+        return SYM_E_WORKSPACE;
+    }
+    SYM_CUDA_OK(cudaMemsetAsync(wl.counts, 0, sizeof(uint32_t) * wl.nreg, st));
+    tile_classify_kernel<ProductRows><<<nb, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, thr, tm, wl);
     SYM_LAUNCH_OK();
-    const unsigned nbw = (unsigned)std::min<int64_t>((int64_t)nb, (int64_t)num_sms() * 16);
-    link_work_kernel<ProductRows><<<nbw, 256, 0, st>>>(rows, fmt, sr, begin, work, n_work, L.flag, L.link);
+    link_work_kernel<ProductRows><<<wl.nreg, 256, 0, st>>>(rows, fmt, sr, begin, wl, L.flag, L.link);
     SYM_LAUNCH_OK();
-    sum_work_kernel<ProductRows><<<nbw, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, work, n_work, L.flag, L.link, thr, L.acc,
-                                                      L.multi, tm);
+    sum_work_kernel<ProductRows><<<wl.nreg, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, wl, L.flag, L.link, thr, L.acc, L.multi, tm);
     SYM_LAUNCH_OK();
     seg_count_kernel<<<(tm.n_seg + 255) / 256, 256, 0, st>>>(tm);
     SYM_LAUNCH_OK();
@@ -805,8 +842,8 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
 }
 
 int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
-                             const TileBlock *blocks_host, int64_t U, uint64_t *out_xz, double *out_c, void *ws,
-                             size_t ws_bytes, cudaStream_t st) {
+                             const TileBlock *blocks_host, const int32_t *a_y, const int32_t *b_y, int64_t U,
+                             uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (T == 0 || U == 0) return SYM_OK;
     DedupLayout L = dedup_layout(ws, ws_bytes, T);
     if (!L.ok) {
@@ -815,9 +852,7 @@ int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const 
     }
     const uint64_t *sr = (T > 1 && sorted_in_alt(sort_begin_bit(T, fmt))) ? L.alt : recs;
     const int chunks = rows.words / 2;
-    const uint4 *A4 = reinterpret_cast<const uint4 *>(rows.A), *B4 = reinterpret_cast<const uint4 *>(rows.B);
     const double2 *Ac = reinterpret_cast<const double2 *>(rows.Ac), *Bc = reinterpret_cast<const double2 *>(rows.Bc);
-    uint4 *o = reinterpret_cast<uint4 *>(out_xz);
     double2 *oc = reinterpret_cast<double2 *>(out_c);
     const uint32_t qg = (uint32_t)(g_tile_qgroup < 1 ? 1 : g_tile_qgroup);
     if (g_emit_ev0) SYM_CUDA_OK(cudaEventRecord(g_emit_ev0, st));
@@ -830,22 +865,22 @@ int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const 
             return SYM_E_UNSUPPORTED;
         }
 #define TILE_EMIT(LW) \
-    tile_emit_kernel<LW><<<grid, (TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256, 0, st>>>(A4, Ac, B4, Bc, blk, qg, tm.drop, \
-                                                                                        tm.e01, tm.segoff, o, oc)
+    tile_emit_kernel<LW><<<grid, (TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256, 0, st>>>(                 \
+        rows.A, Ac, a_y, rows.B, Bc, b_y, blk, qg, tm.drop, tm.segoff, out_xz, oc)
         switch (chunks) {
             case 1: TILE_EMIT(0); break;
             case 2: TILE_EMIT(1); break;
             case 4: TILE_EMIT(2); break;
             case 8: TILE_EMIT(3); break;
             case 16: TILE_EMIT(4); break;
-            default: set_error("ordered-tile mode needs 1, 2, 4, 8 or 16 chunks per row"); return SYM_E_UNSUPPORTED;
+            default: set_error("ordered-tile mode needs 1, 2, 4, 8 or 16 words per block"); return SYM_E_UNSUPPORTED;
         }
 #undef TILE_EMIT
         SYM_LAUNCH_OK();
     }
     if (g_emit_ev1) SYM_CUDA_OK(cudaEventRecord(g_emit_ev1, st));
-    const unsigned nbw = (unsigned)std::min<int64_t>((T + 255) / 256, (int64_t)num_sms() * 16);
-    tile_fixup_kernel<<<nbw, 256, 0, st>>>(tm, fmt, sr, L.slot, L.total + 1, L.multi, L.acc, oc);
+    const WorkList wl = tile_worklist(L, T);
+    tile_fixup_kernel<<<wl.nreg, 256, 0, st>>>(tm, fmt, sr, wl, L.multi, L.acc, oc);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }

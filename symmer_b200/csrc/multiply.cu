@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
     const uint64_t *__restrict__ a_xz, const uint64_t *__restrict__ a_sk, const int32_t *__restrict__ a_y, uint32_t M_total,
     uint32_t p_begin, uint32_t p_end, const uint64_t *__restrict__ b_xz, const uint64_t *__restrict__ b_sk,
     const int32_t *__restrict__ b_y, uint32_t N, uint32_t q_off, int W, uint64_t key_mask, RecFmt fmt,
-    uint64_t *__restrict__ recs, uint2 *__restrict__ e01, uint32_t seg_base, uint32_t ptiles) {
+    uint64_t *__restrict__ recs) {
     // B tile: QCH rows, (x_w, z_w) interleaved so one 16-byte shared load feeds a word step
     __shared__ ulonglong2 sb[PAIR_QCH][WT];
     __shared__ uint64_t sb_sk[PAIR_QCH];
@@ -72,14 +72,10 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
         for (int w = 0; w < WT; ++w) xa[w] = za[w] = 0ull;
     }
     __syncthreads();
-    // whole warps stay alive for the ballots of the phase bit planes (ordered-tile mode)
-    if (!__any_sync(0xffffffffu, active)) return;
+    if (!active) return;
 
     const uint32_t m_blk = p_end - p_begin;
     const uint32_t p_local = p - p_begin;
-    // word of the warp's 32 rows in the segment bit planes (rows.cuh): 256 rows per CTA = 2 tiles
-    const uint32_t ew_tile = blockIdx.x * (PAIR_THREADS / TILE_ROWS) + (threadIdx.x / TILE_ROWS);
-    const uint32_t ew_word = (threadIdx.x % TILE_ROWS) >> 5;
     for (uint32_t qi = 0; qi < nq; ++qi) {
         uint64_t s = 0, c0 = 0, c1 = 0;
 #pragma unroll
@@ -90,15 +86,27 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
             c1 ^= c0 & v;
             c0 ^= v;
         }
-        const int e = active ? finish_phase(ya, sb_y[qi], s, c0, c1) : 0;
+        const int e = finish_phase(ya, sb_y[qi], s, c0, c1);
         const size_t j = (size_t)(q0 + qi) * m_blk + p_local;
-        if (active) recs[j] = fmt.make(mix64(ska ^ sb_sk[qi]) & key_mask, (uint64_t)(q_off + q0 + qi) * M_total + p, e);
-        if (e01 != nullptr) {
-            const uint32_t e_lo = __ballot_sync(0xffffffffu, e & 1), e_hi = __ballot_sync(0xffffffffu, e & 2);
-            if ((threadIdx.x & 31) == 0)
-                e01[4 * ((size_t)seg_base + (size_t)(q0 + qi) * ptiles + ew_tile) + ew_word] = make_uint2(e_lo, e_hi);
-        }
+        recs[j] = fmt.make(mix64(ska ^ sb_sk[qi]) & key_mask, (uint64_t)(q_off + q0 + qi) * M_total + p, e);
     }
+}
+
+// Ordered-tile mode: records without the phase exponent (the tiled emission computes it from the rows it
+// holds in registers), so a record is just the mixed XOR of two sketches: 8 B store per pair, HBM-write bound.
+constexpr int KEYS_QCH = 64;
+__global__ void __launch_bounds__(256) pair_keys_kernel(const uint64_t *__restrict__ a_sk, uint32_t M_total, uint32_t p_begin,
+                                                         uint32_t m_blk, const uint64_t *__restrict__ b_sk, uint32_t nq,
+                                                         uint32_t q_off, uint64_t key_mask, RecFmt fmt,
+                                                         uint64_t *__restrict__ recs) {
+    const uint32_t p_local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p_local >= m_blk) return;
+    const uint32_t p = p_begin + p_local;
+    const uint64_t ska = a_sk[p];
+    const uint32_t q_lo = blockIdx.y * KEYS_QCH, q_hi = min(nq, q_lo + KEYS_QCH);
+#pragma unroll 4
+    for (uint32_t q = q_lo; q < q_hi; ++q)
+        recs[(size_t)q * m_blk + p_local] = fmt.make(mix64(ska ^ b_sk[q]) & key_mask, (uint64_t)(q_off + q) * M_total + p, 0);
 }
 
 // generic fallback for W > 16: one thread per pair, rows read through L1/L2
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(256) pair_records_generic_kernel(
 static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const int32_t *a_y, int64_t M_total,
                                int64_t p_begin, int64_t p_end, const uint64_t *b_xz, const uint64_t *b_sk,
                                const int32_t *b_y, int64_t N, int W, RecFmt fmt, uint64_t *recs, cudaStream_t st,
-                               int64_t q_off = 0, uint2 *e01 = nullptr, uint32_t seg_base = 0, uint32_t ptiles = 0) {
+                               int64_t q_off = 0) {
     // b_xz / b_sk / b_y point at B row q_off; N rows from there. t uses the global index q_off + q.
     const int64_t m_blk = p_end - p_begin;
     if (m_blk <= 0 || N <= 0) return SYM_OK;
@@ -136,7 +144,7 @@ static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const
 #define PAIR_CASE(WT)                                                                                               \
     pair_records_kernel<WT><<<grid, PAIR_THREADS, 0, st>>>(a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin,   \
                                                            (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N,           \
-                                                           (uint32_t)q_off, W, g_key_mask, fmt, recs, e01, seg_base, ptiles)
+                                                           (uint32_t)q_off, W, g_key_mask, fmt, recs)
     if (grid.y > 65535) {
         set_error("too many B rows for one launch (N=%lld)", (long long)N);
         return SYM_E_UNSUPPORTED;
@@ -417,7 +425,6 @@ struct MulBlocksPlan {
     uint64_t *recs;
     TileBlock *d_blocks;
     uint32_t *drop;
-    uint2 *e01;
     uint32_t *segoff;
     void *rest;
     size_t rest_bytes;
@@ -472,14 +479,12 @@ static int mul_blocks_plan(int64_t M_total, int64_t N, int32_t W, const int64_t 
     P.recs = ar.take<uint64_t>(t);
     P.d_blocks = nullptr;
     P.drop = nullptr;
-    P.e01 = nullptr;
     P.segoff = nullptr;
     if (P.mode == MODE_TILES) {
         const size_t sg = (size_t)P.n_seg;
-        need += arena_need(256, sizeof(TileBlock)) + arena_need(4 * sg, 4) + arena_need(4 * sg, 8) + arena_need(sg + 1, 4);
+        need += arena_need(256, sizeof(TileBlock)) + arena_need(4 * sg, 4) + arena_need(sg + 1, 4);
         P.d_blocks = ar.take<TileBlock>(256);
         P.drop = ar.take<uint32_t>(4 * sg);
-        P.e01 = ar.take<uint2>(4 * sg);
         P.segoff = ar.take<uint32_t>(sg + 1);
     }
     P.rest = ws ? (void *)(ar.base + ar.off) : nullptr;
@@ -496,7 +501,6 @@ static TileMap tile_map_of(const MulBlocksPlan &P, int64_t M_total) {
     tm.M = (uint32_t)M_total;
     tm.n_seg = P.n_seg;
     tm.drop = P.drop;
-    tm.e01 = P.e01;
     tm.segoff = P.segoff;
     return tm;
 }
@@ -536,9 +540,22 @@ extern "C" int sym_mul_blocks_count(const uint64_t *a_xz, const double *a_c, int
     size_t off = 0;
     for (int b = 0; b < P.nblk; ++b) {
         const TileBlock &tb = P.blocks[b];
-        SYM_TRY(launch_pair_records(a_xz, P.a_sk, P.a_y, M_total, tb.p0, (int64_t)tb.p0 + tb.m_blk,
-                                    b_xz + (size_t)tb.q0 * 2 * W, P.b_sk + tb.q0, P.b_y + tb.q0, tb.nq, W, fmt, P.recs + off,
-                                    st, tb.q0, P.e01, tb.seg_base, tb.ptiles));
+        if (P.mode == MODE_TILES) {
+            if (tb.m_blk > 0 && tb.nq > 0) {
+                dim3 grid((tb.m_blk + 255) / 256, (tb.nq + KEYS_QCH - 1) / KEYS_QCH);
+                if (grid.y > 65535) {
+                    set_error("too many B rows for one launch (N=%u)", tb.nq);
+                    return SYM_E_UNSUPPORTED;
+                }
+                pair_keys_kernel<<<grid, 256, 0, st>>>(P.a_sk, (uint32_t)M_total, tb.p0, tb.m_blk, P.b_sk + tb.q0, tb.nq, tb.q0,
+                                                       g_key_mask, fmt, P.recs + off);
+                SYM_LAUNCH_OK();
+            }
+        } else {
+            SYM_TRY(launch_pair_records(a_xz, P.a_sk, P.a_y, M_total, tb.p0, (int64_t)tb.p0 + tb.m_blk,
+                                        b_xz + (size_t)tb.q0 * 2 * W, P.b_sk + tb.q0, P.b_y + tb.q0, tb.nq, W, fmt,
+                                        P.recs + off, st, tb.q0));
+        }
         off += (size_t)tb.m_blk * tb.nq;
     }
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
@@ -563,8 +580,8 @@ extern "C" int sym_mul_blocks_emit(const uint64_t *a_xz, const double *a_c, int6
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
     RecFmt fmt{t_bits_for(M_total * N)};
     if (P.mode == MODE_TILES)
-        return dedup_product_emit_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.blocks, U, out_xz, out_c, P.rest,
-                                        P.rest_bytes, (cudaStream_t)stream);
+        return dedup_product_emit_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.blocks, P.a_y, P.b_y, U, out_xz,
+                                        out_c, P.rest, P.rest_bytes, (cudaStream_t)stream);
     return dedup_product_emit(P.recs, P.T, fmt, rows, P.mode == MODE_BY_T, U, out_xz, out_c, P.rest, P.rest_bytes,
                               (cudaStream_t)stream);
 }
@@ -577,7 +594,7 @@ extern "C" size_t sym_mul_cleanup_ws_bytes(int64_t M, int64_t N, int32_t W) {
     const size_t segs = (size_t)(N > 0 ? N : 1) * (size_t)((M + TILE_ROWS - 1) / TILE_ROWS + 1);
     (void)blk;
     return sym_pair_records_ws_bytes(M, N, W) + arena_need((size_t)T, 8) + dedup_ws_bytes(T) +
-           arena_need(256, sizeof(TileBlock)) + arena_need(4 * segs, 4) + arena_need(4 * segs, 8) + arena_need(segs + 1, 4) + 2048;
+           arena_need(256, sizeof(TileBlock)) + arena_need(4 * segs, 4) + arena_need(segs + 1, 4) + 2048;
 }
 
 extern "C" int sym_mul_cleanup_count(const uint64_t *a_xz, const double *a_c, int64_t M, const uint64_t *b_xz,

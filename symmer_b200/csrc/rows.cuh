@@ -34,6 +34,7 @@ struct ProductRows {
     int words;   // 2*W
     uint32_t N = 0;                                // rows of B (0 = unknown)
     const uint32_t *__restrict__ pass_all = nullptr;  // device flag: every single cross term passes |c| > thr
+    bool lazy_phase = false;   // records carry no phase exponent (ordered-tile mode): recompute it on demand
 
     __device__ __forceinline__ bool all_pass() const { return pass_all != nullptr && *pass_all != 0u; }
 
@@ -69,11 +70,36 @@ struct ProductRows {
             if ((a1[k] ^ b1[k]) != (a2[k] ^ b2[k])) return false;
         return true;
     }
+    // phase exponent of the cross term from its rows (base.py:785-788), for the modes whose records do not carry it
+    __device__ __noinline__ int phase(uint32_t t) const {
+        uint32_t p, q;
+        split(t, p, q);
+        const uint64_t *ra = A + (size_t)p * words, *rb = B + (size_t)q * words;
+        const int W = words >> 1;
+        uint64_t s = 0, c0 = 0, c1 = 0;
+        int y_in = 0;
+        for (int w = 0; w < W; ++w) {
+            const uint64_t xa = ra[w], za = ra[W + w], xb = rb[w], zb = rb[W + w];
+            y_in += __popcll(xa & za) + __popcll(xb & zb);
+            s ^= xa & zb;
+            const uint64_t v = (xa ^ xb) & (za ^ zb);
+            c1 ^= c0 & v;
+            c0 ^= v;
+        }
+        return (3 * y_in + __popcll(c0) + 2 * __popcll(c1) + 2 * (__popcll(s) & 1)) & 3;
+    }
     __device__ __forceinline__ void coeff(uint32_t t, int e, double &re, double &im) const {
         uint32_t p, q;
         split(t, p, q);
         cmul(Ac[2 * (size_t)p], Ac[2 * (size_t)p + 1], Bc[2 * (size_t)q], Bc[2 * (size_t)q + 1], re, im);
+        if (lazy_phase) e = phase(t);
         mul_i_pow(re, im, e);
+    }
+    // |coefficient| only matters (threshold tests): no phase
+    __device__ __forceinline__ void coeff_unphased(uint32_t t, double &re, double &im) const {
+        uint32_t p, q;
+        split(t, p, q);
+        cmul(Ac[2 * (size_t)p], Ac[2 * (size_t)p + 1], Bc[2 * (size_t)q], Bc[2 * (size_t)q + 1], re, im);
     }
 };
 
@@ -99,6 +125,7 @@ struct PlainRows {
         re = C[2 * (size_t)t];
         im = C[2 * (size_t)t + 1];
     }
+    __device__ __forceinline__ void coeff_unphased(uint32_t t, double &re, double &im) const { coeff(t, 0, re, im); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -109,8 +136,8 @@ struct PlainRows {
 // into SEGMENTS of TILE_ROWS consecutive p for one q; segment id
 //   s = seg_base + (q - q0) * ptiles + (p - p0) / TILE_ROWS,  bit = (p - p0) % TILE_ROWS.
 // Per segment: 4 words of drop bits (set by the reduction for every cross term that does not
-// survive), 4 x 2 words of phase-exponent bit planes (written by the pair-record kernel) and one
-// output offset (exclusive scan of the survivor counts).
+// survive) and one output offset (exclusive scan of the survivor counts). Records carry no phase
+// exponent in this mode: the emission kernel has both rows in registers and computes it there.
 constexpr int TILE_ROWS = 128;
 
 struct TileBlock {
@@ -129,7 +156,6 @@ struct TileMap {
     uint32_t M;                // rows of A: t = q*M + p
     uint32_t n_seg;
     uint32_t *drop;            // uint32[4 * n_seg]
-    uint2 *e01;                // uint2[4 * n_seg]: bit planes (e & 1, e >> 1)
     uint32_t *segoff;          // uint32[n_seg + 1]: counts, then their exclusive scan in place
 
 #ifdef __CUDACC__
@@ -189,7 +215,7 @@ int dedup_plain_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const PlainRow
 int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, double thr,
                              int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
 int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
-                             const TileBlock *blocks_host, int64_t U, uint64_t *out_xz, double *out_c, void *ws,
-                             size_t ws_bytes, cudaStream_t st);
+                             const TileBlock *blocks_host, const int32_t *a_y, const int32_t *b_y, int64_t U,
+                             uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace symb
