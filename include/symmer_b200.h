@@ -278,7 +278,10 @@ int sym_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t T, int32_t begin_bit,
  * sym_mul_cleanup scatters by t (above it: knob 6; default 2^22); 1: row emission (0 two kernels, 1 CTA-fused, 2 warp-fused); 2: radix scatter shape;
  * 3: extra sort bits; 4: apply/expval kernel (1 binned, 0 four-row); 5: GF(2) large path (1 blocked
  * panels, 0 one pivot per sweep); 6: large products in ordered-tile mode (1, default) or sorted-hash
- * order (0); 7: B rows per CTA of the tiled row emission (default 16). */
+ * order (0); 7: B rows per CTA of the tiled row emission (default 16); 8: record sort as one-sweep
+ * passes with decoupled look-back (1, default) or histogram + scan + scatter per pass (0); 9: in
+ * ordered-tile mode the first radix pass generates the records itself (1) or pair_keys_kernel writes them
+ * first (0, default: measured faster). */
 int sym_set_tuning(int32_t which, int64_t value);
 /* Measurement hook: two cudaEvent_t (as void*, NULL to disable) recorded on the stream immediately
  * before and after the row-emission kernel (emit_kernel) of the next *_emit calls, so that a

@@ -178,30 +178,67 @@ __global__ void __launch_bounds__(256) sum_work_kernel(Rows rows, RecFmt fmt, co
 // Ordered-tile mode, first pass over the sorted records: a record whose sort bucket holds nothing
 // else is a singleton survivor (or fails the threshold on its own) — no link, no sum, nothing
 // written. Only the records of shared buckets go on the worklist for link / sum / fix-up.
+constexpr int CLS_ITEMS = 8;                    // records per thread: eight independent loads in flight, and
+constexpr int CLS_TILE = 256 * CLS_ITEMS;       // one counter update (an L2 round trip) per 2048 records
 template <class Rows>
 __global__ void __launch_bounds__(256) tile_classify_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
                                                              int sort_shift, double thr, TileMap tm, WorkList wl) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool shared_bucket = false;
-    if (i < T) {
-        const uint64_t r = sr[i];
-        const bool same_prev = i > 0 && ((r ^ sr[i - 1]) >> sort_shift) == 0;
-        const bool same_next = i + 1 < T && ((r ^ sr[i + 1]) >> sort_shift) == 0;
-        shared_bucket = same_prev || same_next;
-        if (!shared_bucket && !(thr < 0.0 || rows.all_pass())) {
-            double re, im;
-            rows.coeff_unphased(fmt.t(r), re, im);
-            if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r));
-        }
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t base = (int64_t)blockIdx.x * CLS_TILE + threadIdx.x;
+    uint64_t r[CLS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < CLS_ITEMS; ++j) {
+        const int64_t i = base + j * 256;
+        r[j] = i < T ? sr[i] : 0ull;
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, shared_bucket);
-    if (m == 0u) return;
-    const int lane = threadIdx.x & 31;
-    const uint32_t reg = blockIdx.x % wl.nreg;
-    uint32_t base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(wl.counts + reg, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (shared_bucket) wl.work[(size_t)reg * wl.cap + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    uint32_t m[CLS_ITEMS];
+    uint32_t mine = 0, warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < CLS_ITEMS; ++j) {
+        const int64_t i = base + j * 256;
+        // the neighbours come from the adjacent lanes; the warp's edge lanes load theirs
+        uint64_t rp = __shfl_up_sync(0xffffffffu, r[j], 1), rn = __shfl_down_sync(0xffffffffu, r[j], 1);
+        if (lane == 0 && i > 0 && i < T) rp = sr[i - 1];
+        if (lane == 31 && i + 1 < T) rn = sr[i + 1];
+        bool shared_bucket = false;
+        if (i < T) {
+            const bool same_prev = i > 0 && ((r[j] ^ rp) >> sort_shift) == 0;
+            const bool same_next = i + 1 < T && ((r[j] ^ rn) >> sort_shift) == 0;
+            shared_bucket = same_prev || same_next;
+            if (!shared_bucket && !(thr < 0.0 || rows.all_pass())) {
+                double re, im;
+                rows.coeff_unphased(fmt.t(r[j]), re, im);
+                if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r[j]));
+            }
+        }
+        m[j] = __ballot_sync(0xffffffffu, shared_bucket);
+        if (shared_bucket) mine |= 1u << j;
+        warp_total += (uint32_t)__popc(m[j]);
+    }
+    if (lane == 0) s_warp[wid] = warp_total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c = s_warp[w];
+            s_warp[w] = tot;
+            tot += c;
+        }
+        s_base = tot ? atomicAdd(wl.counts + blockIdx.x % wl.nreg, tot) : 0u;
+    }
+    __syncthreads();
+    if (warp_total == 0u) return;
+    uint32_t pos = s_base + s_warp[wid];
+    uint32_t *dst = wl.work + (size_t)(blockIdx.x % wl.nreg) * wl.cap;
+#pragma unroll
+    for (int j = 0; j < CLS_ITEMS; ++j) {
+        if ((mine >> j) & 1u) dst[pos + __popc(m[j] & lt)] = (uint32_t)(base + j * 256);
+        pos += (uint32_t)__popc(m[j]);
+    }
 }
 
 // pass_all flag of a product: min|a| * min|b| clears the threshold with a 4x margin (the rounded
@@ -780,10 +817,10 @@ __global__ void __launch_bounds__(256) tile_fixup_kernel(TileMap tm, RecFmt fmt,
 // worklist storage: L.slot and L.kept (adjacent, both unused in this mode) hold the regions, the
 // radix histogram buffer (free once the sort is done) holds the counters
 static WorkList tile_worklist(const DedupLayout &L, int64_t T) {
-    const int64_t nb = (T + 255) / 256;
+    const int64_t nb = (T + CLS_TILE - 1) / CLS_TILE;   // CTAs of tile_classify_kernel
     WorkList wl;
     wl.nreg = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(2048, nb / 16));
-    wl.cap = (uint32_t)std::min<int64_t>(((nb + wl.nreg - 1) / wl.nreg) * 256, T);
+    wl.cap = (uint32_t)std::min<int64_t>(((nb + wl.nreg - 1) / wl.nreg) * CLS_TILE, T);
     wl.work = L.slot;
     wl.counts = L.hist;
     return wl;
@@ -791,8 +828,9 @@ static WorkList tile_worklist(const DedupLayout &L, int64_t T) {
 
 int g_tile_qgroup = 16;   // tuning knob 7: B rows per CTA of tile_emit_kernel
 
-int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, double thr,
-                             int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
+int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
+                             const ProductKeySrc *ksrc, double thr, int64_t *n_out, int64_t *n_out_host, void *ws,
+                             size_t ws_bytes, cudaStream_t st) {
     if (ws_bytes < dedup_ws_bytes(T)) {
         set_error("workspace too small: need %zu bytes, got %zu", dedup_ws_bytes(T), ws_bytes);
         return SYM_E_WORKSPACE;
@@ -804,7 +842,8 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
     }
     const int begin = sort_begin_bit(T, fmt);
     uint64_t *sr = nullptr;
-    SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
+    if (ksrc) SYM_TRY(radix_sort_product_keys(*ksrc, recs, L.alt, T, begin, L.hist, &sr, st));
+    else SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
     const unsigned nb = (unsigned)((T + 255) / 256);
     ProductRows rows_sum = rows;
     rows_sum.lazy_phase = true;   // pair_keys_kernel records carry no phase exponent
@@ -821,7 +860,8 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
         return SYM_E_WORKSPACE;
     }
     SYM_CUDA_OK(cudaMemsetAsync(wl.counts, 0, sizeof(uint32_t) * wl.nreg, st));
-    tile_classify_kernel<ProductRows><<<nb, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, thr, tm, wl);
+    tile_classify_kernel<ProductRows><<<(unsigned)((T + CLS_TILE - 1) / CLS_TILE), 256, 0, st>>>(rows_sum, fmt, sr, T, begin, thr,
+                                                                                                tm, wl);
     SYM_LAUNCH_OK();
     link_work_kernel<ProductRows><<<wl.nreg, 256, 0, st>>>(rows, fmt, sr, begin, wl, L.flag, L.link);
     SYM_LAUNCH_OK();

@@ -212,8 +212,10 @@ int dedup_plain_emit(const uint64_t *recs, int64_t T, RecFmt fmt, const PlainRow
                      double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);
 
 // ordered-tile mode (products only); blocks_host mirrors tm.blocks
-int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, double thr,
-                             int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
+struct ProductKeySrc;   // sort.cuh: records generated inside the first radix pass (nullptr: recs already holds them)
+int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
+                             const ProductKeySrc *ksrc, double thr, int64_t *n_out, int64_t *n_out_host, void *ws,
+                             size_t ws_bytes, cudaStream_t st);
 int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
                              const TileBlock *blocks_host, const int32_t *a_y, const int32_t *b_y, int64_t U,
                              uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);

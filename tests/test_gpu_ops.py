@@ -378,6 +378,64 @@ def test_mul_blocks_cleanup_matches_block_products(ops):
         ops.set_tuning(6, 1)
 
 
+@pytest.mark.parametrize("onesweep,fused", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_record_sort_variants_agree(ops, onesweep, fused):
+    """One-sweep passes (decoupled look-back over hundreds of tiles) and the first pass that
+    generates its own records must give exactly what the histogram + scan + scatter form gives:
+    term sets against the oracle, and first-occurrence order (a stable sort) in ordered-tile mode.
+    Also through plain cleanup (records read from memory) and the block-list product."""
+    try:
+        ops.set_tuning(8, onesweep)
+        ops.set_tuning(9, fused)
+        ops.set_tuning(0, 0)
+        n, m1, m2 = 40, 2500, 420                       # 1.05e6 cross terms = 257 sort tiles, one word per block
+        a_s, a_c = po.random_operator(n, m1, seed=77)
+        b_s, b_c = po.random_operator(n, m2, seed=78)
+        b_s[:200] = a_s[:200]
+        a_s[1250:] = a_s[:1250]
+        s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, b_s, b_c)
+        if len(ref_c) == len(cc):
+            assert np.array_equal(s, ref_s)
+        a_s, a_c = po.random_operator(1000, 300, seed=79)
+        b_s, b_c = po.random_operator(1000, 200, seed=80)
+        b_s[:50] = a_s[:50]
+        s, cc, ref_s, ref_c = _check_product(ops, a_s, a_c, b_s, b_c)
+        if len(ref_c) == len(cc):
+            assert np.array_equal(s, ref_s)
+        # block list (8 blocks: still generated inside the first pass; 9: materialised first)
+        a, ac = dev_op(ops, a_s, a_c)
+        b, bc = dev_op(ops, b_s, b_c)
+        for nb in (8, 9):
+            pb = np.linspace(0, 300, nb + 1).astype(int)
+            blocks = [(int(pb[i]), int(pb[i + 1]), 0 if i % 2 else 100, 100 if i % 2 else 200) for i in range(nb)]
+            rows, coeffs = [], []
+            for p0, p1, q0, q1 in blocks:
+                r, c = po.cross_terms(a_s[p0:p1], a_c[p0:p1], b_s[q0:q1], b_c[q0:q1])
+                rows.append(r)
+                coeffs.append(c)
+            ref_s, ref_c = po.symplectic_cleanup(np.vstack(rows), np.hstack(coeffs), 1e-15)
+            xz, c, T = ops.mul_blocks_cleanup(a, ac, b, bc, blocks)
+            s, cc = host_op(ops, xz, c, 1000)
+            ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=np.abs(a_c).max() * np.abs(b_c).max())
+            assert ok, (nb, why)
+            if len(cc) == len(ref_c):
+                assert np.array_equal(s, ref_s)
+        # plain cleanup of 2e5 stored rows with many duplicates: first-occurrence order
+        rng = np.random.default_rng(5)
+        base_s, base_c = po.random_operator(200, 50000, seed=81)
+        idx = rng.integers(0, 50000, size=200000)
+        big_s, big_c = base_s[idx], rng.standard_normal(200000) + 1j * rng.standard_normal(200000)
+        ref_s, ref_c = po.symplectic_cleanup(big_s, big_c, 1e-15)
+        xz, c = ops.cleanup(*dev_op(ops, big_s, big_c))
+        s, cc = host_op(ops, xz, c, 200)
+        assert np.array_equal(s, ref_s)
+        assert np.allclose(cc, ref_c, rtol=1e-12, atol=1e-12)
+    finally:
+        ops.set_tuning(8, 1)
+        ops.set_tuning(9, 1)
+        ops.set_tuning(0, 1 << 22)
+
+
 def test_sorted_hash_order_path(ops):
     """Force the large-product path (output in sorted-hash order) on small inputs."""
     try:
