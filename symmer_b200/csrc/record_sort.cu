@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(THREADS, MINB) os_pass_kernel(Src src, uint64_
         __syncwarp();
     }
     __syncthreads();
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, excl_d = 0;
     if (threadIdx.x < RS_RADIX) {
         const int d = threadIdx.x;
 #pragma unroll
@@ -331,28 +331,12 @@ __global__ void __launch_bounds__(THREADS, MINB) os_pass_kernel(Src src, uint64_
 #pragma unroll
         for (int w = 0; w < RS_RADIX / 32; ++w)
             if (w < wid) woff += wtot[w];
-        const uint32_t excl = dbase[d] + woff;
-        dbase[d] = excl;
-        // decoupled look-back over the tiles before this one
-        uint32_t prev = 0;
-        if (tile > 0) {
-            int64_t t = (int64_t)tile - 1;
-            for (;;) {
-                uint32_t v = ld_volatile_u32(state + (size_t)t * RS_RADIX + d);
-                uint32_t spins = 0;
-                while ((v >> 30) == 0u) {
-                    if (++spins > (1u << 22)) __trap();   // a predecessor never published: fail loudly, never hang
-                    v = ld_volatile_u32(state + (size_t)t * RS_RADIX + d);
-                }
-                prev += v & 0x3fffffffu;
-                if ((v >> 30) == 2u) break;
-                --t;
-            }
-            st_volatile_u32(state + (size_t)tile * RS_RADIX + d, 0x80000000u | (prev + cnt));
-        }
-        delta[d] = bases[d] + prev - excl;
+        excl_d = dbase[d] + woff;
+        dbase[d] = excl_d;
     }
     __syncthreads();
+    // stage the tile in digit order first: it needs no global offsets, and the tiles this one is about to
+    // wait for get that much closer to publishing theirs
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         int64_t idx = wbase + j * 32 + lane;
@@ -360,6 +344,34 @@ __global__ void __launch_bounds__(THREADS, MINB) os_pass_kernel(Src src, uint64_
             uint32_t d = (uint32_t)(k[j] >> shift) & mask;
             srec[dbase[d] + wh[wid][d] + r[j]] = k[j];
         }
+    }
+    if (threadIdx.x < RS_RADIX) {
+        const int d = threadIdx.x;
+        // decoupled look-back over the tiles before this one, four state words in flight per step
+        uint32_t prev = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (t - u >= 0) ? ld_volatile_u32(state + (size_t)(t - u) * RS_RADIX + d) : 0x80000000u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (done) break;
+                    uint32_t x = v[u], spins = 0;
+                    while ((x >> 30) == 0u) {
+                        if (++spins > (1u << 22)) __trap();   // a predecessor never published: fail loudly, never hang
+                        x = ld_volatile_u32(state + (size_t)(t - u) * RS_RADIX + d);
+                    }
+                    prev += x & 0x3fffffffu;
+                    done = (x >> 30) == 2u;
+                }
+                t -= 4;
+            }
+            st_volatile_u32(state + (size_t)tile * RS_RADIX + d, 0x80000000u | (prev + cnt));
+        }
+        delta[d] = bases[d] + prev - excl_d;
     }
     __syncthreads();
     const int64_t remain = T - tile_base;
