@@ -66,10 +66,13 @@ struct WorkList {
     uint32_t *counts;
     uint32_t nreg, cap;
 };
-#define FOR_EACH_WORK(wl, i)                                                   \
-    for (uint32_t _r = blockIdx.x; _r < (wl).nreg; _r += gridDim.x)            \
-        for (uint32_t _k = threadIdx.x, _n = (wl).counts[_r]; _k < _n; _k += blockDim.x) \
-            if (const uint32_t i = (wl).work[(size_t)_r * (wl).cap + _k]; true)
+// consumers: WORK_SPLIT CTAs per region (grid = nreg * WORK_SPLIT), each striding over the region's entries
+constexpr uint32_t WORK_SPLIT = 8;
+#define FOR_EACH_WORK(wl, i)                                                                                     \
+    for (uint32_t _r = blockIdx.x / WORK_SPLIT, _k = (blockIdx.x % WORK_SPLIT) * blockDim.x + threadIdx.x,       \
+                  _n = (wl).counts[_r];                                                                          \
+         _k < _n; _k += WORK_SPLIT * blockDim.x)                                                                 \
+        if (const uint32_t i = (wl).work[(size_t)_r * (wl).cap + _k]; true)
 
 template <class Rows>
 __global__ void __launch_bounds__(256) link_work_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int sort_shift,
@@ -107,26 +110,62 @@ __device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, con
     double re = 0.0, im = 0.0;
     bool have = false, is_multi = false;
     bool prev_mine = true;   // is record j-1 a member of this head's group?
-    for (int64_t j = i + 1; j < T; ++j) {
-        const uint64_t rj = sr[j];
-        if (((r0 ^ rj) >> sort_shift) != 0) break;       // end of the bucket
-        const uint8_t fj = flag[j];
-        bool mine;
-        if (fj == FLAG_PREV) mine = prev_mine;
-        else if (fj == FLAG_LINK) mine = fmt.same_hash(r0, rj) && chain_root(flag, link, (int64_t)link[j]) == i;
-        else mine = false;
-        if (mine) {
-            if (!have) {
-                rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
-                have = true;
-            }
-            double r2, i2;
-            rows.coeff(fmt.t(rj), fmt.e(rj), r2, i2);
-            re += r2;
-            im += i2;
-            is_multi = true;
+    // The walk is sequential in j (np.add.at order) but its loads need not be: records, flags and
+    // coefficients are fetched SUM_BATCH at a time, so a long group (the M identity terms of a square,
+    // say) costs one memory round trip per batch instead of three per member.
+    constexpr int SUM_BATCH = 8;
+    bool open = true;
+    for (int64_t j0 = i + 1; open && j0 < T; j0 += SUM_BATCH) {
+        uint64_t rj[SUM_BATCH];
+        uint8_t fj[SUM_BATCH];
+        int n_in = 0;
+#pragma unroll
+        for (int u = 0; u < SUM_BATCH; ++u) rj[u] = (j0 + u < T) ? sr[j0 + u] : 0ull;
+#pragma unroll
+        for (int u = 0; u < SUM_BATCH; ++u) {
+            const bool in = open && (j0 + u < T) && ((r0 ^ rj[u]) >> sort_shift) == 0;   // still inside the bucket
+            open = in;
+            n_in += in ? 1 : 0;
         }
-        prev_mine = mine;
+        if (n_in == 0) break;
+#pragma unroll
+        for (int u = 0; u < SUM_BATCH; ++u) fj[u] = (u < n_in) ? flag[j0 + u] : FLAG_HEAD;
+        bool mine[SUM_BATCH];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < SUM_BATCH; ++u) {
+            bool mn = false;
+            if (u < n_in) {
+                if (fj[u] == FLAG_PREV) mn = prev_mine;
+                else if (fj[u] == FLAG_LINK)
+                    mn = fmt.same_hash(r0, rj[u]) && chain_root(flag, link, (int64_t)link[j0 + u]) == i;
+                prev_mine = mn;
+            }
+            mine[u] = mn;
+            any |= mn;
+        }
+        if (!any) continue;
+        double cr[SUM_BATCH], ci[SUM_BATCH];
+#pragma unroll
+        for (int u = 0; u < SUM_BATCH; ++u) {
+            cr[u] = 0.0;
+            ci[u] = 0.0;
+            if (mine[u]) rows.coeff(fmt.t(rj[u]), fmt.e(rj[u]), cr[u], ci[u]);
+        }
+        if (!have) {
+            int e0 = fmt.e(r0);
+            if constexpr (TILE) e0 = rows.phase(fmt.t(r0));   // members were stamped by phase_work_kernel, heads were not
+            rows.coeff(fmt.t(r0), e0, re, im);
+            have = true;
+        }
+#pragma unroll
+        for (int u = 0; u < SUM_BATCH; ++u) {
+            if (mine[u]) {
+                re += cr[u];
+                im += ci[u];
+            }
+        }
+        is_multi = true;
     }
     if (TILE) {
         if (is_multi) {
@@ -163,6 +202,19 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T) return;
     sum_one<Rows, BY_T, DIRECT, false>(rows, fmt, sr, T, i, sort_shift, flag, link, thr, acc, keep, multi, TileMap());
+}
+
+// ordered-tile mode: records are generated without a phase exponent (the tiled emission computes it for the
+// survivors); the records that join a group (everything link_work_kernel did not leave as a head) get
+// theirs here, in parallel, between link and sum
+template <class Rows>
+__global__ void __launch_bounds__(256) phase_work_kernel(Rows rows, RecFmt fmt, uint64_t *__restrict__ sr, WorkList wl,
+                                                          const uint8_t *__restrict__ flag) {
+    FOR_EACH_WORK(wl, i) {
+        if (flag[i] == FLAG_HEAD) continue;   // a head computes its own, and only if its group has members
+        const uint64_t rec = sr[i];
+        sr[i] = (rec & ~3ull) | (uint64_t)rows.phase(fmt.t(rec));
+    }
 }
 
 // ordered-tile mode: the reduction over the worklist (records of non-singleton buckets)
@@ -819,7 +871,7 @@ __global__ void __launch_bounds__(256) tile_fixup_kernel(TileMap tm, RecFmt fmt,
 static WorkList tile_worklist(const DedupLayout &L, int64_t T) {
     const int64_t nb = (T + CLS_TILE - 1) / CLS_TILE;   // CTAs of tile_classify_kernel
     WorkList wl;
-    wl.nreg = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(2048, nb / 16));
+    wl.nreg = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(2048, nb));
     wl.cap = (uint32_t)std::min<int64_t>(((nb + wl.nreg - 1) / wl.nreg) * CLS_TILE, T);
     wl.work = L.slot;
     wl.counts = L.hist;
@@ -846,7 +898,6 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
     else SYM_TRY(radix_sort_records(recs, L.alt, T, begin, L.hist, &sr, st));
     const unsigned nb = (unsigned)((T + 255) / 256);
     ProductRows rows_sum = rows;
-    rows_sum.lazy_phase = true;   // pair_keys_kernel records carry no phase exponent
     if (thr >= 0.0 && rows.N > 0) {
         min_abs_flag_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
                                                 reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr, L.total + 2);
@@ -863,9 +914,11 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
     tile_classify_kernel<ProductRows><<<(unsigned)((T + CLS_TILE - 1) / CLS_TILE), 256, 0, st>>>(rows_sum, fmt, sr, T, begin, thr,
                                                                                                 tm, wl);
     SYM_LAUNCH_OK();
-    link_work_kernel<ProductRows><<<wl.nreg, 256, 0, st>>>(rows, fmt, sr, begin, wl, L.flag, L.link);
+    link_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, begin, wl, L.flag, L.link);
     SYM_LAUNCH_OK();
-    sum_work_kernel<ProductRows><<<wl.nreg, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, wl, L.flag, L.link, thr, L.acc, L.multi, tm);
+    phase_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, wl, L.flag);
+    SYM_LAUNCH_OK();
+    sum_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows_sum, fmt, sr, T, begin, wl, L.flag, L.link, thr, L.acc, L.multi, tm);
     SYM_LAUNCH_OK();
     seg_count_kernel<<<(tm.n_seg + 255) / 256, 256, 0, st>>>(tm);
     SYM_LAUNCH_OK();
@@ -920,7 +973,7 @@ int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const 
     }
     if (g_emit_ev1) SYM_CUDA_OK(cudaEventRecord(g_emit_ev1, st));
     const WorkList wl = tile_worklist(L, T);
-    tile_fixup_kernel<<<wl.nreg, 256, 0, st>>>(tm, fmt, sr, wl, L.multi, L.acc, oc);
+    tile_fixup_kernel<<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(tm, fmt, sr, wl, L.multi, L.acc, oc);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }

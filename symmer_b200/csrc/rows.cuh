@@ -34,7 +34,6 @@ struct ProductRows {
     int words;   // 2*W
     uint32_t N = 0;                                // rows of B (0 = unknown)
     const uint32_t *__restrict__ pass_all = nullptr;  // device flag: every single cross term passes |c| > thr
-    bool lazy_phase = false;   // records carry no phase exponent (ordered-tile mode): recompute it on demand
 
     __device__ __forceinline__ bool all_pass() const { return pass_all != nullptr && *pass_all != 0u; }
 
@@ -70,7 +69,8 @@ struct ProductRows {
             if ((a1[k] ^ b1[k]) != (a2[k] ^ b2[k])) return false;
         return true;
     }
-    // phase exponent of the cross term from its rows (base.py:785-788), for the modes whose records do not carry it
+    // phase exponent of the cross term from its rows (base.py:785-788): ordered-tile mode stamps it on the few
+    // records that may take part in a sum (phase_work_kernel); the other modes compute it for every pair up front
     __device__ __noinline__ int phase(uint32_t t) const {
         uint32_t p, q;
         split(t, p, q);
@@ -78,6 +78,7 @@ struct ProductRows {
         const int W = words >> 1;
         uint64_t s = 0, c0 = 0, c1 = 0;
         int y_in = 0;
+#pragma unroll 4
         for (int w = 0; w < W; ++w) {
             const uint64_t xa = ra[w], za = ra[W + w], xb = rb[w], zb = rb[W + w];
             y_in += __popcll(xa & za) + __popcll(xb & zb);
@@ -92,7 +93,6 @@ struct ProductRows {
         uint32_t p, q;
         split(t, p, q);
         cmul(Ac[2 * (size_t)p], Ac[2 * (size_t)p + 1], Bc[2 * (size_t)q], Bc[2 * (size_t)q + 1], re, im);
-        if (lazy_phase) e = phase(t);
         mul_i_pow(re, im, e);
     }
     // |coefficient| only matters (threshold tests): no phase
