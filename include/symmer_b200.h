@@ -121,6 +121,11 @@ int sym_commute(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N
 size_t sym_commute_mma_ws_bytes(int64_t M, int64_t N, int32_t W);
 int sym_commute_mma(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
                     uint8_t *out, void *ws, size_t ws_bytes, void *stream);
+/* Same with out_pitch bytes between output rows (out_pitch >= N). A pitch that is a multiple of 32
+ * keeps every row 16-byte aligned, so ragged N (NaCl: 42 599 terms) takes the 32-byte vector stores
+ * instead of per-byte stores (measured 10x at 36 qubits); bytes N..out_pitch-1 of a row are scratch. */
+int sym_commute_mma_pitched(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
+                            uint8_t *out, int64_t out_pitch, void *ws, size_t ws_bytes, void *stream);
 /* Same symplectic inner product, bit-packed output: out_bits[i][j/32] bit j%32 (row stride
  * ceil(N/32) uint32). Used when the matrix is consumed on the device (masks, graph colouring). */
 int sym_commute_bits(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,

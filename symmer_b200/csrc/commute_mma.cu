@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) transpose_words_kernel(const uint64_t *__
 
 __global__ void __launch_bounds__(MMA_THREADS, 2) commute_mma_kernel(const uint64_t *__restrict__ a_t, uint32_t M,
                                                                       const uint64_t *__restrict__ b_t, uint32_t N, int W,
-                                                                      uint8_t *__restrict__ out) {
+                                                                      uint8_t *__restrict__ out, size_t pitch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA[NUM_STAGES], *sB[NUM_STAGES];
 #pragma unroll
@@ -216,8 +216,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 2) commute_mma_kernel(const uint6
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row < M) {
             const uint32_t jbase = j0 + col_half + cb;
-            uint8_t *dst = out + (size_t)row * N + jbase;
-            if (jbase + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            // pitch = bytes between output rows (>= N). With a pitch that is a multiple of 32 every 32-byte chunk
+            // is aligned and may spill into the row's padding, so the vector stores cover ragged N too.
+            uint8_t *dst = out + (size_t)row * pitch + jbase;
+            if (jbase + 32 <= pitch && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                 uint32_t p[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
@@ -249,7 +251,13 @@ extern "C" size_t sym_commute_mma_ws_bytes(int64_t M, int64_t N, int32_t W) {
 
 extern "C" int sym_commute_mma(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W, uint8_t *out,
                                void *ws, size_t ws_bytes, void *stream) {
+    return sym_commute_mma_pitched(a_xz, M, b_xz, N, W, out, N, ws, ws_bytes, stream);
+}
+
+extern "C" int sym_commute_mma_pitched(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
+                                       uint8_t *out, int64_t out_pitch, void *ws, size_t ws_bytes, void *stream) {
     SYM_REQUIRE(M >= 0 && N >= 0 && W >= 1, "bad size");
+    SYM_REQUIRE(out_pitch >= N, "out_pitch must be >= N");
     SYM_REQUIRE(M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31), "operand too large");
     if (M == 0 || N == 0) return SYM_OK;
     if (ws_bytes < sym_commute_mma_ws_bytes(M, N, W)) {
@@ -276,7 +284,7 @@ extern "C" int sym_commute_mma(const uint64_t *a_xz, int64_t M, const uint64_t *
     const int64_t tiles_m = (M + MMA_M - 1) / MMA_M;
     SYM_REQUIRE(tiles_m <= 65535, "too many A rows for one launch (slice A)");
     dim3 grid((unsigned)((N + MMA_N - 1) / MMA_N), (unsigned)tiles_m);
-    commute_mma_kernel<<<grid, MMA_THREADS, smem, st>>>(a_t, (uint32_t)M, b_t, (uint32_t)N, W, out);
+    commute_mma_kernel<<<grid, MMA_THREADS, smem, st>>>(a_t, (uint32_t)M, b_t, (uint32_t)N, W, out, (size_t)out_pitch);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }

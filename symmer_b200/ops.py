@@ -261,11 +261,14 @@ def commute_mma(a_xz, b_xz):
     M, W = _rows(a_xz)
     N, W2 = _rows(b_xz)
     assert W == W2
-    out = torch.empty((M, N), dtype=torch.uint8, device=a_xz.device)
+    # rows padded to a multiple of 32 bytes: every row stays 16-byte aligned and the kernel keeps its 32-byte
+    # vector stores for ragged N; the caller gets the [M, N] view of the padded buffer
+    pitch = (N + 31) // 32 * 32
+    out = torch.empty((M, pitch), dtype=torch.uint8, device=a_xz.device)
     L = lib()
     ws = workspace(L.sym_commute_mma_ws_bytes(M, N, W))
-    _cabi.check(L.sym_commute_mma(_p(a_xz), M, _p(b_xz), N, W, _p(out), _p(ws), ws.numel(), _stream()))
-    return out.view(torch.bool)
+    _cabi.check(L.sym_commute_mma_pitched(_p(a_xz), M, _p(b_xz), N, W, _p(out), pitch, _p(ws), ws.numel(), _stream()))
+    return out.view(torch.bool)[:, :N]
 
 
 def commute_bits(a_xz, b_xz):

@@ -193,6 +193,26 @@ def test_commute_random_both_kernels(ops, n, m1, m2):
     assert np.array_equal(ops.commute(a, b).cpu().numpy(), ref)
 
 
+def test_commute_mma_unpitched_abi_ragged(ops):
+    """sym_commute_mma with the natural pitch N (odd: rows unaligned, per-byte epilogue) must equal the pitched call."""
+    import ctypes
+    from symmer_b200 import _cabi
+    n, m1, m2 = 36, 300, 2599
+    a_s, _ = po.random_operator(n, m1, seed=4)
+    b_s, _ = po.random_operator(n, m2, seed=5)
+    a = ops.pack(torch.from_numpy(a_s), n)
+    b = ops.pack(torch.from_numpy(b_s), n)
+    out = torch.empty((m1, m2), dtype=torch.uint8, device=a.device)
+    L = ops.lib()
+    ws = ops.workspace(L.sym_commute_mma_ws_bytes(m1, m2, 1))
+    _cabi.check(L.sym_commute_mma(ctypes.c_void_p(a.data_ptr()), m1, ctypes.c_void_p(b.data_ptr()), m2, 1,
+                                  ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    ref = po.commutes_termwise(a_s, b_s)
+    assert np.array_equal(out.cpu().numpy().astype(bool), ref)
+    assert np.array_equal(ops.commute_mma(a, b).cpu().numpy(), ref)
+
+
 def test_commute_large_dispatches_to_tensor_cores(ops):
     n, M = 200, 3000                                   # 9e6 pairs > MMA_MIN_PAIRS
     a_s, _ = po.random_operator(n, M, seed=9)
