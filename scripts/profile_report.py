@@ -28,9 +28,9 @@ def read_launches(path):
 
 def launches(path, out, step_index=4):
     seq = read_launches(path)
-    starts = [i for i, (n, _) in enumerate(seq) if n.startswith('pair_records_kernel')]
-    # a step = from the two sketch/ycount launches before pair_records up to the emit kernel
-    emits = [i for i, (n, _) in enumerate(seq) if n.startswith('emit_')]
+    starts = [i for i, (n, _) in enumerate(seq) if n.startswith(('pair_records_kernel', 'pair_keys_kernel'))]
+    # a step = from the two sketch/ycount launches before the record kernel up to the last kernel of the emission
+    emits = [i for i, (n, _) in enumerate(seq) if n.startswith(('emit_', 'tile_fixup'))]
     k = min(step_index, len(starts) - 1)
     lo, hi = starts[k] - 4, emits[k] + 1
     step = seq[lo:hi]

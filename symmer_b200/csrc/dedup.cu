@@ -136,9 +136,11 @@ __device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, con
         for (int u = 0; u < SUM_BATCH; ++u) {
             bool mn = false;
             if (u < n_in) {
-                if (fj[u] == FLAG_PREV) mn = prev_mine;
-                else if (fj[u] == FLAG_LINK)
-                    mn = fmt.same_hash(r0, rj[u]) && chain_root(flag, link, (int64_t)link[j0 + u]) == i;
+                // only records with this head's hash can be members; in ordered-tile mode the others may not even
+                // have a flag (they never went on the worklist)
+                if (!fmt.same_hash(r0, rj[u])) mn = false;
+                else if (fj[u] == FLAG_PREV) mn = prev_mine;
+                else if (fj[u] == FLAG_LINK) mn = chain_root(flag, link, (int64_t)link[j0 + u]) == i;
                 prev_mine = mn;
             }
             mine[u] = mn;
@@ -227,9 +229,10 @@ __global__ void __launch_bounds__(256) sum_work_kernel(Rows rows, RecFmt fmt, co
         sum_one<Rows, false, true, true>(rows, fmt, sr, T, (int64_t)i, sort_shift, flag, link, thr, acc, nullptr, multi, tm);
 }
 
-// Ordered-tile mode, first pass over the sorted records: a record whose sort bucket holds nothing
-// else is a singleton survivor (or fails the threshold on its own) — no link, no sum, nothing
-// written. Only the records of shared buckets go on the worklist for link / sum / fix-up.
+// Ordered-tile mode, first pass over the sorted records: a record whose sort bucket holds no other
+// record with its full hash is a singleton survivor (or fails the threshold on its own) — no link,
+// no sum, nothing written. Only records with a same-hash bucket mate go on the worklist for
+// link / phase / sum / fix-up (0.4 % of the records of a collision-free 1.25e8-term product).
 constexpr int CLS_ITEMS = 8;                    // records per thread: eight independent loads in flight, and
 constexpr int CLS_TILE = 256 * CLS_ITEMS;       // one counter update (an L2 round trip) per 2048 records
 template <class Rows>
@@ -246,8 +249,8 @@ __global__ void __launch_bounds__(256) tile_classify_kernel(Rows rows, RecFmt fm
         const int64_t i = base + j * 256;
         r[j] = i < T ? sr[i] : 0ull;
     }
-    uint32_t m[CLS_ITEMS];
-    uint32_t mine = 0, warp_total = 0;
+    // pass 1 (unrolled, branch-light): same-hash mate among the two immediate neighbours?
+    uint32_t mine = 0, unsure = 0;   // bit j: record j has a same-hash bucket mate / shares its bucket but not with a same-hash neighbour
 #pragma unroll
     for (int j = 0; j < CLS_ITEMS; ++j) {
         const int64_t i = base + j * 256;
@@ -255,19 +258,51 @@ __global__ void __launch_bounds__(256) tile_classify_kernel(Rows rows, RecFmt fm
         uint64_t rp = __shfl_up_sync(0xffffffffu, r[j], 1), rn = __shfl_down_sync(0xffffffffu, r[j], 1);
         if (lane == 0 && i > 0 && i < T) rp = sr[i - 1];
         if (lane == 31 && i + 1 < T) rn = sr[i + 1];
-        bool shared_bucket = false;
         if (i < T) {
             const bool same_prev = i > 0 && ((r[j] ^ rp) >> sort_shift) == 0;
             const bool same_next = i + 1 < T && ((r[j] ^ rn) >> sort_shift) == 0;
-            shared_bucket = same_prev || same_next;
-            if (!shared_bucket && !(thr < 0.0 || rows.all_pass())) {
+            const bool mate = (same_prev && fmt.same_hash(r[j], rp)) || (same_next && fmt.same_hash(r[j], rn));
+            if (mate) mine |= 1u << j;
+            else if (same_prev || same_next) unsure |= 1u << j;
+        }
+    }
+    // pass 2 (rare: ~3 % of the records share a bucket, almost all of those buckets hold just two): look past
+    // the immediate neighbours for a same-hash mate
+    while (unsure) {
+        const int j = __ffs(unsure) - 1;
+        unsure &= unsure - 1u;
+        const int64_t i = base + j * 256;
+        const uint64_t ri = sr[i];   // (r[] stays in registers: no dynamic indexing)
+        bool mate = false;
+        for (int64_t k = i - 2; k >= 0 && !mate; --k) {
+            const uint64_t rk = sr[k];
+            if (((ri ^ rk) >> sort_shift) != 0) break;
+            mate = fmt.same_hash(ri, rk);
+        }
+        for (int64_t k = i + 2; k < T && !mate; ++k) {
+            const uint64_t rk = sr[k];
+            if (((ri ^ rk) >> sort_shift) != 0) break;
+            mate = fmt.same_hash(ri, rk);
+        }
+        if (mate) mine |= 1u << j;
+    }
+    // singletons: nothing to do unless a single cross term can fail the threshold
+    if (!(thr < 0.0 || rows.all_pass())) {
+#pragma unroll
+        for (int j = 0; j < CLS_ITEMS; ++j) {
+            const int64_t i = base + j * 256;
+            if (i < T && !((mine >> j) & 1u)) {
                 double re, im;
                 rows.coeff_unphased(fmt.t(r[j]), re, im);
                 if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r[j]));
             }
         }
-        m[j] = __ballot_sync(0xffffffffu, shared_bucket);
-        if (shared_bucket) mine |= 1u << j;
+    }
+    uint32_t m[CLS_ITEMS];
+    uint32_t warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < CLS_ITEMS; ++j) {
+        m[j] = __ballot_sync(0xffffffffu, (mine >> j) & 1u);
         warp_total += (uint32_t)__popc(m[j]);
     }
     if (lane == 0) s_warp[wid] = warp_total;
