@@ -99,6 +99,42 @@ def main():
         emit("C3(i) 100 independent non-Clifford rotations of the same 100k-term operator", gpu_s=t100,
              rows_per_s=100 * 100000 / t100)
 
+    if "rotseq" in which or "rotate" in which:
+        # C3(ii): the longest SEQUENTIAL prefix of a random non-Clifford rotation sequence that fits a row cap
+        # (rows grow ~1.5x per rotation: 100 sequential random rotations of 1e5 rows are impossible)
+        cap = 40_000_000                                  # rows: 10.9 GB of packed operator + dedup workspace
+        np.random.seed(4)
+        op = PauliwordOp.random(1000, 100000)
+        gens = []
+        for k in range(24):
+            G = PauliwordOp.random(1000, 1)
+            G.coeff_vec[0] = 1
+            gens.append((G, 0.1 + 1.3 * np.random.rand()))
+        start = op
+        times = []
+        for rep in range(2):      # the first pass pays cudaMalloc for every new buffer size (240 ms cold vs 34 ms warm)
+            op = start
+            torch.cuda.synchronize()
+            rows_in, steps, sizes = 0, 0, [op.n_terms]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for G, th in gens:
+                if op.n_terms * 2 > cap:
+                    break
+                rows_in += op.n_terms
+                op = op.perform_rotations([(G, th)])
+                steps += 1
+                sizes.append(op.n_terms)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e-3)
+        t = times[-1]
+        emit("C3(ii) sequential non-Clifford rotations of a 1000q x 100k-term operator until the next one would exceed "
+             f"{cap:.0e} rows", gpu_s=t, gpu_s_cold_allocator=times[0], rotations=steps, rows_in_total=rows_in,
+             rows_per_s=rows_in / t, rows_after_each=sizes, model_gbs=rows_in * 5.5 * 272 / t / 1e9,
+             frac_hbm=rows_in * 5.5 * 272 / t / 1e9 / PEAK)
+        del op, start
+
     if "expval" in which:
         for tag in ["H2O_STO3G", "NH3_STO3G", "HOOH_STO3G"]:
             symp, coeff, n = load_ham(tag)

@@ -293,6 +293,8 @@ def test_first_occurrence_vs_sorted_hash_switch(sb):
     assert np.allclose(lo.coeff_vec, ref_c, rtol=1e-12)
     ref_s, ref_c = po.multiply(B.symp_matrix, B.coeff_vec, A.symp_matrix, A.coeff_vec)
     same_terms(hi, ref_s, ref_c, scale=float(np.abs(A.coeff_vec).max() * np.abs(B.coeff_vec).max()))
+    if hi.n_terms == len(ref_c):                        # above the switch: ordered-tile mode, same order too
+        assert np.array_equal(hi.symp_matrix, ref_s)
 
 
 def test_molecular_square_heavy_duplication(sb, hamiltonians):

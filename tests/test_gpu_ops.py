@@ -456,6 +456,45 @@ def test_record_sort_variants_agree(ops, onesweep, fused):
         ops.set_tuning(0, 1 << 22)
 
 
+def test_bench_size_product_properties(ops):
+    """BASELINE config C5/8 at FULL size (1000 q, 12 500 x 10 000 terms = 1.25e8 cross terms, 34 GB of output),
+    checked through size-independent properties: random 1000-qubit rows never collide, so every cross term
+    survives and — first-occurrence order — output row t = q*M + p must be A[p] ^ B[q] bit for bit; a block of
+    64 rows of A against all of B is compared with the materialised cross terms (rows bit-exact, coefficients
+    1e-14), and 2e6 random rows with the XOR of their operands."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs 60 GB of free device memory")
+    n, M, N = 1000, 12500, 10000
+    a_s, a_c = po.random_operator(n, M, seed=100)
+    b_s, b_c = po.random_operator(n, N, seed=7)
+    a, ac = dev_op(ops, a_s, a_c)
+    b, bc = dev_op(ops, b_s, b_c)
+    xz, c = ops.mul_cleanup(a, ac, b, bc)
+    assert xz.shape[0] == M * N and c.shape[0] == M * N
+    # (1) a 64-row block of A against all of B, against the materialised cross terms of the same block
+    p0 = 4321
+    blk_xz, blk_c = ops.cross_mul(a[p0:p0 + 64].contiguous(), ac[p0:p0 + 64].contiguous(), b, bc)   # t' = q*64 + p'
+    t = (torch.arange(N, device=a.device).repeat_interleave(64) * M + p0 + torch.arange(64, device=a.device).repeat(N))
+    assert torch.equal(xz[t], blk_xz)
+    assert torch.allclose(c[t], blk_c, rtol=1e-14, atol=0)
+    # ... and that block against the oracle on a slice small enough for the CPU
+    ref_rows, ref_c = po.cross_terms(a_s[p0:p0 + 64], a_c[p0:p0 + 64], b_s[:50], b_c[:50])
+    assert np.array_equal(ops.unpack(blk_xz[:3200].contiguous(), n).cpu().numpy(), ref_rows)
+    assert np.allclose(blk_c[:3200].cpu().numpy(), ref_c, rtol=1e-14, atol=0)
+    # (2) 2e6 random output rows equal the XOR of their operands
+    g = torch.Generator(device=a.device)
+    g.manual_seed(0)
+    ts = torch.randint(0, M * N, (2_000_000,), device=a.device, generator=g)
+    assert torch.equal(xz[ts], a[ts % M] ^ b[ts // M])
+    # (3) |coefficient| of every output term = |a_p| |b_q| (phases are powers of i): a checksum over all 1.25e8 terms
+    mag = (ac.abs()[None, :] * bc.abs()[:, None]).reshape(-1)
+    assert torch.allclose(c.abs(), mag, rtol=1e-13, atol=0)
+    del xz, c, mag
+    ops.release_workspace()
+    torch.cuda.empty_cache()
+
+
 def test_sorted_hash_order_path(ops):
     """Force the large-product path (output in sorted-hash order) on small inputs."""
     try:
