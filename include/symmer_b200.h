@@ -95,6 +95,13 @@ int sym_mul_blocks_count(const uint64_t *a_xz, const double *a_c, int64_t M_tota
                          const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
                          double zero_threshold, int64_t *n_out, int64_t *n_out_host, void *ws,
                          size_t ws_bytes, void *stream);
+/* sym_mul_blocks_count with the sketch and Y-count tables of A supplied by the caller (what
+ * sym_sketch_rows / sym_ycount would compute; both NULL = computed here). */
+int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a_c, const uint64_t *a_sketch,
+                                const int32_t *a_ycount, int64_t M_total, const uint64_t *b_xz,
+                                const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host,
+                                int32_t nblk, double zero_threshold, int64_t *n_out, int64_t *n_out_host,
+                                void *ws, size_t ws_bytes, void *stream);
 int sym_mul_blocks_emit(const uint64_t *a_xz, const double *a_c, int64_t M_total, const uint64_t *b_xz,
                         const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
                         int64_t U, uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, void *stream);
@@ -145,6 +152,19 @@ size_t sym_rotate_ws_bytes(int64_t M);
 int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_t W, const uint64_t *q_xz,
                double cos_a, double sin_a, int32_t mode, double sign, uint64_t *out_xz, double *out_c,
                int64_t *n_out, void *ws, size_t ws_bytes, void *stream);
+
+/* Fused form of the general rotation INCLUDING its dedup (large operators). sym_rotate_split leaves
+ * the M rows stably partitioned into (commuting with Q | anticommuting with Q), coefficients
+ * untouched, together with the row sketches and Y counts of the partitioned rows (computed in the
+ * same read as the commutation test); n_commuting: device int64[1]. The rotation is then ONE
+ * block-list product of the split operator with the three-row operator [I, cos*I, -i*sin*Q]
+ * (sym_mul_blocks_count_tables / sym_mul_blocks_emit with blocks {0,nc,0,1} and {nc,M,1,3}):
+ * base.py:1090-1161 expressed through base.py:764-794, the rotated rows are never materialised
+ * before the dedup. out_sketch: uint64[M], out_ycount: int32[M]. */
+size_t sym_rotate_split_ws_bytes(int64_t M);
+int sym_rotate_split(const uint64_t *xz, const double *c, int64_t M, int32_t W, const uint64_t *q_xz,
+                     uint64_t *out_xz, double *out_c, uint64_t *out_sketch, int32_t *out_ycount,
+                     int64_t *n_commuting, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- a9/a10 matrix-free operator application: to_sparse_matrix (base.py:1458-1510) semantics,
  * qubit 0 = most significant bit of the basis index.

@@ -30,6 +30,8 @@ SIGNATURES = {
     "sym_mul_blocks_ws_bytes": (c_sz, [c_i64, c_i64, c_i32, c_p, c_i32]),
     "sym_mul_blocks_count": (ctypes.c_int, [c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_f64, c_p, c_p, c_p,
                                             c_sz, c_p]),
+    "sym_mul_blocks_count_tables": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_f64,
+                                                   c_p, c_p, c_p, c_sz, c_p]),
     "sym_mul_blocks_emit": (ctypes.c_int, [c_p, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_p, c_i32, c_i64, c_p, c_p, c_p,
                                            c_sz, c_p]),
     "sym_cleanup_ws_bytes": (c_sz, [c_i64, c_i32]),
@@ -44,6 +46,8 @@ SIGNATURES = {
     "sym_rotate_ws_bytes": (c_sz, [c_i64]),
     "sym_rotate": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_f64, c_f64, c_i32, c_f64, c_p, c_p, c_p, c_p, c_sz,
                                   c_p]),
+    "sym_rotate_split_ws_bytes": (c_sz, [c_i64]),
+    "sym_rotate_split": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "sym_term_masks": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_p, c_p, c_p]),
     "sym_apply": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i64, c_i64, c_i32, c_p]),
     "sym_expval": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i64, c_i64, c_i32, c_p]),

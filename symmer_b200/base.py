@@ -25,6 +25,10 @@ warnings.simplefilter('always', UserWarning)
 
 # above this many qubits a dense 2^n state no longer fits comfortably next to the operator
 DENSE_STATE_MAX_QUBITS = 30
+# general rotations of operators with at least this many terms run rotation + dedup as one block-list product
+# (ops.rotate_dedup: measured 4.7 vs 6.0 ms at 1e7 rows, equal at 1e6); smaller ones keep the two-step form,
+# which has fewer launches (0.30 vs 0.39 ms at 1e5 rows)
+FUSED_ROTATION_MIN_TERMS = 1 << 21
 
 
 class PauliwordOp:
@@ -388,7 +392,8 @@ class PauliwordOp:
 
     # ------------------------------------------------------------------ a8 rotations (base.py:1090-1186)
     def _rotation_step(self, Pword: "PauliwordOp", angle, threshold: float = 1e-18):
-        """One rotation without the trailing dedup. Returns (operator, needs_dedup)."""
+        """One rotation. Returns (operator, status): 'clifford' = rows relabelled, no dedup needed;
+        'dirty' = general rotation without its dedup; 'clean' = general rotation already deduplicated."""
         if angle is None:
             angle = np.pi / 2
         if complex(angle).imag != 0:
@@ -404,19 +409,23 @@ class PauliwordOp:
         if abs(int_part - multiple) <= threshold:
             sign = -1.0 if int_part in [2, 3] else 1.0          # base.py:1148-1149
             xz, cc = ops.rotate(self._xz, c, Pword._xz, 0.0, 0.0, 1 if int_part % 2 else 2, sign)
-            return PauliwordOp._from_device(xz, cc, self.n_qubits), False
+            return PauliwordOp._from_device(xz, cc, self.n_qubits), 'clifford'
         if abs(angle) > 1e6:
             warnings.warn('Large angle can lead to precision errors: recommend using high-precision math library '
                           'such as mpmath or redefine angle in range [-pi, pi]')
+        if self.n_terms >= FUSED_ROTATION_MIN_TERMS:
+            # rotation + dedup as one block-list product: the rotated rows are never materialised in between
+            xz, cc = ops.rotate_dedup(self._xz, c, Pword._xz, np.cos(angle), np.sin(angle))
+            return PauliwordOp._from_device(xz, cc, self.n_qubits), 'clean'
         xz, cc = ops.rotate(self._xz, c, Pword._xz, np.cos(angle), np.sin(angle), 0)
-        return PauliwordOp._from_device(xz, cc, self.n_qubits), True
+        return PauliwordOp._from_device(xz, cc, self.n_qubits), 'dirty'
 
     def _rotate_by_single_Pword(self, Pword: "PauliwordOp", angle: float = None,
                                 threshold: float = 1e-18) -> "PauliwordOp":
         """R P R^dagger with R = exp(i*angle/2*Q). Clifford angles return without dedup (like the
         reference); general angles are cleaned once."""
-        op, needs = self._rotation_step(Pword, angle, threshold)
-        return op.cleanup() if needs else op
+        op, status = self._rotation_step(Pword, angle, threshold)
+        return op.cleanup() if status == 'dirty' else op
 
     def perform_rotations(self, rotations: List[Tuple["PauliwordOp", float]]) -> "PauliwordOp":
         """base.py:1163-1186. The reference cleans up after every rotation; a Clifford rotation is a
@@ -424,9 +433,10 @@ class PauliwordOp:
         op = self
         pending = True
         for pauli_rotation, angle in rotations:
-            op, needs = op._rotation_step(pauli_rotation, angle)
-            if needs:
+            op, status = op._rotation_step(pauli_rotation, angle)
+            if status == 'dirty':
                 op = op.cleanup()
+            if status != 'clifford':
                 pending = False
         return op.cleanup() if pending else op
 

@@ -330,40 +330,44 @@ __global__ void __launch_bounds__(256) tile_classify_kernel(Rows rows, RecFmt fm
 
 // pass_all flag of a product: min|a| * min|b| clears the threshold with a 4x margin (the rounded
 // product of any single pair is within a few ulp of |a||b|), so no singleton cross term can fail
-// |c| > thr and the sum kernel need not gather coefficients for them. One block; M + N is small.
-__global__ void __launch_bounds__(1024) min_abs_flag_kernel(const double2 *__restrict__ a, int64_t M,
-                                                             const double2 *__restrict__ b, int64_t N, double thr,
-                                                             uint32_t *__restrict__ flag) {
-    __shared__ double sa[32], sb[32];
-    double ma = INFINITY, mb = INFINITY;
-    for (int64_t i = threadIdx.x; i < M; i += 1024) {
+// |c| > thr and the reduction need not gather coefficients for them. Grid-stride minimum per operand
+// (bit patterns of non-negative doubles order like unsigned integers: atomicMin), then one thread.
+__global__ void __launch_bounds__(256) min_abs_kernel(const double2 *__restrict__ a, int64_t M, unsigned long long *__restrict__ out) {
+    __shared__ double sm[8];
+    double m = INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
         double h = hypot(a[i].x, a[i].y);
         if (!(h >= 0.0)) h = 0.0;   // NaN
-        ma = fmin(ma, h);
-    }
-    for (int64_t i = threadIdx.x; i < N; i += 1024) {
-        double h = hypot(b[i].x, b[i].y);
-        if (!(h >= 0.0)) h = 0.0;
-        mb = fmin(mb, h);
+        m = fmin(m, h);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ma = fmin(ma, __shfl_xor_sync(0xffffffffu, ma, o));
-        mb = fmin(mb, __shfl_xor_sync(0xffffffffu, mb, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        sa[threadIdx.x >> 5] = ma;
-        sb[threadIdx.x >> 5] = mb;
-    }
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 32; ++w) {
-            ma = fmin(ma, sa[w]);
-            mb = fmin(mb, sb[w]);
-        }
-        const double prod = ma * mb;
-        *flag = (isfinite(prod) && prod > 4.0 * thr) ? 1u : 0u;
+        for (int w = 1; w < 8; ++w) m = fmin(m, sm[w]);
+        atomicMin(out, (unsigned long long)__double_as_longlong(m));
     }
+}
+
+__global__ void min_abs_flag_finish_kernel(const unsigned long long *__restrict__ mins, double thr, uint32_t *__restrict__ flag) {
+    const double prod = __longlong_as_double((long long)mins[0]) * __longlong_as_double((long long)mins[1]);
+    *flag = (isfinite(prod) && prod > 4.0 * thr) ? 1u : 0u;
+}
+
+// mins: two uint64 of scratch (free until the scans run); flag: device uint32
+static int launch_min_abs_flag(const double2 *a, int64_t M, const double2 *b, int64_t N, double thr, unsigned long long *mins,
+                               uint32_t *flag, cudaStream_t st) {
+    SYM_CUDA_OK(cudaMemsetAsync(mins, 0xff, 2 * sizeof(unsigned long long), st));
+    const unsigned ga = (unsigned)std::max<int64_t>(1, std::min<int64_t>((M + 255) / 256, (int64_t)num_sms() * 8));
+    const unsigned gb = (unsigned)std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 8));
+    min_abs_kernel<<<ga, 256, 0, st>>>(a, M, mins);
+    SYM_LAUNCH_OK();
+    min_abs_kernel<<<gb, 256, 0, st>>>(b, N, mins + 1);
+    SYM_LAUNCH_OK();
+    min_abs_flag_finish_kernel<<<1, 1, 0, st>>>(mins, thr, flag);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
 }
 
 // Compaction (emit phase): kept_t[slot] = term index of the survivor, out_c[slot] = its coefficient,
@@ -678,10 +682,9 @@ static int dedup_plan(uint64_t *recs, int64_t T, RecFmt fmt, const Rows &rows, d
     Rows rows_sum = rows;
     if constexpr (std::is_same<Rows, ProductRows>::value && !BY_T) {
         if (thr >= 0.0 && rows.N > 0) {
-            min_abs_flag_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
-                                                    reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr,
-                                                    L.total + 2);
-            SYM_LAUNCH_OK();
+            SYM_TRY(launch_min_abs_flag(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
+                                        reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr,
+                                        reinterpret_cast<unsigned long long *>(L.scratch), L.total + 2, st));
             rows_sum.pass_all = L.total + 2;
         }
     }
@@ -934,9 +937,9 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
     const unsigned nb = (unsigned)((T + 255) / 256);
     ProductRows rows_sum = rows;
     if (thr >= 0.0 && rows.N > 0) {
-        min_abs_flag_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
-                                                reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr, L.total + 2);
-        SYM_LAUNCH_OK();
+        SYM_TRY(launch_min_abs_flag(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
+                                    reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr,
+                                    reinterpret_cast<unsigned long long *>(L.scratch), L.total + 2, st));
         rows_sum.pass_all = L.total + 2;
     }
     // worklist of the records that share a sort bucket

@@ -528,6 +528,16 @@ extern "C" int sym_mul_blocks_count(const uint64_t *a_xz, const double *a_c, int
                                     const double *b_c, int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
                                     double zero_threshold, int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes,
                                     void *stream) {
+    return sym_mul_blocks_count_tables(a_xz, a_c, nullptr, nullptr, M_total, b_xz, b_c, N, W, blocks_host, nblk,
+                                       zero_threshold, n_out, n_out_host, ws, ws_bytes, stream);
+}
+
+extern "C" int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a_c, const uint64_t *a_sketch,
+                                           const int32_t *a_ycount, int64_t M_total, const uint64_t *b_xz, const double *b_c,
+                                           int64_t N, int32_t W, const int64_t *blocks_host, int32_t nblk,
+                                           double zero_threshold, int64_t *n_out, int64_t *n_out_host, void *ws,
+                                           size_t ws_bytes, void *stream) {
+    SYM_REQUIRE((a_sketch == nullptr) == (a_ycount == nullptr), "a_sketch and a_ycount come together");
     MulBlocksPlan P;
     SYM_TRY(mul_blocks_plan(M_total, N, W, blocks_host, nblk, ws, ws_bytes, P));
     cudaStream_t st = (cudaStream_t)stream;
@@ -540,9 +550,14 @@ extern "C" int sym_mul_blocks_count(const uint64_t *a_xz, const double *a_c, int
         set_error("workspace too small: need %zu bytes, got %zu", P.need, ws_bytes);
         return SYM_E_WORKSPACE;
     }
-    SYM_TRY(sym_sketch_rows(a_xz, M_total, W, P.a_sk, st));
+    if (a_sketch) {   // the caller already has A's tables (sym_rotate_split): two reads of A saved
+        SYM_CUDA_OK(cudaMemcpyAsync(P.a_sk, a_sketch, sizeof(uint64_t) * (size_t)M_total, cudaMemcpyDeviceToDevice, st));
+        SYM_CUDA_OK(cudaMemcpyAsync(P.a_y, a_ycount, sizeof(int32_t) * (size_t)M_total, cudaMemcpyDeviceToDevice, st));
+    } else {
+        SYM_TRY(sym_sketch_rows(a_xz, M_total, W, P.a_sk, st));
+        SYM_TRY(sym_ycount(a_xz, M_total, W, P.a_y, st));
+    }
     SYM_TRY(sym_sketch_rows(b_xz, N, W, P.b_sk, st));
-    SYM_TRY(sym_ycount(a_xz, M_total, W, P.a_y, st));
     SYM_TRY(sym_ycount(b_xz, N, W, P.b_y, st));
     RecFmt fmt{t_bits_for(M_total * N)};
     if (P.mode == MODE_TILES) {

@@ -11,7 +11,8 @@ namespace symb {
 
 // info byte: bit0 = anticommutes with Q, bits1-2 = phase exponent e of P*Q (coefficient factor i^e)
 __global__ void __launch_bounds__(256) rotate_info_kernel(const uint64_t *__restrict__ xz, int64_t M, int W,
-                                                           const uint64_t *__restrict__ q_xz, uint8_t *__restrict__ info) {
+                                                           const uint64_t *__restrict__ q_xz, uint8_t *__restrict__ info,
+                                                           uint64_t *__restrict__ sk_out, int32_t *__restrict__ y_out) {
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
@@ -38,19 +39,27 @@ __global__ void __launch_bounds__(256) rotate_info_kernel(const uint64_t *__rest
     if (lane == 0) {
         int e = (3 * (ya + yb) + yout + 2 * sg) & 3;
         info[row] = (uint8_t)(par | (e << 1));
+        if (y_out) y_out[row] = ya;
+    }
+    if (sk_out) {   // generic widths: a second pass over the row (uniform branch, whole warp)
+        const uint64_t h = warp_sketch_row(r, 2 * W, lane);
+        if (lane == 0) sk_out[row] = h;
     }
 }
 
 // fast path (W even, W <= 16): 8 lanes per row, 16-byte loads, 4 rows per warp
+// Optionally also the row sketch (same function as sketch8_kernel) and the Y count of every row, so that
+// a product that follows (the fused rotation) need not read the rows again for its tables.
 __global__ void __launch_bounds__(256) rotate_info8_kernel(const uint64_t *__restrict__ xz, int64_t M, int W,
-                                                            const uint64_t *__restrict__ q_xz, uint8_t *__restrict__ info) {
+                                                            const uint64_t *__restrict__ q_xz, uint8_t *__restrict__ info,
+                                                            uint64_t *__restrict__ sk_out, int32_t *__restrict__ y_out) {
     const int lane = threadIdx.x & 31, g = lane & 7;
     int64_t row = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
     const bool ok = row < M;
     const uint4 *r4 = reinterpret_cast<const uint4 *>(xz + (ok ? row : 0) * 2 * W);
     const uint4 *q4 = reinterpret_cast<const uint4 *>(q_xz);
     const int chunks = W >> 1;   // 16-byte chunks per block
-    uint64_t comm = 0, s = 0;
+    uint64_t comm = 0, s = 0, h = 0;
     int ya = 0, yb = 0, yout = 0;
 #pragma unroll
     for (int rep = 0; rep < 1; ++rep) {
@@ -68,10 +77,17 @@ __global__ void __launch_bounds__(256) rotate_info8_kernel(const uint64_t *__res
                 ya += __popcll(xa[k] & za[k]);
                 yb += __popcll(xb[k] & zb[k]);
                 yout += __popcll((xa[k] ^ xb[k]) & (za[k] ^ zb[k]));
+                // row words 2c+k (X block) and 2(chunks+c)+k (Z block): the lane index of the sketch is the word index
+                h ^= lane_linear(xa[k], 2 * c + k) ^ lane_linear(za[k], 2 * (chunks + c) + k);
             }
         }
     }
     int par = __popcll(comm) & 1, sg = __popcll(s) & 1;
+    if (sk_out) {
+        h ^= __shfl_xor_sync(0xffffffffu, h, 1);
+        h ^= __shfl_xor_sync(0xffffffffu, h, 2);
+        h ^= __shfl_xor_sync(0xffffffffu, h, 4);
+    }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
         par ^= __shfl_xor_sync(0xffffffffu, par, o);
@@ -83,6 +99,8 @@ __global__ void __launch_bounds__(256) rotate_info8_kernel(const uint64_t *__res
     if (ok && g == 0) {
         int e = (3 * (ya + yb) + yout + 2 * sg) & 3;
         info[row] = (uint8_t)(par | (e << 1));
+        if (sk_out) sk_out[row] = h;
+        if (y_out) y_out[row] = ya;
     }
 }
 
@@ -201,8 +219,33 @@ __global__ void __launch_bounds__(256) rotate_write4_kernel(const uint4 *__restr
     }
 }
 
+// sym_rotate_split: stable split of the rows into (commuting with Q | anticommuting with Q), coefficients untouched.
+// The general rotation is then ONE block-list product (sym_mul_blocks_*) of the split operator with the three-row
+// operator [I, cos I, -i sin Q]: commuting rows x [I], anticommuting rows x [cos I, -i sin Q] — the rotated
+// rows are never materialised before the dedup (base.py:1090-1161 as a product, base.py:764-794).
+__global__ void __launch_bounds__(256) rotate_split_kernel(const uint4 *__restrict__ xz, const double2 *__restrict__ c, int64_t M,
+                                                            uint32_t chunks, const uint8_t *__restrict__ info,
+                                                            const uint32_t *__restrict__ rank, const uint32_t *__restrict__ total,
+                                                            const uint64_t *__restrict__ sk, const int32_t *__restrict__ yc,
+                                                            uint4 *__restrict__ out_xz, double2 *__restrict__ out_c,
+                                                            uint64_t *__restrict__ out_sk, int32_t *__restrict__ out_y) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t row = g / chunks;
+    if (row >= (size_t)M) return;
+    const uint32_t k = (uint32_t)(g - row * chunks);
+    const bool anti = info[row] & 1;
+    const size_t n_comm = (size_t)M - *total;
+    const size_t dst = anti ? n_comm + rank[row] : row - rank[row];
+    out_xz[dst * chunks + k] = xz[g];
+    if (k == 0) {
+        out_c[dst] = c[row];
+        out_sk[dst] = sk[row];
+        out_y[dst] = yc[row];
+    }
+}
+
 __global__ void rotate_count_kernel(const uint32_t *__restrict__ total, int64_t M, int mode, int64_t *__restrict__ n_out) {
-    *n_out = (mode == 0) ? M + (int64_t)*total : M;
+    *n_out = (mode == 0) ? M + (int64_t)*total : (mode == 3 ? M - (int64_t)*total : M);   // 3: sym_rotate_split
 }
 
 }  // namespace symb
@@ -235,9 +278,9 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
     uint32_t *scratch = ar.take<uint32_t>(scan_scratch_elems(M));
     uint32_t *total = ar.take<uint32_t>(4);
     if (group8_ok(W))
-        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info);
+        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, nullptr, nullptr);
     else
-        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info);
+        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, nullptr, nullptr);
     SYM_LAUNCH_OK();
     if (mode == 0) {
         rotate_anti_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(info, M, anti);
@@ -268,6 +311,52 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
         SYM_LAUNCH_OK();
     }
     rotate_count_kernel<<<1, 1, 0, st>>>(total, M, mode, n_out);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" size_t sym_rotate_split_ws_bytes(int64_t M) {
+    if (M < 1) M = 1;
+    return sym_rotate_ws_bytes(M) + arena_need((size_t)M, 8) + arena_need((size_t)M, 4) + 1024;
+}
+
+extern "C" int sym_rotate_split(const uint64_t *xz, const double *c, int64_t M, int32_t W, const uint64_t *q_xz,
+                                uint64_t *out_xz, double *out_c, uint64_t *out_sketch, int32_t *out_ycount,
+                                int64_t *n_commuting, void *ws, size_t ws_bytes, void *stream) {
+    SYM_REQUIRE(M >= 0 && W >= 1, "bad size");
+    SYM_REQUIRE(M < ((int64_t)1 << 32), "too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (M == 0) {
+        SYM_CUDA_OK(cudaMemsetAsync(n_commuting, 0, sizeof(int64_t), st));
+        return SYM_OK;
+    }
+    if (ws_bytes < sym_rotate_split_ws_bytes(M)) {
+        set_error("workspace too small");
+        return SYM_E_WORKSPACE;
+    }
+    Arena ar(ws, ws_bytes);
+    uint8_t *info = ar.take<uint8_t>((size_t)M);
+    uint8_t *anti = ar.take<uint8_t>((size_t)M);
+    uint32_t *rank = ar.take<uint32_t>((size_t)M);
+    uint32_t *scratch = ar.take<uint32_t>(scan_scratch_elems(M));
+    uint32_t *total = ar.take<uint32_t>(4);
+    uint64_t *sk = ar.take<uint64_t>((size_t)M);
+    int32_t *yc = ar.take<int32_t>((size_t)M);
+    if (group8_ok(W))
+        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, sk, yc);
+    else
+        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, sk, yc);
+    SYM_LAUNCH_OK();
+    rotate_anti_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(info, M, anti);
+    SYM_LAUNCH_OK();
+    SYM_TRY(scan_exclusive_u8(anti, rank, M, total, scratch, st));
+    const uint32_t chunks = (uint32_t)W;
+    const size_t threads = (size_t)M * chunks;
+    rotate_split_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const uint4 *>(xz), reinterpret_cast<const double2 *>(c), M, chunks, info, rank, total, sk, yc,
+        reinterpret_cast<uint4 *>(out_xz), reinterpret_cast<double2 *>(out_c), out_sketch, out_ycount);
+    SYM_LAUNCH_OK();
+    rotate_count_kernel<<<1, 1, 0, st>>>(total, M, 3, n_commuting);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }

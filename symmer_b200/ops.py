@@ -181,7 +181,7 @@ def mul_cleanup(a_xz, a_c, b_xz, b_c, zero_threshold=1e-15):
     return out_xz, out_c
 
 
-def mul_blocks_cleanup(a_xz, a_c, b_xz, b_c, blocks, zero_threshold=1e-15):
+def mul_blocks_cleanup(a_xz, a_c, b_xz, b_c, blocks, zero_threshold=1e-15, a_sketch=None, a_ycount=None):
     """Product + cleanup restricted to disjoint rectangular blocks [(p0, p1, q0, q1), ...] of the
     cross-term grid A x B (the exchange-free sharded product: rank r passes the blocks it owns).
     Survivors leave block by block in (q, p) order. Returns (xz[U,2W], c[U], n_cross_terms)."""
@@ -201,8 +201,9 @@ def mul_blocks_cleanup(a_xz, a_c, b_xz, b_c, blocks, zero_threshold=1e-15):
         _cabi.check(-1)
     ws = workspace(nbytes)
     U = ctypes.c_int64(0)
-    _cabi.check(L.sym_mul_blocks_count(_p(a_xz), _p(_coeff(a_c)), M, _p(b_xz), _p(_coeff(b_c)), N, W, flat, len(blocks),
-                                       _thr(zero_threshold), None, ctypes.byref(U), _p(ws), ws.numel(), _stream()))
+    _cabi.check(L.sym_mul_blocks_count_tables(_p(a_xz), _p(_coeff(a_c)), _p(a_sketch), _p(a_ycount), M, _p(b_xz),
+                                              _p(_coeff(b_c)), N, W, flat, len(blocks), _thr(zero_threshold), None,
+                                              ctypes.byref(U), _p(ws), ws.numel(), _stream()))
     U = U.value
     out_xz = torch.empty((U, 2 * W), dtype=torch.int64, device=dev)
     out_c = torch.empty(U, dtype=torch.complex128, device=dev)
@@ -295,6 +296,40 @@ def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0):
     if mode == 0:
         n = int(n_out.item())
         return out_xz[:n], out_c[:n]
+    return out_xz, out_c
+
+
+def rotate_split(xz, c, q_xz):
+    """Stable split of the rows into (commuting with Q | anticommuting with Q) with the sketch and Y-count
+    tables of the split rows: (xz', c', sketch int64[M], ycount int32[M], n_commuting)."""
+    M, W = _rows(xz)
+    dev = xz.device
+    out_xz = torch.empty_like(xz)
+    out_c = torch.empty_like(c)
+    sk = torch.empty(M, dtype=torch.int64, device=dev)
+    yc = torch.empty(M, dtype=torch.int32, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    if M == 0:
+        return out_xz, out_c, sk, yc, 0
+    L = lib()
+    ws = workspace(L.sym_rotate_split_ws_bytes(M))
+    _cabi.check(L.sym_rotate_split(_p(xz), _p(_coeff(c)), M, W, _p(q_xz), _p(out_xz), _p(out_c), _p(sk), _p(yc), _p(n_out),
+                                   _p(ws), ws.numel(), _stream()))
+    return out_xz, out_c, sk, yc, int(n_out.item())
+
+
+def rotate_dedup(xz, c, q_xz, cos_a, sin_a, zero_threshold=1e-15):
+    """General rotation R P R^dagger, R = exp(i*angle/2*Q), INCLUDING its dedup, as one block-list product
+    (base.py:1090-1161 = base.py:764-794 applied to blocks): commuting rows x [I], anticommuting rows x
+    [cos I, -i sin Q]. The rotated rows are never materialised before the dedup; survivors leave with the
+    commuting rows first. Returns (xz', c')."""
+    M, W = _rows(xz)
+    sxz, sc, sk, yc, n_comm = rotate_split(xz, c, q_xz)
+    b_xz = torch.zeros((3, 2 * W), dtype=torch.int64, device=xz.device)
+    b_xz[2] = q_xz.reshape(-1)
+    b_c = torch.tensor([1.0, float(cos_a), -1j * float(sin_a)], dtype=torch.complex128, device=xz.device)
+    out_xz, out_c, _ = mul_blocks_cleanup(sxz, sc, b_xz, b_c, [(0, n_comm, 0, 1), (n_comm, M, 1, 3)], zero_threshold,
+                                          a_sketch=sk, a_ycount=yc)
     return out_xz, out_c
 
 

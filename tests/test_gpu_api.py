@@ -141,6 +141,39 @@ def test_rotations_against_reference(sb, golden):
         same_terms(op.perform_rotations(rots), g["out_symp"], g["out_coeff"], scale=np.abs(g["coeff"]).max())
 
 
+def test_fused_rotation_path(sb, golden):
+    """General rotations through ops.rotate_dedup (rotation + dedup as one block-list product, the path of
+    operators with >= 2^15 terms), forced on the reference's golden cases, then on a 40 000-term operator
+    against the oracle, including a sequence that mixes Clifford and general angles."""
+    import symmer_b200.base as base
+    P = sb.PauliwordOp
+    old = base.FUSED_ROTATION_MIN_TERMS
+    try:
+        base.FUSED_ROTATION_MIN_TERMS = 0
+        for nm in sorted(k for k in golden if k.startswith(("rot_single_", "rot_seq_"))):
+            g = golden[nm]
+            op = P(g["symp"], g["coeff"])
+            rots = [(P(q.reshape(1, -1), [1]), None if np.isnan(a) else float(a)) for q, a in zip(g["q_symp"], g["angle"])]
+            same_terms(op.perform_rotations(rots), g["out_symp"], g["out_coeff"], scale=np.abs(g["coeff"]).max())
+        np.random.seed(5)
+        op = P.random(3, 10)
+        Q = P.from_list(['XYZ'], [1])
+        for t in [0.37, -1.9, 2.5]:
+            R = np.cos(t / 2) * np.eye(8) + 1j * np.sin(t / 2) * Q.to_sparse_matrix.toarray()
+            expect = R @ op.to_sparse_matrix.toarray() @ R.conj().T
+            assert np.allclose(op.perform_rotations([(Q, t)]).to_sparse_matrix.toarray(), expect)
+    finally:
+        base.FUSED_ROTATION_MIN_TERMS = old
+    for n, M in [(1000, 40000), (70, 33000)]:
+        s, c = po.random_operator(n, M, seed=n)
+        s[M // 2:] = s[:M - M // 2]                              # duplicated rows: the fused dedup must merge them
+        qs, _ = po.random_operator(n, 3, seed=n + 1)
+        rots = [(qs[0], 0.37), (qs[1], np.pi / 2), (qs[2], -1.1)]
+        ref_s, ref_c = po.perform_rotations(s, c, rots)
+        out = P(s, c).perform_rotations([(P(q.reshape(1, -1), [1]), a) for q, a in rots])
+        same_terms(out, ref_s, ref_c, scale=np.abs(c).max() * 2)
+
+
 def test_rotation_is_conjugation(sb):
     """R P R^dagger with R = cos(t/2) I + i sin(t/2) Q, checked on dense matrices (reference
     tests/test_evolution/test_circuit_symmerlator.py style)."""

@@ -314,6 +314,31 @@ def test_rotations_golden(ops, golden):
         assert ok, (nm, why)
 
 
+@pytest.mark.parametrize("n", [3, 64, 100, 700, 1000, 1100, 2100])
+def test_rotate_split_tables_and_fused_rotation(ops, n):
+    """sym_rotate_split: stable (commuting | anticommuting) partition whose sketch / Y-count tables equal
+    sym_sketch_rows / sym_ycount of the partitioned rows; then the fused rotation + dedup against the oracle."""
+    M = 777
+    s, c = po.random_operator(n, M, seed=n)
+    s[500:] = s[:277]                                        # duplicate rows
+    q, _ = po.random_operator(n, 1, seed=n + 5)
+    xz, cc = dev_op(ops, s, c)
+    qxz = ops.pack(torch.from_numpy(q), n)
+    sxz, sc, sk, yc, n_comm = ops.rotate_split(xz, cc, qxz)
+    comm = po.commutes_termwise(s, q)[:, 0]
+    order = np.concatenate([np.flatnonzero(comm), np.flatnonzero(~comm)])
+    assert n_comm == int(comm.sum())
+    assert np.array_equal(ops.unpack(sxz, n).cpu().numpy(), s[order])
+    assert np.array_equal(sc.cpu().numpy(), c[order])
+    assert torch.equal(sk, ops.sketch(sxz))
+    assert torch.equal(yc, ops.ycount(sxz))
+    for angle in [0.37, -2.2]:
+        oxz, oc = ops.rotate_dedup(xz, cc, qxz, np.cos(angle), np.sin(angle))
+        ref_s, ref_c = po.perform_rotations(s, c, [(q[0], angle)])
+        ok, why = po.compare_term_sets(*host_op(ops, oxz, oc, n), ref_s, ref_c, scale=np.abs(c).max() * 2)
+        assert ok, (angle, why)
+
+
 @pytest.mark.parametrize("n,m1,m2", [(5, 300, 7), (64, 130, 13), (100, 257, 9), (200, 129, 20), (500, 140, 33),
                                      (1000, 260, 45), (1000, 100, 3), (1000, 128, 128), (1100, 30, 9), (40, 1, 50)])
 def test_ordered_tile_mode_first_occurrence_order(ops, n, m1, m2):
