@@ -94,8 +94,56 @@ __device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_
 // TILE (ordered-tile mode, see rows.cuh): nothing is written for a record that survives as a
 // singleton; a record that does not survive sets its drop bit, and a surviving group head leaves
 // its sum in acc[i] with multi[i] = 1 for the fix-up pass after the row emission.
+// ---- the reduction of one head's group, in three parts: walk (sequential, may defer a long group to its warp),
+// ---- the warp-cooperative walk, and the epilogue that stores the result
+
+// Epilogue: what a finished head (or a non-head) writes.
 template <class Rows, bool BY_T, bool DIRECT, bool TILE>
-__device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t T,
+__device__ __forceinline__ void sum_finish(const Rows &rows, const RecFmt &fmt, uint64_t r0, int64_t d, double re, double im,
+                                           bool have, bool is_multi, double thr, double2 *__restrict__ acc,
+                                           uint8_t *__restrict__ keep, uint8_t *__restrict__ multi, const TileMap &tm) {
+    if (TILE) {
+        if (is_multi) {
+            if (keep_test(re, im, thr)) {
+                acc[d] = make_double2(re, im);
+                multi[d] = 1;
+            } else {
+                tm.mark_dropped(fmt.t(r0));
+            }
+        } else if (!(thr < 0.0 || rows.all_pass())) {
+            rows.coeff_unphased(fmt.t(r0), re, im);
+            if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r0));
+        }
+        return;
+    }
+    if (is_multi || !DIRECT) {
+        if (!have) rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+        acc[d] = make_double2(re, im);
+        multi[d] = 1;
+        keep[d] = keep_test(re, im, thr);
+    } else if (thr < 0.0 || rows.all_pass()) {
+        keep[d] = 1;         // singleton that cannot fail the threshold: the coefficient is computed once, at emission
+    } else {
+        rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
+        keep[d] = keep_test(re, im, thr);
+    }
+}
+
+template <class Rows, bool TILE>
+__device__ __forceinline__ void head_coeff(const Rows &rows, const RecFmt &fmt, uint64_t r0, double &re, double &im) {
+    int e0 = fmt.e(r0);
+    if constexpr (TILE) e0 = rows.phase(fmt.t(r0));   // members were stamped by phase_work_kernel, heads were not
+    rows.coeff(fmt.t(r0), e0, re, im);
+}
+
+// Sequential walk of the head at sorted position i (np.add.at order). Records, flags and coefficients are fetched
+// SUM_BATCH at a time. Returns true when the group is still open after SUM_DEFER_BATCHES batches: the caller's warp
+// then redoes this head cooperatively (sum_walk_warp) — a long group (the M identity terms of a square, the ~50-term
+// groups of a molecular H*H) would otherwise be one thread's chain of dependent loads.
+constexpr int SUM_BATCH = 8;
+constexpr int SUM_DEFER_BATCHES = 2;
+template <class Rows, bool BY_T, bool DIRECT, bool TILE>
+__device__ __forceinline__ bool sum_one(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t T,
                                         int64_t i, int sort_shift, const uint8_t *__restrict__ flag,
                                         const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
                                         uint8_t *__restrict__ keep, uint8_t *__restrict__ multi, const TileMap &tm) {
@@ -105,17 +153,15 @@ __device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, con
     if (flag[i] != FLAG_HEAD) {
         if (TILE) tm.mark_dropped(fmt.t(r0));
         else keep[d] = 0;
-        return;
+        return false;
     }
     double re = 0.0, im = 0.0;
     bool have = false, is_multi = false;
     bool prev_mine = true;   // is record j-1 a member of this head's group?
-    // The walk is sequential in j (np.add.at order) but its loads need not be: records, flags and
-    // coefficients are fetched SUM_BATCH at a time, so a long group (the M identity terms of a square,
-    // say) costs one memory round trip per batch instead of three per member.
-    constexpr int SUM_BATCH = 8;
     bool open = true;
+    int batches = 0;
     for (int64_t j0 = i + 1; open && j0 < T; j0 += SUM_BATCH) {
+        if (batches++ == SUM_DEFER_BATCHES) return true;   // long group: nothing has been written yet
         uint64_t rj[SUM_BATCH];
         uint8_t fj[SUM_BATCH];
         int n_in = 0;
@@ -155,9 +201,7 @@ __device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, con
             if (mine[u]) rows.coeff(fmt.t(rj[u]), fmt.e(rj[u]), cr[u], ci[u]);
         }
         if (!have) {
-            int e0 = fmt.e(r0);
-            if constexpr (TILE) e0 = rows.phase(fmt.t(r0));   // members were stamped by phase_work_kernel, heads were not
-            rows.coeff(fmt.t(r0), e0, re, im);
+            head_coeff<Rows, TILE>(rows, fmt, r0, re, im);
             have = true;
         }
 #pragma unroll
@@ -169,30 +213,73 @@ __device__ __forceinline__ void sum_one(const Rows &rows, const RecFmt &fmt, con
         }
         is_multi = true;
     }
-    if (TILE) {
-        if (is_multi) {
-            if (keep_test(re, im, thr)) {
-                acc[d] = make_double2(re, im);
-                multi[d] = 1;
-            } else {
-                tm.mark_dropped(fmt.t(r0));
-            }
-        } else if (!(thr < 0.0 || rows.all_pass())) {
-            rows.coeff_unphased(fmt.t(r0), re, im);
-            if (!keep_test(re, im, thr)) tm.mark_dropped(fmt.t(r0));
+    sum_finish<Rows, BY_T, DIRECT, TILE>(rows, fmt, r0, d, re, im, have, is_multi, thr, acc, keep, multi, tm);
+    return false;
+}
+
+// The same walk by a whole (converged) warp for the head at position i: lane l looks at record base + l, membership
+// of the FLAG_PREV chains is resolved with ballots (a PREV record follows the nearest earlier record that is not
+// PREV), coefficients are gathered in parallel and added by every lane in record order — the same additions in the
+// same order as the sequential walk, so the result is bit-identical to it. Every lane returns the sums.
+template <class Rows, bool TILE>
+__device__ __forceinline__ void sum_walk_warp(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                              int64_t i, int sort_shift, const uint8_t *__restrict__ flag,
+                                              const uint32_t *__restrict__ link, int lane, double &re, double &im,
+                                              bool &is_multi) {
+    const uint64_t r0 = sr[i];
+    head_coeff<Rows, TILE>(rows, fmt, r0, re, im);
+    is_multi = false;
+    bool carry = true;   // membership of the record just before this window (the head itself at first)
+    for (int64_t base = i + 1; base < T; base += 32) {
+        const int64_t j = base + lane;
+        const uint64_t rj = j < T ? sr[j] : 0ull;
+        const bool in = j < T && ((r0 ^ rj) >> sort_shift) == 0;
+        const uint32_t out_mask = __ballot_sync(0xffffffffu, !in);
+        const int n_in = out_mask ? __ffs(out_mask) - 1 : 32;        // the bucket is contiguous
+        if (n_in == 0) break;
+        const bool valid = lane < n_in;
+        const uint8_t fj = valid ? flag[j] : FLAG_HEAD;
+        const bool sh = valid && fmt.same_hash(r0, rj);
+        const bool is_prev = sh && fj == FLAG_PREV;
+        const bool m0 = sh && fj == FLAG_LINK && chain_root(flag, link, (int64_t)link[j]) == i;
+        const uint32_t decided = __ballot_sync(0xffffffffu, !is_prev);
+        const uint32_t m0_mask = __ballot_sync(0xffffffffu, m0);
+        const uint32_t lower = decided & ((1u << lane) - 1u);
+        const bool mine = is_prev ? (lower ? ((m0_mask >> (31 - __clz(lower))) & 1u) != 0u : carry) : m0;
+        const uint32_t mine_mask = __ballot_sync(0xffffffffu, mine);
+        carry = (mine_mask >> 31) & 1u;
+        double cr = 0.0, ci = 0.0;
+        if (mine) rows.coeff(fmt.t(rj), fmt.e(rj), cr, ci);
+        for (uint32_t m = mine_mask; m; m &= m - 1u) {               // uniform loop, record order
+            const int l = __ffs(m) - 1;
+            re += __shfl_sync(0xffffffffu, cr, l);
+            im += __shfl_sync(0xffffffffu, ci, l);
         }
-        return;
+        is_multi |= mine_mask != 0u;
+        if (n_in < 32) break;
     }
-    if (is_multi || !DIRECT) {
-        if (!have) rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
-        acc[d] = make_double2(re, im);
-        multi[d] = 1;
-        keep[d] = keep_test(re, im, thr);
-    } else if (thr < 0.0 || rows.all_pass()) {
-        keep[d] = 1;         // singleton that cannot fail the threshold: the coefficient is computed once, at emission
-    } else {
-        rows.coeff(fmt.t(r0), fmt.e(r0), re, im);
-        keep[d] = keep_test(re, im, thr);
+}
+
+// One record per lane (valid lanes only), then the warp finishes its deferred heads one after the other.
+template <class Rows, bool BY_T, bool DIRECT, bool TILE>
+__device__ __forceinline__ void sum_warp_step(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t T,
+                                              bool valid, int64_t i, int sort_shift, const uint8_t *__restrict__ flag,
+                                              const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
+                                              uint8_t *__restrict__ keep, uint8_t *__restrict__ multi, const TileMap &tm) {
+    const int lane = threadIdx.x & 31;
+    const bool deferred =
+        valid && sum_one<Rows, BY_T, DIRECT, TILE>(rows, fmt, sr, T, i, sort_shift, flag, link, thr, acc, keep, multi, tm);
+    for (uint32_t pend = __ballot_sync(0xffffffffu, deferred); pend; pend &= pend - 1u) {
+        const int l = __ffs(pend) - 1;
+        const int64_t il = __shfl_sync(0xffffffffu, (long long)i, l);
+        double re, im;
+        bool is_multi;
+        sum_walk_warp<Rows, TILE>(rows, fmt, sr, T, il, sort_shift, flag, link, lane, re, im, is_multi);
+        if (lane == l) {
+            const uint64_t r0 = sr[il];
+            const int64_t d = BY_T ? (int64_t)fmt.t(r0) : il;
+            sum_finish<Rows, BY_T, DIRECT, TILE>(rows, fmt, r0, d, re, im, true, is_multi, thr, acc, keep, multi, tm);
+        }
     }
 }
 
@@ -201,9 +288,9 @@ __global__ void __launch_bounds__(256) sum_kernel(Rows rows, RecFmt fmt, const u
                                                    int sort_shift, const uint8_t *__restrict__ flag,
                                                    const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
                                                    uint8_t *__restrict__ keep, uint8_t *__restrict__ multi) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    sum_one<Rows, BY_T, DIRECT, false>(rows, fmt, sr, T, i, sort_shift, flag, link, thr, acc, keep, multi, TileMap());
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    sum_warp_step<Rows, BY_T, DIRECT, false>(rows, fmt, sr, T, i < T, i, sort_shift, flag, link, thr, acc, keep, multi,
+                                             TileMap());
 }
 
 // ordered-tile mode: records are generated without a phase exponent (the tiled emission computes it for the
@@ -225,8 +312,14 @@ __global__ void __launch_bounds__(256) sum_work_kernel(Rows rows, RecFmt fmt, co
                                                         int sort_shift, WorkList wl, const uint8_t *__restrict__ flag,
                                                         const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
                                                         uint8_t *__restrict__ multi, TileMap tm) {
-    FOR_EACH_WORK(wl, i)
-        sum_one<Rows, false, true, true>(rows, fmt, sr, T, (int64_t)i, sort_shift, flag, link, thr, acc, nullptr, multi, tm);
+    // whole warps walk the region together (a lane without an entry idles) so that they can finish long groups jointly
+    const uint32_t r = blockIdx.x / WORK_SPLIT, n = wl.counts[r];
+    for (uint32_t k0 = (blockIdx.x % WORK_SPLIT) * blockDim.x + (threadIdx.x & ~31u); k0 < n; k0 += WORK_SPLIT * blockDim.x) {
+        const uint32_t k = k0 + (threadIdx.x & 31u);
+        const bool valid = k < n;
+        const int64_t i = valid ? (int64_t)wl.work[(size_t)r * wl.cap + k] : 0;
+        sum_warp_step<Rows, false, true, true>(rows, fmt, sr, T, valid, i, sort_shift, flag, link, thr, acc, nullptr, multi, tm);
+    }
 }
 
 // Ordered-tile mode, first pass over the sorted records: a record whose sort bucket holds no other

@@ -65,8 +65,16 @@ struct ProductRows {
         split(t2, p2, q2);
         const uint64_t *a1 = A + (size_t)p1 * words, *b1 = B + (size_t)q1 * words;
         const uint64_t *a2 = A + (size_t)p2 * words, *b2 = B + (size_t)q2 * words;
-        for (int k = 0; k < words; ++k)
-            if ((a1[k] ^ b1[k]) != (a2[k] ^ b2[k])) return false;
+        // rows are 16-byte aligned (words = 2W is even): compare 16 bytes per step, four loads in flight
+        const uint4 *u1 = reinterpret_cast<const uint4 *>(a1), *v1 = reinterpret_cast<const uint4 *>(b1);
+        const uint4 *u2 = reinterpret_cast<const uint4 *>(a2), *v2 = reinterpret_cast<const uint4 *>(b2);
+        const int chunks = words >> 1;
+        for (int k = 0; k < chunks; ++k) {
+            const uint4 x1 = u1[k], y1 = v1[k], x2 = u2[k], y2 = v2[k];
+            if (((x1.x ^ y1.x) != (x2.x ^ y2.x)) | ((x1.y ^ y1.y) != (x2.y ^ y2.y)) | ((x1.z ^ y1.z) != (x2.z ^ y2.z)) |
+                ((x1.w ^ y1.w) != (x2.w ^ y2.w)))
+                return false;
+        }
         return true;
     }
     // phase exponent of the cross term from its rows (base.py:785-788): ordered-tile mode stamps it on the few
@@ -116,9 +124,13 @@ struct PlainRows {
     __device__ __forceinline__ uint2 locate(uint32_t t) const { return make_uint2(t, 0u); }
     __device__ __forceinline__ uint4 chunk_at(uint2 h, int c) const { return chunk(h.x, c); }
     __device__ __forceinline__ bool equal(uint32_t t1, uint32_t t2) const {
-        const uint64_t *r1 = X + (size_t)t1 * words, *r2 = X + (size_t)t2 * words;
-        for (int k = 0; k < words; ++k)
-            if (r1[k] != r2[k]) return false;
+        const uint4 *r1 = reinterpret_cast<const uint4 *>(X + (size_t)t1 * words);
+        const uint4 *r2 = reinterpret_cast<const uint4 *>(X + (size_t)t2 * words);
+        const int chunks = words >> 1;   // words = 2W is even: rows are 16-byte aligned
+        for (int k = 0; k < chunks; ++k) {
+            const uint4 a = r1[k], b = r2[k];
+            if ((a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w)) return false;
+        }
         return true;
     }
     __device__ __forceinline__ void coeff(uint32_t t, int, double &re, double &im) const {
