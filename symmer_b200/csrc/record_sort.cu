@@ -396,10 +396,9 @@ size_t record_hist_elems(int64_t T) {
     return h + scan_scratch_elems((int64_t)h) + 64 + OS_EXTRA_ELEMS;
 }
 
-template <class Src>
-static int os_launch_pass(const Src &src, uint64_t *out, int64_t T, int shift, uint32_t mask, const uint32_t *bases,
-                          uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st) {
-    constexpr int TH = 256, IT = 16, MB = 4;
+template <class Src, int TH, int IT, int MB>
+static int os_launch_shape(const Src &src, uint64_t *out, int64_t T, int shift, uint32_t mask, const uint32_t *bases,
+                           uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st) {
     constexpr size_t smem = RS_TILE * 8 + (TH / 32) * RS_RADIX * 4 + 2 * RS_RADIX * 4 + 32 * 4 + 64;
     static bool attr_done = false;
     if (!attr_done) {
@@ -410,6 +409,17 @@ static int os_launch_pass(const Src &src, uint64_t *out, int64_t T, int shift, u
     os_pass_kernel<Src, TH, IT, MB><<<(unsigned)ntiles, TH, smem, st>>>(src, out, T, shift, mask, bases, state, ticket);
     SYM_LAUNCH_OK();
     return SYM_OK;
+}
+
+template <class Src>
+static int os_launch_pass(const Src &src, uint64_t *out, int64_t T, int shift, uint32_t mask, const uint32_t *bases,
+                          uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st) {
+    switch (g_scatter_variant) {   // tuning knob 2 (CTA shape); 3 = 256 threads x 16 records, 4 CTAs/SM is the default
+        case 1: return os_launch_shape<Src, 512, 8, 2>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
+        case 2: return os_launch_shape<Src, 512, 8, 3>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
+        case 5: return os_launch_shape<Src, 256, 16, 5>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
+        default: return os_launch_shape<Src, 256, 16, 4>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
+    }
 }
 
 // keys of pass 0 come from `first` (a buffer or the product key generator), later passes ping-pong a <-> b
