@@ -138,6 +138,12 @@ int sym_commute_mma_pitched(const uint64_t *a_xz, int64_t M, const uint64_t *b_x
 int sym_commute_bits(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
                      uint32_t *out_bits, void *stream);
 
+/* Qubit-wise commutation: PauliwordOp.qubitwise_commutes_termwise / adjacency_matrix_qwc
+ * (base.py:985-1009, 1065-1072). out[i*N + j] = 1 iff on every qubit where A[i] and B[j] both act
+ * non-trivially they carry the same Pauli (uint8, the reference's bool[M,N]). */
+int sym_commute_qwc(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
+                    uint8_t *out, void *stream);
+
 /* ---- a8 rotations: PauliwordOp._rotate_by_single_Pword (base.py:1090-1161)
  * One rotation R P R^dagger, R = exp(i*angle/2*Q), Q = q_xz (a single packed row, coefficient 1).
  * mode 0: general angle: writes M + M_ac rows (row i keeps slot i with cos*c for anticommuting P;
@@ -240,6 +246,14 @@ int sym_project(const uint64_t *xz, const double *c, int64_t M, int32_t W, int32
                 const int32_t *stab_cols, const double *stab_eigs, int32_t S, const int32_t *free_qubits,
                 int32_t n_free, uint64_t *out_xz, double *out_c, int64_t *n_out, int64_t *n_out_host,
                 void *ws, size_t ws_bytes, void *stream);
+
+/* ---- qubit relabelling / embedding: PauliwordOp.reindex (base.py:493-521), PauliwordOp.tensor
+ * (base.py:1188-1204), QuantumState.reindex (base.py:1910-1936).
+ * Output rows have n_out qubits (uint64[M][2*W'], W' = max(1, ceil(n_out/64))); bit k of the output
+ * X (Z) block = bit src[k] of the input X (Z) block, 0 where src[k] < 0 (src: device int32[n_out],
+ * every entry < 64*W_in). Coefficients are untouched. */
+int sym_gather_qubits(const uint64_t *xz, int64_t M, int32_t W_in, const int32_t *src, int32_t n_out,
+                      uint64_t *out_xz, void *stream);
 
 /* ---- multi-GPU building blocks: the product path split at its exchange point.
  * A record is one 64-bit word  [ hash : 62-tb bits | t : tb bits | e : 2 bits ]  with

@@ -275,6 +275,54 @@ def commutes_termwise(a_symp, b_symp) -> np.ndarray:
     return ~matmul_gf2(a_symp, omega_b)
 
 
+def qubitwise_commutes_termwise(a_symp, b_symp) -> np.ndarray:
+    """True where A[i] and B[j] commute qubit by qubit; shape (M, N). base.py:985-1009: on the qubits where
+    both terms are non-trivial (`non_I`) the X bits and the Z bits must agree."""
+    a_symp = np.asarray(a_symp, dtype=bool)
+    b_symp = np.asarray(b_symp, dtype=bool)
+    n = a_symp.shape[1] // 2
+    assert b_symp.shape[1] == 2 * n, "Pauliwords defined for different number of qubits"
+    ax, az = a_symp[:, :n], a_symp[:, n:]
+    columns = []
+    for x_term, z_term in zip(b_symp[:, :n], b_symp[:, n:]):
+        non_i = (ax | az) & (x_term | z_term)                            # :1001
+        x_match = np.all((ax & non_i) == (x_term & non_i), axis=1)       # :1003
+        z_match = np.all((az & non_i) == (z_term & non_i), axis=1)       # :1004
+        columns.append((x_match & z_match).reshape(-1, 1))               # :1006
+    if not columns:
+        return np.zeros((a_symp.shape[0], 0), dtype=bool)
+    return np.hstack(columns)
+
+
+def reindex(symp, qubit_map) -> np.ndarray:
+    """PauliwordOp.reindex, base.py:493-521: `new[:, old_indices] = old[:, new_indices]` on both blocks."""
+    symp = np.asarray(symp, dtype=bool)
+    n = symp.shape[1] // 2
+    if isinstance(qubit_map, list):
+        old_indices, new_indices = sorted(qubit_map), qubit_map
+    else:
+        old_indices, new_indices = zip(*qubit_map.items())
+    old_indices, new_indices = list(old_indices), list(new_indices)
+    assert len(new_indices) == len(set(new_indices)), 'Duplicated index'
+    assert not set(old_indices).difference(new_indices), 'Assignment conflict'
+    x, z = symp[:, :n].copy(), symp[:, n:].copy()
+    x[:, old_indices] = symp[:, :n][:, new_indices]
+    z[:, old_indices] = symp[:, n:][:, new_indices]
+    return np.hstack([x, z])
+
+
+def tensor(a_symp, a_coeff, b_symp, b_coeff):
+    """PauliwordOp.tensor, base.py:1188-1204: pad both factors with identities, then the ordinary product."""
+    a_symp = np.asarray(a_symp, dtype=bool)
+    b_symp = np.asarray(b_symp, dtype=bool)
+    nl, nr = a_symp.shape[1] // 2, b_symp.shape[1] // 2
+    pad_l = np.zeros((a_symp.shape[0], nr), dtype=bool)
+    pad_r = np.zeros((b_symp.shape[0], nl), dtype=bool)
+    left = np.hstack([a_symp[:, :nl], pad_l, a_symp[:, nl:], pad_l])
+    right = np.hstack([pad_r, b_symp[:, :nr], pad_r, b_symp[:, nr:]])
+    return multiply(left, a_coeff, right, b_coeff)
+
+
 # ----------------------------------------------------------------------------------------------
 # a8  rotations                                                       base.py:1090-1186
 # ----------------------------------------------------------------------------------------------

@@ -6,11 +6,14 @@ owns the memory) and every kernel is reached through the C ABI of include/symmer
 """
 from . import _cabi  # noqa: F401  (raises if the CUDA library is missing and cannot be built)
 
-__all__ = ["PauliwordOp", "QuantumState", "IndependentOp", "QubitTapering", "S3Projection"]
+__all__ = ["PauliwordOp", "QuantumState", "IndependentOp", "QubitTapering", "S3Projection", "single_term_expval",
+           "get_PauliwordOp_projector", "get_ij_operator", "change_of_basis_XY_to_Z"]
+_BASE_NAMES = ("PauliwordOp", "QuantumState", "single_term_expval", "get_PauliwordOp_projector", "get_ij_operator",
+               "change_of_basis_XY_to_Z")
 
 
 def __getattr__(name):
-    if name in ("PauliwordOp", "QuantumState"):
+    if name in _BASE_NAMES:
         from . import base
         return getattr(base, name)
     if name == "IndependentOp":

@@ -259,6 +259,112 @@ class PauliwordOp:
     def __iter__(self):
         return iter([self[i] for i in range(self.n_terms)])
 
+    # ------------------------------------------------------------------ qubit relabelling / embedding
+    @staticmethod
+    def _reindex_source(n_qubits: int, qubit_map) -> np.ndarray:
+        """Source qubit of every output position for `reindex` (base.py:506-519, 1923-1934): the reference assigns
+        `new[:, old_indices] = old[:, new_indices]`, i.e. output column old_i reads input column new_i."""
+        if isinstance(qubit_map, list):
+            old_indices, new_indices = sorted(qubit_map), qubit_map
+        elif isinstance(qubit_map, dict):
+            old_indices, new_indices = zip(*qubit_map.items())
+        else:
+            raise TypeError('qubit_map must be a list or a dictionary')
+        old_set, new_set = set(old_indices), set(new_indices)
+        setdiff = old_set.difference(new_set)
+        assert len(new_indices) == len(new_set), 'Duplicated index'
+        assert len(setdiff) == 0, f'Assignment conflict: indices {setdiff} cannot be mapped.'
+        src = np.arange(n_qubits, dtype=np.int32)
+        src[np.asarray(old_indices, dtype=np.int64)] = np.asarray(new_indices, dtype=np.int32)
+        return src
+
+    def reindex(self, qubit_map: Union[List[int], Dict[int, int]]) -> "PauliwordOp":
+        """base.py:493-521: re-label qubits (bit permutation of the packed rows on the device; no dedup, like the
+        reference)."""
+        src = self._reindex_source(self.n_qubits, qubit_map)
+        return PauliwordOp._from_device(ops.gather_qubits(self._xz, src, self.n_qubits), self._coeff_dev().clone(),
+                                        self.n_qubits)
+
+    def tensor(self, right_op: "PauliwordOp") -> "PauliwordOp":
+        """base.py:1188-1204: self (x) right_op. Each factor is embedded into the wider register by the qubit-gather
+        kernel, the tensor product is then the ordinary operator product."""
+        nl, nr = self.n_qubits, right_op.n_qubits
+        src_left = np.concatenate([np.arange(nl, dtype=np.int32), np.full(nr, -1, dtype=np.int32)])
+        src_right = np.concatenate([np.full(nl, -1, dtype=np.int32), np.arange(nr, dtype=np.int32)])
+        left = PauliwordOp._from_device(ops.gather_qubits(self._xz, src_left, nl), self._coeff_dev(), nl + nr)
+        right = PauliwordOp._from_device(ops.gather_qubits(right_op._xz, src_right, nr), right_op._coeff_dev(), nl + nr)
+        return left * right
+
+    def set_processing_method(self, method) -> None:
+        """base.py:76-80. The engine never forks after CUDA initialisation, so the reference's multiprocessing
+        fan-out (process_handler.py) has no counterpart: every method runs on the device."""
+        if method != 'single_thread':
+            warnings.warn(f"processing method '{method}' ignored: symmer_b200 runs every kernel on the GPU from one process")
+
+    def to_dataframe(self):
+        """base.py:1419-1434."""
+        import pandas as pd
+        op_dict = self.to_dictionary
+        coeffs = np.array(list(op_dict.values()), dtype=complex)
+        DF_out = pd.DataFrame.from_dict({'Pauli terms': list(op_dict.keys()), 'Coefficients (real)': coeffs.real})
+        if np.any(coeffs.imag):
+            DF_out['Coefficients (imaginary)'] = coeffs.imag
+        return DF_out
+
+    @classmethod
+    def from_openfermion(cls, openfermion_op, n_qubits=None) -> "PauliwordOp":
+        """base.py:179-202 (needs openfermion, which is an optional third-party dependency)."""
+        try:
+            from openfermion import QubitOperator, count_qubits
+        except ImportError as err:
+            raise ImportError('PauliwordOp.from_openfermion needs the openfermion package') from err
+        assert (isinstance(openfermion_op, QubitOperator)), 'Must supply a QubitOperator'
+        if n_qubits is None:
+            n_qubits = count_qubits(openfermion_op)
+        operator_dict = {}
+        for term, coeff in openfermion_op.terms.items():          # utils.py QubitOperator_to_dict
+            chars = ['I'] * n_qubits
+            for index, pauli in term:
+                chars[index] = pauli
+            key = ''.join(chars)
+            operator_dict[key] = operator_dict.get(key, 0) + coeff
+        if not operator_dict:
+            return cls.empty(n_qubits)
+        return cls.from_dictionary(operator_dict)
+
+    @classmethod
+    def from_qiskit(cls, qiskit_op) -> "PauliwordOp":
+        """base.py:204-221 (needs qiskit, an optional third-party dependency)."""
+        try:
+            from qiskit.quantum_info import SparsePauliOp
+        except ImportError as err:
+            raise ImportError('PauliwordOp.from_qiskit needs the qiskit package') from err
+        assert (isinstance(qiskit_op, SparsePauliOp)), 'Must supply a SparsePauliOp'
+        labels = [p.to_label() for p in qiskit_op.paulis]
+        return cls.from_list(labels, list(qiskit_op.coeffs)).cleanup()
+
+    @property
+    def to_openfermion(self):
+        """base.py:1378-1389."""
+        try:
+            from openfermion import QubitOperator
+        except ImportError as err:
+            raise ImportError('PauliwordOp.to_openfermion needs the openfermion package') from err
+        open_f = QubitOperator()
+        for row, coeff in zip(self.symp_matrix, self.coeff_vec):
+            label = symplectic_to_string(row)
+            open_f += QubitOperator(' '.join(f'{p}{q}' for q, p in enumerate(label) if p != 'I'), coeff)
+        return open_f
+
+    @property
+    def to_qiskit(self):
+        """base.py:1391-1401."""
+        try:
+            from qiskit.quantum_info import SparsePauliOp
+        except ImportError as err:
+            raise ImportError('PauliwordOp.to_qiskit needs the qiskit package') from err
+        return SparsePauliOp([symplectic_to_string(row) for row in self.symp_matrix], coeffs=self.coeff_vec.tolist())
+
     # ------------------------------------------------------------------ a3 Y_count (base.py:604-615)
     @property
     def Y_count(self) -> np.ndarray:
@@ -389,6 +495,96 @@ class PauliwordOp:
         if self.n_terms < 4:
             return True
         return check_adjmat_noncontextual(self.adjacency_matrix)
+
+    def qubitwise_commutes_termwise(self, PwordOp: "PauliwordOp") -> np.ndarray:
+        """base.py:985-1009: bool[self.n_terms, PwordOp.n_terms], True where the two terms carry the same Pauli on
+        every qubit on which both are non-trivial (one kernel over all pairs instead of a loop over terms)."""
+        assert (self.n_qubits == PwordOp.n_qubits), 'Pauliwords defined for different number of qubits'
+        return ops.commute_qwc(self._xz, PwordOp._xz).cpu().numpy()
+
+    @property
+    def adjacency_matrix_qwc(self) -> np.ndarray:
+        """base.py:1064-1072."""
+        if 'adjacency_matrix_qwc' not in self._cache:
+            self._cache['adjacency_matrix_qwc'] = self.qubitwise_commutes_termwise(self)
+        return self._cache['adjacency_matrix_qwc']
+
+    def get_graph(self, edge_relation: Optional[str] = 'C', label_nodes: Optional[bool] = False):
+        """base.py:1206-1250: networkx graph of the commuting (C), anticommuting (AC) or qubit-wise commuting (QWC)
+        relation; the adjacency matrix comes from the device kernels, the graph itself is host data."""
+        import networkx as nx
+        if edge_relation == 'AC':
+            adjmat = ~self.adjacency_matrix.copy()
+        elif edge_relation == 'C':
+            adjmat = self.adjacency_matrix.copy()
+        elif edge_relation == 'QWC':
+            adjmat = self.adjacency_matrix_qwc.copy()
+        else:
+            raise TypeError('Unrecognised edge relation, must be one of C (commuting), AC (anticommuting) or QWC (qubitwise commuting).')
+        np.fill_diagonal(adjmat, False)
+        graph = nx.from_numpy_array(adjmat)
+        if label_nodes:
+            node_list = [symplectic_to_string(row) for row in self.symp_matrix]
+            graph = nx.relabel_nodes(graph, dict(zip(range(len(node_list)), node_list)))
+        return graph
+
+    def largest_clique(self, edge_relation='C') -> "PauliwordOp":
+        """base.py:1252-1267."""
+        import networkx as nx
+        graph = self.get_graph(edge_relation=edge_relation)
+        pauli_indices = sorted(nx.find_cliques(graph), key=lambda x: -len(x))[0]
+        return sum([self[i] for i in pauli_indices])
+
+    def clique_cover(self, edge_relation='C', strategy='largest_first',
+                     colouring_interchange=False) -> Dict[int, "PauliwordOp"]:
+        """base.py:1269-1365: clique partition by greedy colouring of the complement graph, or by sorted insertion."""
+        if strategy == 'sorted_insertion':
+            if colouring_interchange is not False:
+                warnings.warn(f'{strategy} is not a graph colouring method, so colouring_interchange flag is ignored')
+            if edge_relation not in ('C', 'AC', 'QWC'):
+                raise KeyError(edge_relation)
+            ordered = self.sort(by='magnitude', key='decreasing')
+            if self.cleanup().n_terms != self.n_terms:
+                # duplicate or vanishing terms: the running sums of the reference merge/drop them, so follow it literally
+                check_dic = {
+                    'C': lambda x, y: np.all(x.commutes_termwise(y)),
+                    'AC': lambda x, y: np.all(~x.commutes_termwise(y)),
+                    'QWC': lambda x, y: np.all(x.qubitwise_commutes_termwise(y))}
+                sorted_op_list = list(ordered)
+                cliques = {0: sorted_op_list[0]}
+                for selected_op in sorted_op_list[1:]:
+                    for key in cliques.keys():
+                        if check_dic[edge_relation](selected_op, cliques[key]):
+                            cliques[key] += selected_op
+                            break
+                    else:
+                        cliques[len(cliques)] = selected_op
+                return cliques
+            # distinct non-vanishing terms: a clique's running sum is just its member list, so ONE all-pairs matrix
+            # from the device replaces a small launch per (term, clique) test
+            if edge_relation == 'QWC':
+                rel = ordered.adjacency_matrix_qwc
+            elif edge_relation == 'C':
+                rel = ordered.adjacency_matrix
+            else:
+                rel = ~ordered.adjacency_matrix
+            members: Dict[int, list] = {0: [0]}
+            for t in range(1, ordered.n_terms):
+                for key, idx in members.items():
+                    if np.all(rel[t, idx]):
+                        idx.append(t)
+                        break
+                else:
+                    members[len(members)] = [t]
+            return {key: ordered[idx] for key, idx in members.items()}
+        import networkx as nx
+        graph = self.get_graph(edge_relation=edge_relation)
+        inverted_graph = nx.complement(graph)
+        col_map = nx.greedy_color(inverted_graph, strategy=strategy, interchange=colouring_interchange)
+        cliques = {}
+        for p_index, colour in col_map.items():
+            cliques[colour] = cliques.get(colour, PauliwordOp.from_list(['I' * self.n_qubits], [0])) + self[p_index]
+        return cliques
 
     # ------------------------------------------------------------------ a8 rotations (base.py:1090-1186)
     def _rotation_step(self, Pword: "PauliwordOp", angle, threshold: float = 1e-18):
@@ -530,6 +726,31 @@ class PauliwordOp:
         return recon, mask
 
 
+    def jordan_generator_reconstruction(self, generators: "PauliwordOp"):
+        """base.py:562-602: reconstruction under the Jordan product PQ = {P,Q}/2 — the symmetry part of the
+        generators plus ONE anticommuting clique at a time, each through the device-resident
+        `generator_reconstruction`."""
+        from .utils import check_jordan_independent
+        assert check_jordan_independent(generators), 'The non-symmetry elements do not pairwise anticommute.'
+        symmetry_mask = np.all(generators.commutes_termwise(generators), axis=1)
+        if np.all(symmetry_mask):
+            return self.generator_reconstruction(generators)
+        op_reconstruction = np.zeros([self.n_terms, generators.n_terms])
+        successfully_reconstructed = np.zeros(self.n_terms, dtype=bool)
+        ac_terms = generators[~symmetry_mask]
+        gen_symp = generators.symp_matrix
+        for _, clq in ac_terms.clique_cover(edge_relation='C').items():
+            clq_indices = [np.where(np.all(gen_symp == t, axis=1))[0][0] for t in clq.symp_matrix]
+            mask_symmetries_with_P = symmetry_mask.copy()
+            mask_symmetries_with_P[np.array(clq_indices)] = True
+            augmented_symmetries = generators[mask_symmetries_with_P]
+            recon_mat_P, successful_P = self.generator_reconstruction(augmented_symmetries)
+            row, col = np.ix_(successful_P, mask_symmetries_with_P)
+            op_reconstruction[row, col] = recon_mat_P[successful_P]
+            successfully_reconstructed = np.logical_or(successfully_reconstructed, successful_P)
+        return op_reconstruction.astype(int), successfully_reconstructed
+
+
 def _i_pow(k: torch.Tensor) -> torch.Tensor:
     """i^k as complex128 for an integer device tensor (exact)."""
     lut = torch.tensor([1, 1j, -1, -1j], dtype=torch.complex128, device=k.device)
@@ -576,6 +797,58 @@ class QuantumState:
         self._state_host = None
         return self
 
+    @classmethod
+    def haar_random(cls, n_qubits: int, vec_type: str = 'ket') -> "QuantumState":
+        """base.py:1630-1652: first column (ket) / first row (bra) of a Haar-random unitary."""
+        from scipy.stats import unitary_group
+        if vec_type == 'ket':
+            haar_vec = (unitary_group.rvs(2 ** n_qubits)[:, 0]).reshape([-1, 1])
+        elif vec_type == 'bra':
+            haar_vec = (unitary_group.rvs(2 ** n_qubits)[0, :]).reshape([1, -1])
+        else:
+            raise ValueError(f'vector type: {vec_type} unkown')
+        return cls.from_array(haar_vec)
+
+    @classmethod
+    def random(cls, num_qubits: int, num_terms: int, vec_type: str = 'ket') -> "QuantumState":
+        """base.py:1654-1674 — same draws from the global NumPy RNG as the reference."""
+        random_state = np.random.randint(0, 2, (num_terms, num_qubits))
+        coeff_vec = (np.random.rand(num_terms) + np.random.rand(num_terms) * 1j)
+        return QuantumState(random_state, coeff_vec, vec_type=vec_type).cleanup().normalize
+
+    @classmethod
+    def zero(cls, n_qubits: int, vec_type: str = 'ket') -> "QuantumState":
+        """base.py:1676-1692: |0...0> (or <0...0|)."""
+        return QuantumState(np.zeros(n_qubits).reshape(1, -1), coeff_vector=np.array([1]), vec_type=vec_type)
+
+    @classmethod
+    def from_dictionary(cls, state_dict: Dict[str, Union[complex, Tuple[float, float]]]) -> "QuantumState":
+        """base.py:2113-2137: {'1101': a, '0110': b, ...}; (real, imag) tuples accepted."""
+        bin_strings, coeff_vector = zip(*state_dict.items())
+        coeff_vector = np.array(coeff_vector)
+        if len(coeff_vector.shape) == 2:
+            assert (coeff_vector.shape[1] == 2), 'Only tuples of size two allowed (real and imaginary components)'
+            coeff_vector = coeff_vector[:, 0] + 1j * coeff_vector[:, 1]
+        state_matrix = (np.frombuffer(''.join(bin_strings).encode('ascii'), dtype=np.uint8)
+                        .reshape(len(bin_strings), -1) - ord('0')).astype(int)
+        return cls(state_matrix, coeff_vector)
+
+    @classmethod
+    def from_array(cls, statevector: np.ndarray, threshold: float = 1e-15) -> "QuantumState":
+        """base.py:2139-2186: dense 2^N column (ket) or row (bra) vector -> sparse state."""
+        statevector = np.asarray(statevector)
+        assert (((len(statevector.shape) == 2) and (1 in statevector.shape))), 'state must be a bra (row) or ket (column) vector'
+        vec_type = 'bra' if statevector.shape[0] == 1 else 'ket'
+        statevector = statevector.reshape([-1])
+        N = np.log2(statevector.shape[0])
+        assert (N - int(N) == 0), 'the statevector dimension is not a power of 2'
+        if not np.isclose(np.linalg.norm(statevector), 1):
+            warnings.warn(f'statevector is not normalized')
+        N = int(N)
+        non_zero = np.where(abs(statevector) >= threshold)[0]
+        state_matrix = (((non_zero[:, None] & (1 << np.arange(N))[::-1])) > 0).astype(int)
+        return cls(state_matrix, statevector[non_zero], vec_type=vec_type)
+
     @property
     def state_matrix(self) -> np.ndarray:
         if self._state_host is None:
@@ -606,6 +879,86 @@ class QuantumState:
         new = self.state_op - Qstate.state_op
         return QuantumState._from_x_rows(new._xz, new._coeff_dev(), self.n_qubits, self.vec_type)
 
+    def __radd__(self, add_obj) -> "QuantumState":
+        """base.py:1748-1763: lets sum() run over a list of states."""
+        if isinstance(add_obj, Number) and add_obj == 0:
+            return self
+        return self + add_obj
+
+    def __eq__(self, Qstate: "QuantumState") -> bool:
+        """base.py:1718-1730."""
+        return self.state_op == Qstate.state_op
+
+    def sort(self, by='decreasing', key='magnitude') -> "QuantumState":
+        """base.py:1887-1908 (the result is a ket, like the reference's)."""
+        if key == 'magnitude':
+            sort_order = np.argsort(-abs(self.state_op.coeff_vec))
+        elif key == 'support':
+            sort_order = np.argsort(-np.sum(self.state_matrix, axis=1))
+        else:
+            raise ValueError('Only permitted sort key values are magnitude or support')
+        if by == 'increasing':
+            sort_order = sort_order[::-1]
+        elif by != 'decreasing':
+            raise ValueError('Only permitted sort by values are increasing or decreasing')
+        sub = self.state_op._take(np.ascontiguousarray(sort_order))
+        return QuantumState._from_x_rows(sub._xz, sub._coeff_dev(), self.n_qubits, 'ket')
+
+    def reindex(self, qubit_map: Union[List[int], Dict[int, int]]) -> "QuantumState":
+        """base.py:1910-1936: re-label qubits (device bit permutation of the packed bit strings)."""
+        src = PauliwordOp._reindex_source(self.n_qubits, qubit_map)
+        xz = ops.gather_qubits(self.state_op._xz, src, self.n_qubits)
+        return QuantumState._from_x_rows(xz, self.state_op._coeff_dev().clone(), self.n_qubits, self.vec_type)
+
+    def sectors_present(self, symmetry) -> np.ndarray:
+        """base.py:1938-1952: <psi|S|psi> for every generator S of an IndependentOp (coefficients set to one)."""
+        return np.array([single_term_expval(symmetry[i], self) for i in range(symmetry.n_terms)])
+
+    @property
+    def normalize_counts(self) -> "QuantumState":
+        """base.py:1964-1976: coefficients -> sqrt(c / sum(c)), the normalisation of sampled counts."""
+        c = self.state_op._coeff_dev()
+        return QuantumState._from_x_rows(self.state_op._xz, torch.sqrt(c / torch.sum(c)), self.n_qubits, self.vec_type)
+
+    @property
+    def to_dense_matrix(self) -> np.ndarray:
+        """base.py:2017-2023."""
+        return self.to_sparse_matrix.toarray()
+
+    def partial_trace_over_qubits(self, qubits: List[int] = []) -> np.ndarray:
+        """base.py:2025-2039: reduced density matrix after tracing out `qubits`."""
+        psi = self.to_dense_device() if 1 <= self.n_qubits <= DENSE_STATE_MAX_QUBITS else None
+        assert psi is not None, 'partial trace needs a dense state (1 <= n_qubits <= 30)'
+        psi = psi.reshape([2] * self.n_qubits)
+        qubits = list(qubits)
+        rho = torch.tensordot(psi, psi.conj(), dims=(qubits, qubits)) if qubits else torch.tensordot(psi, psi.conj(), dims=0)
+        d = 1 << (self.n_qubits - len(qubits))
+        return rho.reshape(d, d).cpu().numpy()
+
+    def get_rdm(self, qubits: List[int] = []) -> np.ndarray:
+        """base.py:2041-2054: reduced density matrix of the chosen qubits."""
+        trace_over_indices = list(set(range(self.n_qubits)).difference(set(qubits)))
+        return self.partial_trace_over_qubits(trace_over_indices)
+
+    def sample_state(self, n_samples: int, return_normalized: bool = False) -> "QuantumState":
+        """base.py:2070-2096: multinomial sampling in the computational basis (global NumPy RNG, like the reference)."""
+        if not self._is_normalized():
+            raise ValueError('should not sample state that is not normalized')
+        counter = np.random.multinomial(n_samples, np.abs(self.state_op.coeff_vec) ** 2)
+        if return_normalized:
+            counter = np.sqrt(counter / n_samples)
+        dev = self.state_op._xz.device
+        return QuantumState._from_x_rows(self.state_op._xz, torch.from_numpy(np.asarray(counter, dtype=complex)).to(dev),
+                                         self.n_qubits, self.vec_type)
+
+    def measure_state_in_computational_basis(self, P_op: PauliwordOp):
+        """base.py:2188-2212: (U|psi>, U P U^dagger) with U the H / S^dagger change of basis that maps P to Z's."""
+        assert self.vec_type == 'ket', 'cannot perform change of basis on bra'
+        U = change_of_basis_XY_to_Z(P_op)
+        Z_new = U * P_op * U.dagger
+        psi_new_basis = U * self
+        return psi_new_basis, Z_new
+
     @property
     def normalize(self) -> "QuantumState":
         c = self.state_op._coeff_dev()
@@ -614,7 +967,7 @@ class QuantumState:
 
     def _is_normalized(self) -> bool:
         """base.py:1964-1976."""
-        return bool(np.isclose(np.sum(abs(self.state_op.coeff_vec) ** 2), 1))
+        return bool(np.isclose(np.linalg.norm(self.state_op.cleanup().coeff_vec), 1))
 
     def _bit_keys(self):
         """(sketch keys, packed X rows) used to join two states on equal bit strings."""
@@ -727,3 +1080,81 @@ def single_term_expval(P_op: PauliwordOp, psi: QuantumState) -> float:
     unit = PauliwordOp._from_device(P_op._xz, torch.ones(1, dtype=torch.complex128, device=P_op._xz.device),
                                     P_op.n_qubits)
     return unit.expval(psi)
+
+
+def _bit_table(k: int) -> np.ndarray:
+    """bool[2^k, k]: row b = the bits of b, most significant first."""
+    if k == 0:
+        return np.zeros((1, 0), dtype=bool)
+    return ((np.arange(1 << k)[:, None] >> np.arange(k - 1, -1, -1)) & 1).astype(bool)
+
+
+def _popcount64(v: np.ndarray) -> np.ndarray:
+    v = v.astype(np.uint64)
+    count = np.zeros(v.shape, dtype=np.int64)
+    while np.any(v):
+        count += (v & np.uint64(1)).astype(np.int64)
+        v = v >> np.uint64(1)
+    return count
+
+
+def get_ij_operator(i: int, j: int, n_qubits: int, binary_vec: np.ndarray = None, return_operator: bool = True):
+    """base.py:2354-2436: Pauli decomposition of |i><j|. Qubit by qubit |0><0| = (I+Z)/2, |1><1| = (I-Z)/2,
+    |0><1| = (X+iY)/2, |1><0| = (X-iY)/2, so the 2^n terms share the X row bits(i^j), the Z row runs over every
+    bit string b and the coefficient is i^(2|b&i&j| + 3|b&i&~j| + |b&j&~i|) / 2^n."""
+    if n_qubits > 30:
+        raise ValueError('Too many qubits, might run into memory limitations.')
+    b = np.arange(1 << n_qubits, dtype=np.int64)
+    k = 2 * _popcount64(b & i & j) + 3 * _popcount64(b & i & ~j) + _popcount64(b & j & ~i)
+    coeffs = np.array([1, 1j, -1, -1j])[k % 4] / 2 ** n_qubits
+    if i == j:
+        coeffs = coeffs.real
+    z_rows = _bit_table(n_qubits) if binary_vec is None else np.asarray(binary_vec, dtype=bool)
+    x_row = _bit_table(n_qubits)[i ^ j] if n_qubits else np.zeros(0, dtype=bool)
+    ij_symp_matrix = np.hstack([np.broadcast_to(x_row, z_rows.shape), z_rows])
+    if return_operator:
+        return PauliwordOp(ij_symp_matrix, coeffs)
+    return ij_symp_matrix, coeffs
+
+
+def get_PauliwordOp_projector(projector) -> PauliwordOp:
+    """base.py:2275-2351: projector onto a product of single-qubit eigenstates; 'I' leaves a qubit free, '0'/'1' fix
+    the Z basis, '+'/'-' the X basis, '*'/'%' the Y basis. Each fixed qubit contributes (I +- P)/2, so the 2^k terms
+    run over the subsets of fixed qubits with sign (-1)^(number of chosen qubits fixed to the -1 eigenstate)."""
+    projector = np.array(list(projector)) if isinstance(projector, str) else np.asarray(projector)
+    eigen_bit = {'I': 1, '0': 0, '1': 1, '+': 0, '-': 1, '*': 0, '%': 1}
+    assert len(projector.shape) == 1, 'projector can only be defined over a single string or single list of strings (each a single letter)'
+    assert set(projector).issubset(list(eigen_bit.keys())), 'unknown qubit state (must be I,X,Y,Z basis)'
+    n_qubits = len(projector)
+    fixed = np.where(projector != 'I')[0]
+    k = len(fixed)
+    chosen = _bit_table(k)                                                     # subset of fixed qubits in each term
+    minus = np.array([eigen_bit[projector[q]] for q in fixed], dtype=np.int64)
+    sign = 1 - 2 * ((chosen.astype(np.int64) @ minus) % 2) if k else np.ones(1, dtype=np.int64)
+    symp = np.zeros((1 << k, 2 * n_qubits), dtype=bool)
+    in_x = np.isin(projector[fixed], ['+', '-', '*', '%'])                     # X or Y carries an X bit
+    in_z = np.isin(projector[fixed], ['0', '1', '*', '%'])                     # Z or Y carries a Z bit
+    symp[:, fixed[in_x]] = chosen[:, in_x]
+    symp[:, fixed[in_z] + n_qubits] = chosen[:, in_z]
+    return PauliwordOp(symp, sign / 2 ** k)
+
+
+def change_of_basis_XY_to_Z(P_op: PauliwordOp) -> PauliwordOp:
+    """base.py:2474-2537: U with U P U^dagger diagonal: S^dagger = ((1-i) I + (1+i) Z)/2 on every Y of P, then a
+    Hadamard H = (X+Z)/sqrt(2) on every X or Y. Both factors are expanded over the subsets of their qubits and
+    multiplied on the device."""
+    n = P_op.n_qubits
+    x_row, z_row = P_op.X_block[0], P_op.Z_block[0]
+    y_pos = np.flatnonzero(x_row & z_row)
+    h_pos = np.flatnonzero(x_row)                                              # X or Y
+    picks = _bit_table(len(y_pos))
+    symp = np.zeros((picks.shape[0], 2 * n), dtype=bool)
+    symp[:, n + y_pos] = picks
+    n_z = picks.sum(axis=1)
+    s_dag_op = PauliwordOp(symp, ((1 - 1j) ** (len(y_pos) - n_z) * (1 + 1j) ** n_z) / 2 ** len(y_pos))
+    picks = _bit_table(len(h_pos))
+    symp = np.zeros((picks.shape[0], 2 * n), dtype=bool)
+    symp[:, h_pos] = picks
+    symp[:, n + h_pos] = ~picks
+    hadamards = PauliwordOp(symp, np.full(picks.shape[0], (1 / np.sqrt(2)) ** len(h_pos)))
+    return hadamards * s_dag_op

@@ -119,6 +119,93 @@ static int commute_launch(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz,
     return SYM_OK;
 }
 
+
+// qubitwise_commutes_termwise (base.py:985-1009): A[i] and B[j] commute qubit by qubit iff on every qubit
+// where both act non-trivially they carry the same Pauli, i.e. no bit survives
+//   (xa | za) & (xb | zb) & ((xa ^ xb) | (za ^ zb)).
+// Same decomposition as commute_kernel: thread = one B row in registers, CTA = 64 A rows in shared memory.
+template <int WT>
+__global__ void __launch_bounds__(COM_THREADS) qwc_kernel(const uint64_t *__restrict__ a_xz, uint32_t M,
+                                                           const uint64_t *__restrict__ b_xz, uint32_t N, int W,
+                                                           uint8_t *__restrict__ out) {
+    __shared__ ulonglong2 sa[COM_ICH][WT];   // (x_w, z_w) of the A rows
+    const uint32_t i0 = blockIdx.y * COM_ICH;
+    const uint32_t ni = min((uint32_t)COM_ICH, M - i0);
+    for (int i = threadIdx.x; i < COM_ICH * WT; i += COM_THREADS) {
+        int ii = i / WT, w = i % WT;
+        ulonglong2 v = make_ulonglong2(0ull, 0ull);
+        if ((uint32_t)ii < ni && w < W) {
+            const uint64_t *row = a_xz + (size_t)(i0 + ii) * 2 * W;
+            v.x = row[w];
+            v.y = row[W + w];
+        }
+        sa[ii][w] = v;
+    }
+    const uint32_t j = blockIdx.x * COM_THREADS + threadIdx.x;
+    const bool active = j < N;
+    uint64_t xb[WT], zb[WT];
+#pragma unroll
+    for (int w = 0; w < WT; ++w) {
+        xb[w] = (active && w < W) ? b_xz[(size_t)j * 2 * W + w] : 0ull;
+        zb[w] = (active && w < W) ? b_xz[(size_t)j * 2 * W + W + w] : 0ull;
+    }
+    __syncthreads();
+    for (uint32_t ii = 0; ii < ni; ++ii) {
+        uint64_t clash = 0;
+#pragma unroll
+        for (int w = 0; w < WT; ++w) {
+            const ulonglong2 a = sa[ii][w];
+            clash |= (a.x | a.y) & (xb[w] | zb[w]) & ((a.x ^ xb[w]) | (a.y ^ zb[w]));
+        }
+        if (active) out[(size_t)(i0 + ii) * N + j] = clash == 0 ? (uint8_t)1 : (uint8_t)0;
+    }
+}
+
+__global__ void __launch_bounds__(256) qwc_generic_kernel(const uint64_t *__restrict__ a_xz, uint32_t M,
+                                                           const uint64_t *__restrict__ b_xz, uint32_t N, int W,
+                                                           uint8_t *__restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.y;
+    if (j >= N) return;
+    const uint64_t *ra = a_xz + (size_t)i * 2 * W, *rb = b_xz + (size_t)j * 2 * W;
+    uint64_t clash = 0;
+    for (int w = 0; w < W; ++w) {
+        const uint64_t xa = ra[w], za = ra[W + w], xb = rb[w], zb = rb[W + w];
+        clash |= (xa | za) & (xb | zb) & ((xa ^ xb) | (za ^ zb));
+    }
+    out[(size_t)i * N + j] = clash == 0 ? (uint8_t)1 : (uint8_t)0;
+}
+
+static int qwc_launch(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int W, uint8_t *out,
+                      cudaStream_t st) {
+    if (M == 0 || N == 0) return SYM_OK;
+    int64_t done = 0;
+    while (done < M) {
+        int64_t rows = M - done;
+        const uint64_t *a = a_xz + (size_t)done * 2 * W;
+        uint8_t *o = out + (size_t)done * N;
+        if (W <= 16) {
+            const int64_t max_rows = (int64_t)65535 * COM_ICH;   // grid.y limit
+            if (rows > max_rows) rows = max_rows;
+            dim3 grid((unsigned)((N + COM_THREADS - 1) / COM_THREADS), (unsigned)((rows + COM_ICH - 1) / COM_ICH));
+#define QWC_CASE(WT) qwc_kernel<WT><<<grid, COM_THREADS, 0, st>>>(a, (uint32_t)rows, b_xz, (uint32_t)N, W, o)
+            if (W <= 1) QWC_CASE(1);
+            else if (W <= 2) QWC_CASE(2);
+            else if (W <= 4) QWC_CASE(4);
+            else if (W <= 8) QWC_CASE(8);
+            else QWC_CASE(16);
+#undef QWC_CASE
+        } else {
+            if (rows > 65535) rows = 65535;
+            dim3 grid((unsigned)((N + 255) / 256), (unsigned)rows);
+            qwc_generic_kernel<<<grid, 256, 0, st>>>(a, (uint32_t)rows, b_xz, (uint32_t)N, W, o);
+        }
+        SYM_LAUNCH_OK();
+        done += rows;
+    }
+    return SYM_OK;
+}
+
 }  // namespace symb
 
 using namespace symb;
@@ -135,4 +222,11 @@ extern "C" int sym_commute_bits(const uint64_t *a_xz, int64_t M, const uint64_t 
     SYM_REQUIRE(M >= 0 && N >= 0 && W >= 1, "bad size");
     SYM_REQUIRE(M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31), "operand too large");
     return commute_launch<true>(a_xz, M, b_xz, N, W, nullptr, out_bits, (cudaStream_t)stream);
+}
+
+extern "C" int sym_commute_qwc(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W, uint8_t *out,
+                               void *stream) {
+    SYM_REQUIRE(M >= 0 && N >= 0 && W >= 1, "bad size");
+    SYM_REQUIRE(M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31), "operand too large");
+    return qwc_launch(a_xz, M, b_xz, N, W, out, (cudaStream_t)stream);
 }

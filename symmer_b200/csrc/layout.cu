@@ -121,6 +121,28 @@ __global__ void unpack_matrix_kernel(const uint64_t *__restrict__ bits, int64_t 
 
 using namespace symb;
 
+// Qubit gather: bit k of the output X (Z) block = bit src[k] of the input X (Z) block, 0 where src[k] < 0.
+// Serves PauliwordOp.reindex (base.py:493-521: a permutation) and PauliwordOp.tensor (base.py:1188-1204:
+// each factor embedded into the wider register before the product). thread = (row, output word).
+__global__ void __launch_bounds__(256) gather_qubits_kernel(const uint64_t *__restrict__ xz, int64_t M, int W_in,
+                                                             const int32_t *__restrict__ src, int n_out, int W_out,
+                                                             uint64_t *__restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = g / (2 * W_out);
+    if (row >= M) return;
+    const int w = (int)(g - row * (2 * W_out));
+    const int blk = w / W_out, wo = w - blk * W_out;   // blk 0 = X, 1 = Z
+    const uint64_t *in = xz + (size_t)row * 2 * W_in + (size_t)blk * W_in;
+    uint64_t v = 0;
+    const int k0 = wo * 64;
+    const int k1 = min(k0 + 64, n_out);
+    for (int k = k0; k < k1; ++k) {
+        const int q = src[k];
+        if (q >= 0) v |= ((in[q >> 6] >> (q & 63)) & 1ull) << (k - k0);
+    }
+    out[g] = v;
+}
+
 static inline unsigned blocks_for(int64_t threads, int per_block) {
     int64_t b = (threads + per_block - 1) / per_block;
     return (unsigned)(b < 1 ? 1 : b);
@@ -213,6 +235,17 @@ extern "C" int sym_unpack_matrix(const uint64_t *bits, int64_t R, int64_t C, int
     SYM_REQUIRE(R >= 0 && C >= 0 && Cw * 64 >= C, "bad matrix shape");
     if (R == 0 || C == 0) return SYM_OK;
     unpack_matrix_kernel<<<blocks_for(R * C, 256), 256, 0, (cudaStream_t)stream>>>(bits, R, C, Cw, m);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_gather_qubits(const uint64_t *xz, int64_t M, int32_t W_in, const int32_t *src, int32_t n_out,
+                                 uint64_t *out_xz, void *stream) {
+    SYM_REQUIRE(M >= 0 && W_in >= 1 && n_out >= 0, "bad size");
+    if (M == 0) return SYM_OK;
+    const int W_out = n_out > 0 ? (n_out + 63) / 64 : 1;
+    gather_qubits_kernel<<<blocks_for(M * 2 * (int64_t)W_out, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, W_in, src, n_out,
+                                                                                                    W_out, out_xz);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }

@@ -7,6 +7,8 @@ There is no CPU path: without a CUDA device these raise.
 import ctypes
 import math
 
+import numpy as np
+
 import torch
 
 from . import _cabi
@@ -277,6 +279,29 @@ def commute_bits(a_xz, b_xz):
     N, _ = _rows(b_xz)
     out = torch.zeros((M, (N + 31) // 32), dtype=torch.int32, device=a_xz.device)
     _cabi.check(lib().sym_commute_bits(_p(a_xz), M, _p(b_xz), N, W, _p(out), _stream()))
+    return out
+
+
+def commute_qwc(a_xz, b_xz):
+    """bool[M, N], True where A[i] and B[j] commute qubit by qubit (base.py:985-1009)."""
+    M, W = _rows(a_xz)
+    N, W2 = _rows(b_xz)
+    assert W == W2
+    out = torch.empty((M, N), dtype=torch.uint8, device=a_xz.device)
+    _cabi.check(lib().sym_commute_qwc(_p(a_xz), M, _p(b_xz), N, W, _p(out), _stream()))
+    return out.view(torch.bool)
+
+
+def gather_qubits(xz, src, n_in):
+    """Rows over len(src) qubits: output qubit k takes input qubit src[k] (identity where src[k] < 0).
+    Reindexing (a permutation) and the embedding of a tensor factor into a wider register."""
+    M, W = _rows(xz)
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    assert src.ndim == 1 and (src.size == 0 or int(src.max()) < int(n_in)), 'source qubit out of range'
+    n_out = int(src.size)
+    out = torch.empty((M, 2 * words_for(n_out)), dtype=torch.int64, device=xz.device)
+    src_dev = torch.from_numpy(src).to(xz.device)
+    _cabi.check(lib().sym_gather_qubits(_p(xz), M, W, _p(src_dev), n_out, _p(out), _stream()))
     return out
 
 

@@ -19,6 +19,7 @@ _SEAMS = {
     "_cref_binary": _u._cref_binary,                  # utils.py:337
     "cref_binary": _u.cref_binary,                    # utils.py:349
     "check_independent": _u.check_independent,        # utils.py:504
+    "check_jordan_independent": _u.check_jordan_independent,   # utils.py:521
 }
 _MODULES = ["symmer.operators.utils", "symmer.operators.base", "symmer.operators.independent_op",
             "symmer.operators.noncontextual_op", "symmer.operators.anticommuting_op"]

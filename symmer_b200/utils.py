@@ -107,6 +107,22 @@ def check_independent(operators) -> bool:
     return bool(np.all(piv >= 0))
 
 
+def check_jordan_independent(operators) -> bool:
+    """utils.py:521-565: independence under the Jordan product (anticommuting elements may not be multiplied).
+    The commutation matrix and both GF(2) reductions run on the device."""
+    if operators.n_terms > 3 * operators.n_qubits:
+        return False
+    comm_mask = np.sum(operators.commutes_termwise(operators), axis=1) == operators.n_terms
+    comm_part = operators[comm_mask]
+    if comm_part.n_terms and not check_independent(comm_part):
+        return False
+    X_block, Z_block = operators.X_block, operators.Z_block
+    Y_block = np.logical_and(Z_block, X_block)
+    XZY_block = np.hstack((np.logical_xor(X_block, Y_block), np.logical_xor(Z_block, Y_block), Y_block))
+    _, piv = _rref_device(XZY_block)
+    return bool(np.all(piv >= 0))
+
+
 def check_adjmat_noncontextual(adjmat) -> bool:
     """utils.py:567-589 — host logic on the (small) set of distinct commutation characters."""
     adjmat = np.asarray(adjmat, dtype=bool)

@@ -1,0 +1,291 @@
+"""Assertions on the public API either side of the hot path, against vectors produced by the REAL reference
+(tests/golden/make_golden_api.py -> tests/golden/api_vectors.npz). Each case takes the golden dictionary and runs
+through `symmer_b200`'s reference-facing classes; `tests/test_gpu_api_ext.py` runs them on the CUDA kernels
+(`-m gpu`), `tests/test_host_logic.py` runs the same cases on the CPU box with the kernels swapped for the
+NumPy test double (host logic only)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import pauli_oracle as po  # noqa: E402
+
+
+def load_api_golden():
+    data = np.load(os.path.join(ROOT, "tests", "golden", "api_vectors.npz"))
+    cases = {}
+    for key in data.files:
+        name, field = key.split("/", 1)
+        cases.setdefault(name, {})[field] = data[key]
+    return cases
+
+
+def _same_terms(symp_a, coeff_a, symp_b, coeff_b, scale=1.0):
+    ok, why = po.compare_term_sets(symp_a, coeff_a, symp_b, coeff_b, scale=scale)
+    assert ok, why
+
+
+def _same_state(state, ref_matrix, ref_coeff):
+    """Equal bit strings with equal amplitudes, order ignored."""
+    got = {tuple(r): c for r, c in zip(np.asarray(state.state_matrix).tolist(), state.state_op.coeff_vec)}
+    want = {tuple(r): c for r, c in zip(np.asarray(ref_matrix).tolist(), ref_coeff)}
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-12 * max(1.0, abs(want[k])), (k, got[k], want[k])
+
+
+def _qmap(g):
+    vals = [int(v) for v in g["vals"]]
+    if bool(g["is_dict"][0]):
+        return dict(zip([int(k) for k in g["keys"]], vals))
+    return vals
+
+
+# ------------------------------------------------------------------------------------------------ cases
+def case_qwc(api, G):
+    from symmer_b200 import PauliwordOp
+    names = [n for n in G if n.startswith("qwc_")]
+    assert len(names) >= 6
+    for name in names:
+        g = G[name]
+        A = PauliwordOp(g["a_symp"], np.ones(g["a_symp"].shape[0]))
+        B = PauliwordOp(g["b_symp"], np.ones(g["b_symp"].shape[0]))
+        got = A.qubitwise_commutes_termwise(B)
+        assert got.dtype == bool and np.array_equal(got, g["out"]), name
+        assert np.array_equal(A.adjacency_matrix_qwc, g["adj"]), name
+        assert np.array_equal(po.qubitwise_commutes_termwise(g["a_symp"], g["b_symp"]), g["out"]), name
+
+
+def case_reindex(api, G):
+    from symmer_b200 import PauliwordOp
+    names = [n for n in G if n.startswith("reindex_")]
+    assert len(names) >= 5
+    for name in names:
+        g = G[name]
+        P = PauliwordOp(g["symp"], g["coeff"])
+        R = P.reindex(_qmap(g))
+        assert np.array_equal(R.symp_matrix, g["out_symp"]), name           # no dedup, order kept
+        assert np.array_equal(R.coeff_vec, g["out_coeff"]), name
+        assert np.array_equal(po.reindex(g["symp"], _qmap(g)), g["out_symp"]), name
+    P = PauliwordOp.from_list(['XYZ'])
+    for bad in ([0, 0, 1], {0: 1}):
+        try:
+            P.reindex(bad)
+        except AssertionError:
+            continue
+        raise AssertionError(f"reindex({bad}) must be rejected like the reference (base.py:511-512)")
+
+
+def case_tensor(api, G):
+    from symmer_b200 import PauliwordOp
+    names = [n for n in G if n.startswith("tensor_")]
+    assert len(names) >= 4
+    for name in names:
+        g = G[name]
+        L = PauliwordOp(g["a_symp"], g["a_coeff"])
+        R = PauliwordOp(g["b_symp"], g["b_coeff"])
+        T = L.tensor(R)
+        assert T.n_qubits == L.n_qubits + R.n_qubits
+        _same_terms(T.symp_matrix, T.coeff_vec, g["out_symp"], g["out_coeff"])
+        s, c = po.tensor(g["a_symp"], g["a_coeff"], g["b_symp"], g["b_coeff"])
+        _same_terms(s, c, g["out_symp"], g["out_coeff"])
+
+
+def case_graphs(api, G):
+    import networkx as nx
+    from symmer_b200 import PauliwordOp
+    H = PauliwordOp(G["graph_op"]["symp"], G["graph_op"]["coeff"])
+    for rel in ['C', 'AC', 'QWC']:
+        adj = nx.to_numpy_array(H.get_graph(edge_relation=rel), dtype=bool)
+        assert np.array_equal(adj, G[f"graph_{rel}"]["adj"]), rel
+        big = H.largest_clique(edge_relation=rel)
+        g = G[f"largest_clique_{rel}"]
+        _same_terms(big.symp_matrix, big.coeff_vec, g["symp"], g["coeff"])
+        for strategy in ['largest_first', 'sorted_insertion', 'DSATUR']:
+            g = G[f"clique_cover_{rel}_{strategy}"]
+            cover = H.clique_cover(edge_relation=rel, strategy=strategy)
+            assert sorted(cover.keys()) == [int(k) for k in g["keys"]], (rel, strategy)
+            lo = 0
+            for key, size in zip(g["keys"], g["sizes"]):
+                clq = cover[int(key)]
+                _same_terms(clq.symp_matrix, clq.coeff_vec, g["symp"][lo:lo + size], g["coeff"][lo:lo + size])
+                lo += int(size)
+    labelled = H.get_graph(edge_relation='C', label_nodes=True)
+    assert set(labelled.nodes) == set(po.to_strings(H.symp_matrix))
+    try:
+        H.get_graph(edge_relation='nope')
+    except TypeError:
+        pass
+    else:
+        raise AssertionError("unknown edge relation must raise TypeError (base.py:1241)")
+    # duplicate terms: the sorted-insertion cover follows the reference's running sums literally
+    D = PauliwordOp.from_list(['XX', 'ZZ', 'XX', 'YI'], [1, 2, 3, 0.5])
+    cover = D.clique_cover(strategy='sorted_insertion')
+    total = sum(cover.values())
+    assert total == D.cleanup()
+
+
+def case_jordan(api, G):
+    from symmer_b200 import PauliwordOp
+    from symmer_b200.utils import check_jordan_independent
+    for name in ["jordan_small", "jordan_symmetric", "jordan_ref_test"]:
+        g = G[name]
+        gens = PauliwordOp(g["gen_symp"], np.ones(g["gen_symp"].shape[0]))
+        op = PauliwordOp(g["op_symp"], np.ones(g["op_symp"].shape[0]))
+        recon, ok = op.jordan_generator_reconstruction(gens)
+        assert np.array_equal(ok, g["ok"]), name
+        assert np.array_equal(recon[ok], g["recon"][g["ok"]]), name
+        assert recon.dtype.kind == 'i'
+    names = [n for n in G if n.startswith("jordan_indep_")]
+    assert len(names) == 5
+    for name in names:
+        g = G[name]
+        op = PauliwordOp(g["symp"], np.ones(g["symp"].shape[0]))
+        assert bool(check_jordan_independent(op)) == bool(g["out"][0]), name
+
+
+def case_quantum_state_constructors(api, G):
+    from symmer_b200 import QuantumState
+    g = G["qs_random"]
+    np.random.seed(int(g["seed"][0]))
+    psi = QuantumState.random(int(g["n_qubits"][0]), int(g["n_terms"][0]))
+    _same_state(psi, g["state"], g["coeff"])
+    assert psi.vec_type == 'ket' and psi._is_normalized()
+    z = QuantumState.zero(5)
+    _same_state(z, G["qs_zero"]["state"], G["qs_zero"]["coeff"])
+    assert QuantumState.zero(3, vec_type='bra').vec_type == 'bra'
+    g = G["qs_from_dictionary"]
+    s = QuantumState.from_dictionary(dict(zip([str(k) for k in g["keys"]], g["vals"])))
+    assert np.array_equal(s.state_matrix, g["state"]) and np.allclose(s.state_op.coeff_vec, g["coeff"], rtol=1e-15, atol=0)
+    s = QuantumState.from_dictionary({'10': (0.6, 0.0), '01': (0.0, 0.8)})
+    assert np.allclose(s.state_op.coeff_vec, [0.6, 0.8j])
+    for kind in ['ket', 'bra']:
+        g = G[f"qs_from_array_{kind}"]
+        s = QuantumState.from_array(g["vec"])
+        assert s.vec_type == kind == str(g["vec_type"][0])
+        assert np.array_equal(s.state_matrix, g["state"]) and np.array_equal(s.state_op.coeff_vec, g["coeff"])
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        QuantumState.from_array(np.array([[1.0], [1.0]]))
+        assert any('not normalized' in str(w.message) for w in caught)
+    for bad in (np.ones(4), np.ones((3, 1))):
+        try:
+            QuantumState.from_array(bad)
+        except AssertionError:
+            continue
+        raise AssertionError("from_array must reject non-vectors and non power-of-two sizes")
+    np.random.seed(3)
+    h = QuantumState.haar_random(3)
+    assert h.n_qubits == 3 and h._is_normalized() and h.vec_type == 'ket'
+    assert QuantumState.haar_random(2, vec_type='bra').vec_type == 'bra'
+
+
+def case_quantum_state_methods(api, G):
+    from symmer_b200 import IndependentOp, PauliwordOp, QuantumState
+    base = G["qs_base"]
+    psi = QuantumState(base["state"], base["coeff"])
+    for key in ['magnitude', 'support']:
+        for by in ['decreasing', 'increasing']:
+            g = G[f"qs_sort_{key}_{by}"]
+            s = psi.sort(by=by, key=key)
+            assert np.array_equal(s.state_matrix, g["state"]), (key, by)
+            assert np.array_equal(s.state_op.coeff_vec, g["coeff"]), (key, by)
+    for bad in (dict(key='nope'), dict(by='sideways')):
+        try:
+            psi.sort(**bad)
+        except ValueError:
+            continue
+        raise AssertionError("sort must reject unknown keys / orders (base.py:1902-1907)")
+    for i in range(2):
+        g = G[f"qs_reindex_{i}"]
+        s = psi.reindex(_qmap(g))
+        assert np.array_equal(s.state_matrix, g["state"]) and np.array_equal(s.state_op.coeff_vec, g["coeff"])
+    g = G["qs_normalize_counts"]
+    s = QuantumState(base["state"], g["in_coeff"]).normalize_counts
+    assert np.allclose(s.state_op.coeff_vec, g["coeff"], rtol=1e-14, atol=0)
+    assert np.allclose(psi.to_dense_matrix, G["qs_dense"]["dense"], rtol=1e-15, atol=0)
+    assert psi.to_dense_matrix.shape == (32, 1)
+    for i in range(4):
+        g = G[f"qs_ptrace_{i}"]
+        rho = psi.partial_trace_over_qubits([int(q) for q in g["qubits"]])
+        assert rho.shape == g["rho"].shape and np.allclose(rho, g["rho"], rtol=1e-12, atol=1e-15), i
+        g = G[f"qs_rdm_{i}"]
+        rho = psi.get_rdm([int(q) for q in g["qubits"]])
+        assert rho.shape == g["rho"].shape and np.allclose(rho, g["rho"], rtol=1e-12, atol=1e-15), i
+    for name, norm in [("qs_sample", False), ("qs_sample_norm", True)]:
+        g = G[name]
+        np.random.seed(int(g["seed"][0]))
+        s = psi.sample_state(int(g["n_samples"][0]), return_normalized=norm)
+        assert np.array_equal(s.state_matrix, g["state"]) and np.allclose(s.state_op.coeff_vec, g["coeff"], rtol=1e-15)
+    try:
+        QuantumState(base["state"], 2 * base["coeff"]).sample_state(10)
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("sampling an unnormalised state must raise (base.py:2082-2083)")
+    g = G["qs_sectors"]
+    S = IndependentOp(g["sym_symp"], np.ones(g["sym_symp"].shape[0]))
+    assert np.allclose(psi.sectors_present(S), g["out"], rtol=1e-12, atol=1e-14)
+    for i in range(3):
+        g = G[f"qs_measure_{i}"]
+        Pm = PauliwordOp(g["p_symp"], [1])
+        new_psi, Znew = psi.measure_state_in_computational_basis(Pm)
+        _same_state(new_psi, g["state"], g["coeff"])
+        _same_terms(Znew.symp_matrix, Znew.coeff_vec, g["z_symp"], g["z_coeff"])
+        assert not np.any(Znew.X_block)
+    assert (psi == QuantumState(base["state"][::-1].copy(), base["coeff"][::-1].copy())) is bool(G["qs_eq"]["same"][0])
+    assert (psi == QuantumState(base["state"], base["coeff"][::-1].copy())) is bool(G["qs_eq"]["different"][0])
+    assert sum([psi, psi]) == QuantumState(base["state"], 2 * base["coeff"])
+
+
+def case_projector_helpers(api, G):
+    from symmer_b200 import change_of_basis_XY_to_Z, get_ij_operator, get_PauliwordOp_projector, PauliwordOp
+    for i in range(5):
+        g = G[f"ij_{i}"]
+        a, b, n = [int(v) for v in g["ijn"]]
+        op = get_ij_operator(a, b, n)
+        _same_terms(op.symp_matrix, op.coeff_vec, g["symp"], g["coeff"])
+        symp, coeff = get_ij_operator(a, b, n, return_operator=False)
+        assert np.array_equal(symp, g["symp"]) and np.allclose(coeff, g["coeff"], rtol=1e-15, atol=0)
+        dense = np.zeros((1 << n, 1 << n), dtype=complex)
+        dense[a, b] = 1
+        assert np.allclose(op.to_sparse_matrix.toarray(), dense, atol=1e-15)
+    for i in range(5):
+        g = G[f"projector_{i}"]
+        op = get_PauliwordOp_projector(str(g["label"][0]))
+        _same_terms(op.symp_matrix, op.coeff_vec, g["symp"], g["coeff"])
+    assert get_PauliwordOp_projector(list('0+')) == get_PauliwordOp_projector('0+')
+    for i in range(3):
+        g = G[f"change_basis_{i}"]
+        Pm = PauliwordOp(g["p_symp"], [1])
+        U = change_of_basis_XY_to_Z(Pm)
+        _same_terms(U.symp_matrix, U.coeff_vec, g["symp"], g["coeff"])
+
+
+def case_misc_methods(api, G):
+    from symmer_b200 import PauliwordOp
+    P = PauliwordOp.from_list(['XX', 'ZY', 'II'], [1, 2j, -0.5])
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        P.set_processing_method('single_thread')
+        assert not caught
+        P.set_processing_method('ray')
+        assert len(caught) == 1
+    df = P.to_dataframe()
+    assert list(df['Pauli terms']) == ['XX', 'ZY', 'II']
+    assert np.allclose(df['Coefficients (real)'], [1, 0, -0.5]) and np.allclose(df['Coefficients (imaginary)'], [0, 2, 0])
+    assert 'Coefficients (imaginary)' not in PauliwordOp.from_list(['XZ'], [2]).to_dataframe().columns
+    for attr in ['to_openfermion', 'to_qiskit']:
+        try:
+            getattr(P, attr)
+        except ImportError:
+            pass
+
+
+CASES = [case_qwc, case_reindex, case_tensor, case_graphs, case_jordan, case_quantum_state_constructors,
+         case_quantum_state_methods, case_projector_helpers, case_misc_methods]
