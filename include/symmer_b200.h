@@ -213,6 +213,20 @@ int sym_to_csr(const int64_t *z_masks, const double *c_phased, int64_t M, int32_
                const int64_t *x_groups, int64_t G, const int32_t *group_start, double *data,
                int64_t *indices, int64_t *indptr, void *stream);
 
+/* ---- inverse of a9: PauliwordOp.from_matrix (base.py:238-425), get_ij_operator (base.py:2354-2436).
+ * Pauli decomposition by Walsh-Hadamard transforms of the XOR-diagonals d_x[r] = M[r, r^x] (basis index r
+ * with qubit 0 = most significant bit):  c'_{x,z} = 2^-n sum_r (-1)^{popcount(r & z)} M[r, r^x], and the
+ * coefficient of the Pauli with masks (x, z) is c' * i^{popcount(x & z)}.
+ * sym_pauli_decompose_dense: matrix = complex128[2^n][2^n] row-major (n_qubits <= 15), out[x][z] = c'.
+ * sym_pauli_decompose_diagonals: diag = complex128[K][2^n], the K populated diagonals of a sparse matrix,
+ *   transformed in place (diag[k][z] = c' for the k-th x).
+ * sym_rows_from_masks: inverse of sym_term_masks — masks + c' -> packed single-word rows and coefficients
+ *   with the i^{popcount(x&z)} factor applied (1 <= n_qubits <= 62). */
+int sym_pauli_decompose_dense(const double *matrix, int32_t n_qubits, double *out, void *stream);
+int sym_pauli_decompose_diagonals(double *diag, int64_t K, int32_t n_qubits, void *stream);
+int sym_rows_from_masks(const int64_t *x_masks, const int64_t *z_masks, const double *c_phased, int64_t M,
+                        int32_t n_qubits, uint64_t *xz, double *c, void *stream);
+
 /* ---- a11 GF(2): _rref_binary (utils.py:292-315), row-driven pivot rule, no row swaps.
  * bits: uint64[R][Cw] bit-packed rows (column j = bit j%64 of word j/64), reduced in place.
  * pivots: device int32[R], pivot column of each row after reduction or -1 for a zero row. */

@@ -55,6 +55,9 @@ SIGNATURES = {
     "sym_expval": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_p, c_i64, c_i64, c_i32, c_p]),
     "sym_expval_prepare_sym": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p]),
     "sym_to_csr": (ctypes.c_int, [c_p, c_p, c_i64, c_i32, c_p, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    "sym_pauli_decompose_dense": (ctypes.c_int, [c_p, c_i32, c_p, c_p]),
+    "sym_pauli_decompose_diagonals": (ctypes.c_int, [c_p, c_i64, c_i32, c_p]),
+    "sym_rows_from_masks": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_p, c_p]),
     "sym_rref_ws_bytes": (c_sz, [c_i64]),
     "sym_rref": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
     "sym_bit_transpose": (ctypes.c_int, [c_p, c_i64, c_i64, c_p, c_i64, c_p]),

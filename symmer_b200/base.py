@@ -173,6 +173,95 @@ class PauliwordOp:
         """base.py:223-236: 0 * I...I."""
         return cls.from_dictionary({'I' * n_qubits: 0})
 
+    # ------------------------------------------------------------------ matrix -> operator (base.py:238-425)
+    @classmethod
+    def from_matrix(cls, matrix, operator_basis: "PauliwordOp" = None, strategy: str = 'projector',
+                    disable_loading_bar: Optional[bool] = False) -> "PauliwordOp":
+        """base.py:366-425. Both reference strategies ('projector': a |i><j| expansion per matrix entry, 'full_basis':
+        a trace against every one of the 4^n Paulis) compute the same coefficients; here they are ONE
+        Walsh-Hadamard transform per populated XOR-diagonal of the matrix on the device
+        (`sym_pauli_decompose_*`, the inverse of `to_sparse_matrix`). Terms come out ordered by their [X|Z] bit
+        string like the reference's, exact zeros dropped; with `operator_basis` only those terms are evaluated."""
+        from scipy.sparse import issparse
+        if isinstance(matrix, np.matrix):
+            matrix = np.array(matrix)
+        n_qubits = int(np.ceil(np.log2(max(matrix.shape))))
+        if n_qubits > 30 and operator_basis is None:
+            raise ValueError('Matrix too large! Will run into memory limitations.')
+        if operator_basis is None and strategy not in ('full_basis', 'projector'):
+            raise ValueError('Unrecognised strategy, must be one of full_basis or projector')
+        if not (issparse(matrix) or isinstance(matrix, np.ndarray)):
+            raise ValueError('Unrecognised matrix type, must be one of np.array or sp.sparse.csr_matrix')
+        side = 1 << n_qubits
+        dev = ops.device()
+        basis = None
+        if operator_basis is not None:
+            basis = operator_basis.copy().cleanup()
+            assert basis.n_qubits == n_qubits, 'operator basis defined over a different number of qubits'
+        if n_qubits == 0:
+            value = complex(matrix[0, 0])
+            return cls(np.zeros((1 if value != 0 else 0, 0), dtype=bool), [value] if value != 0 else [])
+        if basis is None and isinstance(matrix, np.ndarray) and n_qubits <= 12:
+            # dense matrix: the kernel gathers every diagonal itself
+            padded = np.zeros((side, side), dtype=complex)
+            padded[:matrix.shape[0], :matrix.shape[1]] = matrix
+            table = ops.pauli_decompose_dense(torch.from_numpy(padded).to(dev), n_qubits)
+            xs = torch.arange(side, dtype=torch.int64, device=dev)
+        else:
+            if issparse(matrix):
+                coo = matrix.tocoo()
+                rows, cols, vals = coo.row.astype(np.int64), coo.col.astype(np.int64), coo.data.astype(complex)
+            else:
+                rows, cols = np.nonzero(matrix)
+                vals = np.asarray(matrix[rows, cols], dtype=complex)
+            offsets = rows ^ cols
+            if basis is not None:
+                wanted = np.unique(_unsorted_masks(basis)[0].cpu().numpy())
+                keep = np.isin(offsets, wanted)
+                rows, vals, offsets = rows[keep], vals[keep], offsets[keep]
+                xs_host, which = wanted, np.searchsorted(wanted, offsets)
+            else:
+                xs_host, which = np.unique(offsets, return_inverse=True)
+            table = torch.zeros((len(xs_host), side), dtype=torch.complex128, device=dev)
+            if len(rows):
+                flat = torch.view_as_real(table).reshape(-1, 2)
+                slot = torch.from_numpy(np.asarray(which, dtype=np.int64) * side + rows).to(dev)
+                v = torch.from_numpy(vals).to(dev)
+                flat[:, 0].index_add_(0, slot, v.real.contiguous())
+                flat[:, 1].index_add_(0, slot, v.imag.contiguous())
+            ops.pauli_decompose_diagonals(table, n_qubits)
+            xs = torch.from_numpy(np.asarray(xs_host, dtype=np.int64)).to(dev)
+        if basis is None:
+            k, z = torch.nonzero(table != 0, as_tuple=True)          # row-major: ascending (x, z) like the reference
+            xz, c = ops.rows_from_masks(xs[k], z, table[k, z], n_qubits)
+            return cls._from_device(xz, c, n_qubits)
+        warnings.warn('Basis supplied MAY not be sufficiently expressive, output operator projected onto basis supplied.')
+        xm, zm, _ = _unsorted_masks(basis)
+        k = torch.searchsorted(xs, xm)
+        coeffs = table[k, zm] * _i_pow(ops.ycount(basis._xz).to(torch.int64))
+        out = cls._from_device(basis._xz, coeffs, n_qubits)
+        return out[np.flatnonzero(out.coeff_vec)]
+
+    @classmethod
+    def _from_matrix_full_basis(cls, matrix, n_qubits: int, operator_basis: "PauliwordOp" = None,
+                                disable_loading_bar: Optional[bool] = False) -> "PauliwordOp":
+        """base.py:238-284 (same device decomposition as `from_matrix`)."""
+        return cls.from_matrix(matrix, operator_basis=operator_basis, strategy='full_basis')
+
+    @classmethod
+    def _from_matrix_projector(cls, matrix, n_qubits: int, disable_loading_bar: Optional[bool] = False) -> "PauliwordOp":
+        """base.py:286-363 (same device decomposition as `from_matrix`)."""
+        assert n_qubits <= 32, 'cannot decompose matrices above 32 qubits'
+        return cls.from_matrix(matrix, strategy='projector')
+
+    @classmethod
+    def haar_random(cls, n_qubits: int, strategy: Optional[str] = 'projector',
+                    disable_loading_bar: Optional[bool] = False) -> "PauliwordOp":
+        """base.py:109-126: Pauli decomposition of a Haar-random unitary."""
+        from scipy.stats import unitary_group
+        haar_matrix = unitary_group.rvs(2 ** n_qubits) if n_qubits else np.exp(2j * np.pi * np.random.rand(1, 1))
+        return cls.from_matrix(haar_matrix, strategy=strategy, disable_loading_bar=disable_loading_bar)
+
     def copy(self) -> "PauliwordOp":
         return deepcopy(self)
 

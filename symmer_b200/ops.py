@@ -467,6 +467,34 @@ def to_csr(xm, zm, cp, n_qubits):
     return data, indices, indptr
 
 
+def pauli_decompose_dense(matrix, n_qubits):
+    """complex128[2^n, 2^n] device matrix -> c'[x, z] (see include/symmer_b200.h): one Walsh-Hadamard transform
+    per XOR-diagonal. The Pauli with masks (x, z) has coefficient c' * i^popcount(x&z)."""
+    side = 1 << int(n_qubits)
+    matrix = matrix.contiguous()
+    assert matrix.is_cuda and matrix.dtype == torch.complex128 and tuple(matrix.shape) == (side, side)
+    out = torch.empty_like(matrix)
+    _cabi.check(lib().sym_pauli_decompose_dense(_p(matrix), int(n_qubits), _p(out), _stream()))
+    return out
+
+
+def pauli_decompose_diagonals(diag, n_qubits):
+    """In place: complex128[K, 2^n] XOR-diagonals d_x[r] = M[r, r^x] -> c'[k, z]."""
+    assert diag.is_cuda and diag.dtype == torch.complex128 and diag.is_contiguous() and diag.shape[1] == 1 << int(n_qubits)
+    _cabi.check(lib().sym_pauli_decompose_diagonals(_p(diag), diag.shape[0], int(n_qubits), _stream()))
+    return diag
+
+
+def rows_from_masks(xm, zm, cp, n_qubits):
+    """Inverse of term masks: (x, z) basis-index masks + phased coefficients -> (packed rows [M, 2], coefficients)."""
+    M = xm.numel()
+    xz = torch.empty((M, 2), dtype=torch.int64, device=xm.device)
+    c = torch.empty(M, dtype=torch.complex128, device=xm.device)
+    _cabi.check(lib().sym_rows_from_masks(_p(xm.contiguous()), _p(zm.contiguous()), _p(_coeff(cp.contiguous())), M,
+                                          int(n_qubits), _p(xz), _p(c), _stream()))
+    return xz, c
+
+
 # ------------------------------------------------------------------------------------------- GF(2)
 def pack_matrix(m):
     """bool[R, C] (device) -> int64[R, Cw]."""

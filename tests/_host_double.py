@@ -252,6 +252,42 @@ def expval_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
     return torch.tensor(complex(np.vdot(p[sl], y[sl])), dtype=torch.complex128)
 
 
+def _wht(table):
+    """Walsh-Hadamard transform along the last axis (natural order), scaled by 1/len."""
+    t = np.array(table, dtype=complex)
+    side = t.shape[-1]
+    h = 1
+    while h < side:
+        t = t.reshape(t.shape[0], -1, 2, h)
+        t = np.stack([t[:, :, 0] + t[:, :, 1], t[:, :, 0] - t[:, :, 1]], axis=2)
+        h *= 2
+    return t.reshape(t.shape[0], side) / side
+
+
+def pauli_decompose_dense(matrix, n_qubits):
+    m = matrix.numpy()
+    side = 1 << int(n_qubits)
+    r = np.arange(side)
+    diag = np.stack([m[r, r ^ x] for x in range(side)])
+    return _tc(_wht(diag))
+
+
+def pauli_decompose_diagonals(diag, n_qubits):
+    diag.copy_(_tc(_wht(diag.numpy())))
+    return diag
+
+
+def rows_from_masks(xm, zm, cp, n_qubits):
+    n = int(n_qubits)
+    shifts = np.arange(n - 1, -1, -1)
+    xb = ((xm.numpy()[:, None] >> shifts) & 1).astype(bool)
+    zb = ((zm.numpy()[:, None] >> shifts) & 1).astype(bool)
+    c = _c(cp) * (1j) ** (np.sum(xb & zb, axis=1) % 4)
+    if xb.shape[0] == 0:
+        return torch.zeros((0, 2), dtype=torch.int64), _tc(c)
+    return _to_xz(po.pack_bits(np.hstack([xb, zb]))), _tc(c)
+
+
 # ------------------------------------------------------------------------------------------- GF(2)
 def pack_matrix(m):
     m = m.numpy().astype(bool)
@@ -299,7 +335,7 @@ def or_rows(bits, rows=None):
 
 _SWAPPED = ["device", "pack", "unpack", "ycount", "sketch", "gather_qubits", "cleanup", "mul_cleanup", "cross_mul",
             "commute", "commute_qwc", "rotate", "rotate_dedup", "project", "term_masks_sorted", "to_csr", "apply_dense",
-            "expval_dense", "pack_matrix", "unpack_matrix", "rref_packed", "bit_transpose", "or_rows"]
+            "expval_dense", "pauli_decompose_dense", "pauli_decompose_diagonals", "rows_from_masks", "pack_matrix", "unpack_matrix", "rref_packed", "bit_transpose", "or_rows"]
 
 
 @contextlib.contextmanager

@@ -267,6 +267,51 @@ def case_projector_helpers(api, G):
         _same_terms(U.symp_matrix, U.coeff_vec, g["symp"], g["coeff"])
 
 
+def case_from_matrix(api, G):
+    import scipy.sparse as sps
+    from symmer_b200 import PauliwordOp
+    names = [n for n in G if n.startswith("from_matrix_") and n != "from_matrix_basis"]
+    assert len(names) == 10
+    for name in names:
+        g = G[name]
+        strategy = 'projector' if name.endswith('projector') else 'full_basis'
+        scale = float(np.abs(g["matrix"]).max())
+        for mat in (g["matrix"], sps.csr_matrix(g["matrix"])):
+            if sps.issparse(mat) and mat.shape[0] != mat.shape[1]:
+                continue                                   # the reference pads dense matrices only
+            op = PauliwordOp.from_matrix(mat, strategy=strategy, disable_loading_bar=True)
+            _same_terms(op.symp_matrix, op.coeff_vec, g["symp"], g["coeff"], scale=scale)
+            # ordered by the [X|Z] bit string like the reference's output (base.py:353-356)
+            keys = [int(''.join('1' if b else '0' for b in row), 2) for row in op.symp_matrix]
+            assert keys == sorted(keys), name
+            n = op.n_qubits
+            side = 1 << n
+            dense = np.zeros((side, side), dtype=complex)
+            m = np.asarray(g["matrix"])
+            dense[:m.shape[0], :m.shape[1]] = m
+            assert np.allclose(op.to_sparse_matrix.toarray(), dense, atol=1e-13 * max(1.0, scale))
+    g = G["from_matrix_basis"]
+    basis = PauliwordOp(g["basis_symp"], np.ones(g["basis_symp"].shape[0]))
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        op = PauliwordOp.from_matrix(g["matrix"], operator_basis=basis)
+        assert any('sufficiently expressive' in str(w.message) for w in caught)
+    _same_terms(op.symp_matrix, op.coeff_vec, g["symp"], g["coeff"])
+    np.random.seed(12)
+    H = PauliwordOp.random(4, 30)
+    assert PauliwordOp.from_matrix(H.to_sparse_matrix) == H
+    assert PauliwordOp.from_matrix(H.to_sparse_matrix.toarray(), strategy='full_basis') == H
+    U = PauliwordOp.haar_random(2)
+    assert (U * U.dagger).cleanup(zero_threshold=1e-12) == PauliwordOp.from_list(['II'])
+    try:
+        PauliwordOp.from_matrix(np.eye(2), strategy='nope')
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("unknown strategy must raise ValueError (base.py:423)")
+    assert PauliwordOp.from_matrix(np.zeros((4, 4))).n_terms == 0
+
+
 def case_misc_methods(api, G):
     from symmer_b200 import PauliwordOp
     P = PauliwordOp.from_list(['XX', 'ZY', 'II'], [1, 2j, -0.5])
@@ -288,4 +333,4 @@ def case_misc_methods(api, G):
 
 
 CASES = [case_qwc, case_reindex, case_tensor, case_graphs, case_jordan, case_quantum_state_constructors,
-         case_quantum_state_methods, case_projector_helpers, case_misc_methods]
+         case_quantum_state_methods, case_projector_helpers, case_from_matrix, case_misc_methods]
