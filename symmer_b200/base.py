@@ -815,6 +815,11 @@ class PauliwordOp:
         return recon, mask
 
 
+    def conjugate_op(self, R: "PauliwordOp") -> "PauliwordOp":
+        """base.py:1512-1562: declared but not implemented in the reference either (it points to
+        `anticommuting_op.conjugate_Pop_with_R`); R self R^dagger is `R * self * R.dagger` here."""
+        raise NotImplementedError('not done yet. Full function at: from symmer.operators.anticommuting_op.conjugate_Pop_with_R')
+
     def jordan_generator_reconstruction(self, generators: "PauliwordOp"):
         """base.py:562-602: reconstruction under the Jordan product PQ = {P,Q}/2 — the symmetry part of the
         generators plus ONE anticommuting clique at a time, each through the device-resident
@@ -1039,6 +1044,35 @@ class QuantumState:
         dev = self.state_op._xz.device
         return QuantumState._from_x_rows(self.state_op._xz, torch.from_numpy(np.asarray(counter, dtype=complex)).to(dev),
                                          self.n_qubits, self.vec_type)
+
+    def plot_state(self, logscale: bool = False, probability_threshold: float = None, binary_xlabels=False,
+                   dpi: int = 100):
+        """base.py:2214-2272: bar chart of the basis-state probabilities (needs matplotlib, an optional dependency)."""
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as err:
+            raise ImportError('QuantumState.plot_state needs the matplotlib package') from err
+        st = self.cleanup()
+        prob = abs(st.state_op.coeff_vec) ** 2
+        index = np.asarray(st.basis_indices_device().cpu().numpy(), dtype=np.int64)
+        if probability_threshold is not None:
+            keep = prob > probability_threshold
+            prob, index = prob[keep], index[keep]
+        order = np.argsort(index)
+        prob, index = prob[order], index[order]
+        fig, axis = plt.subplots(dpi=dpi)
+        if binary_xlabels:
+            labels = [format(int(i), f'0{self.n_qubits}b') for i in index]
+            axis.bar(np.arange(len(index)), prob, width=0.8)
+            axis.set_xticks(np.arange(len(index)))
+            axis.set_xticklabels(labels, rotation=90)
+        else:
+            axis.bar(index, prob, width=0.8)
+        if logscale:
+            axis.set_yscale('log')
+        axis.set_xlabel('Basis state index')
+        axis.set_ylabel('Probability')
+        return axis
 
     def measure_state_in_computational_basis(self, P_op: PauliwordOp):
         """base.py:2188-2212: (U|psi>, U P U^dagger) with U the H / S^dagger change of basis that maps P to Z's."""

@@ -42,6 +42,28 @@ class S3Projection:
             return PauliwordOp(np.array([], dtype=bool), [complex(c.sum().cpu().numpy())])
         return PauliwordOp._from_device(xz, c, n_free).cleanup()
 
+    def _project_state(self, state: QuantumState) -> QuantumState:
+        """projection/base.py:126-158: the state seen from the stabilizer subspace. Hadamards on the qubits whose
+        stabilizer was rotated onto X, the projectors (S^2 + S)/2 = (I + S)/2 of the rotated single-qubit
+        stabilizers, then the stabilizer rotations as exponentials exp(i pi/4 R); the stabilized qubit positions are
+        dropped and duplicates summed. Every product runs on the device."""
+        from functools import reduce
+        from .evolution import Had, trotter
+        rotated = self.stabilizers.rotate_onto_single_qubit_paulis()
+        transformation_list = [Had(self.stabilizers.n_qubits, int(i)) for i in
+                               np.where(np.sum(rotated.X_block & ~rotated.Z_block, axis=0))[0]]
+        for i in range(rotated.n_terms):
+            sq = PauliwordOp._from_device(rotated[i].device_rows, rotated[i].device_coeffs, rotated.n_qubits)
+            transformation_list.append((sq * sq + sq) * .5)
+        for rot in self.stabilizers.stabilizer_rotations:
+            transformation_list.append(trotter(rot[0] * (np.pi / 4 * 1j)))
+        transformation = reduce(lambda x, y: x * y, transformation_list)
+        transformed_state = transformation * state
+        stab = np.where(rotated.symp_matrix)[1] % self.stabilizers.n_qubits
+        free = np.setdiff1d(np.arange(self.stabilizers.n_qubits), stab)
+        return QuantumState(transformed_state.state_matrix[:, free],
+                            transformed_state.state_op.coeff_vec).cleanup(zero_threshold=1e-12)
+
     def perform_projection(self, operator: PauliwordOp, ref_state: Union[List[int], np.ndarray] = None,
                            sector: Union[List[int], np.ndarray] = None) -> PauliwordOp:
         """projection/base.py:86-124."""
@@ -59,8 +81,7 @@ class S3Projection:
 
 
 class QubitTapering(S3Projection):
-    """projection/qubit_tapering.py:9-106 (operator tapering; state projection goes through the
-    reference's gate library and is outside the hot path)."""
+    """projection/qubit_tapering.py:9-111."""
     name = 'qubit_tapering'
 
     def __init__(self, operator: PauliwordOp, target_sqp: str = 'Z') -> None:
@@ -78,6 +99,10 @@ class QubitTapering(S3Projection):
             stabilizers.target_sqp = self.target_sqp
             self._symmetry_generators = stabilizers
         return self._symmetry_generators
+
+    def project_state(self, state_to_project: QuantumState) -> QuantumState:
+        """qubit_tapering.py:108-111."""
+        return self._project_state(state_to_project)
 
     def taper_it(self, ref_state: Union[List[int], np.ndarray, QuantumState] = None,
                  sector: Union[List[int], np.ndarray] = None, aux_operator: PauliwordOp = None) -> PauliwordOp:

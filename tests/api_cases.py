@@ -312,6 +312,44 @@ def case_from_matrix(api, G):
     assert PauliwordOp.from_matrix(np.zeros((4, 4))).n_terms == 0
 
 
+def case_evolution_and_state_projection(api, G):
+    from symmer_b200 import PauliwordOp, QuantumState, QubitTapering
+    from symmer_b200 import evolution as ev
+    gates = {"I": ev.I(3), "X": ev.X(3, 1), "Y": ev.Y(3, 2), "Z": ev.Z(3, 0), "Had": ev.Had(3, 1), "CZ": ev.CZ(3, 0, 2),
+             "CX": ev.CX(3, 2, 0), "CY": ev.CY(3, 1, 2), "RX": ev.RX(3, 0, 0.37), "RY": ev.RY(3, 1, -1.2),
+             "RZ": ev.RZ(3, 2, 2.5), "U1": ev.U1(3, 1, 0.81), "S": ev.S(3, 2)}
+    for name, op in gates.items():
+        g = G[f"gate_{name}"]
+        op = op.cleanup()
+        _same_terms(op.symp_matrix, op.coeff_vec, g["symp"], g["coeff"])
+    cx = ev.CX(2, 0, 1).to_sparse_matrix.toarray()
+    assert np.allclose(cx, [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], atol=1e-14)
+    g = G["exp_single"]
+    E = ev.exponentiate_single_Pop(PauliwordOp(g["symp"], g["coeff"]))
+    _same_terms(E.symp_matrix, E.coeff_vec, g["out_symp"], g["out_coeff"])
+    try:
+        ev.exponentiate_single_Pop(PauliwordOp.from_list(['X', 'Z']))
+    except AssertionError:
+        pass
+    else:
+        raise AssertionError("only single Pauli terms can be exponentiated (exponentiation.py:17)")
+    for trotnum in [1, 3]:
+        g = G[f"trotter_{trotnum}"]
+        E = ev.trotter(PauliwordOp(g["symp"], g["coeff"]).multiply_by_constant(0.2j), trotnum=trotnum)
+        _same_terms(E.symp_matrix, E.coeff_vec, g["out_symp"], g["out_coeff"])
+    for tag in ["H3+", "Be"]:
+        g = G[f"project_state_{tag}"]
+        H = PauliwordOp(g["h_symp"], g["h_coeff"])
+        QT = QubitTapering(H)
+        Ht = QT.taper_it(ref_state=g["hf"])
+        _same_terms(Ht.symp_matrix, Ht.coeff_vec, g["tapered_symp"], g["tapered_coeff"],
+                    scale=float(np.abs(g["h_coeff"]).max()))
+        psi = QuantumState(g["psi_state"], g["psi_coeff"])
+        proj = QT.project_state(psi)
+        assert proj.n_qubits == Ht.n_qubits
+        _same_state(proj, g["out_state"], g["out_coeff"])
+
+
 def case_misc_methods(api, G):
     from symmer_b200 import PauliwordOp
     P = PauliwordOp.from_list(['XX', 'ZY', 'II'], [1, 2j, -0.5])
@@ -333,4 +371,5 @@ def case_misc_methods(api, G):
 
 
 CASES = [case_qwc, case_reindex, case_tensor, case_graphs, case_jordan, case_quantum_state_constructors,
-         case_quantum_state_methods, case_projector_helpers, case_from_matrix, case_misc_methods]
+         case_quantum_state_methods, case_projector_helpers, case_from_matrix,
+         case_evolution_and_state_projection, case_misc_methods]

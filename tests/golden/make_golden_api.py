@@ -215,6 +215,42 @@ op = PauliwordOp.from_matrix(H.to_sparse_matrix.toarray(), operator_basis=basis,
 put("from_matrix_basis", matrix=H.to_sparse_matrix.toarray(), basis_symp=basis.symp_matrix, symp=op.symp_matrix,
     coeff=op.coeff_vec)
 
+# --- 8. gate library, exponentials, state projection --------------------------------------------------
+import json  # noqa: E402
+from symmer import QubitTapering  # noqa: E402
+from symmer.evolution import trotter  # noqa: E402
+from symmer.evolution.exponentiation import exponentiate_single_Pop  # noqa: E402
+from symmer.evolution import gate_library as gl  # noqa: E402
+
+gates = {"I": gl.I(3), "X": gl.X(3, 1), "Y": gl.Y(3, 2), "Z": gl.Z(3, 0), "Had": gl.Had(3, 1), "CZ": gl.CZ(3, 0, 2),
+         "CX": gl.CX(3, 2, 0), "CY": gl.CY(3, 1, 2), "RX": gl.RX(3, 0, 0.37), "RY": gl.RY(3, 1, -1.2),
+         "RZ": gl.RZ(3, 2, 2.5), "U1": gl.U1(3, 1, 0.81), "S": gl.S(3, 2)}
+for name, op in gates.items():
+    op = op.cleanup()
+    put(f"gate_{name}", symp=op.symp_matrix, coeff=op.coeff_vec)
+P1 = PauliwordOp.from_list(['XYZI'], [0.3 - 0.8j])
+E = exponentiate_single_Pop(P1)
+put("exp_single", symp=P1.symp_matrix, coeff=P1.coeff_vec, out_symp=E.symp_matrix, out_coeff=E.coeff_vec)
+np.random.seed(41)
+T = PauliwordOp.random(3, 4)
+for trotnum in [1, 3]:
+    E = trotter(T.multiply_by_constant(0.2j), trotnum=trotnum)
+    put(f"trotter_{trotnum}", symp=T.symp_matrix, coeff=T.coeff_vec, out_symp=E.symp_matrix, out_coeff=E.coeff_vec)
+
+for tag, fname in [("H3+", "H3+_STO-3G_SINGLET_JW.json"), ("Be", "Be_STO-3G_SINGLET_JW.json")]:
+    with open(os.path.join("/root/reference/tests/hamiltonian_data", fname)) as f:
+        dd = json.load(f)
+    H = PauliwordOp.from_dictionary({k: complex(v[0], v[1]) for k, v in dd["hamiltonian"].items()})
+    hf = np.asarray(dd["data"]["hf_array"], dtype=int)
+    QT = QubitTapering(H)
+    Ht = QT.taper_it(ref_state=hf)
+    np.random.seed(42)
+    psi = QuantumState(hf) if tag == "Be" else QuantumState.random(H.n_qubits, 6)
+    proj = QT.project_state(psi)
+    put(f"project_state_{tag}", h_symp=H.symp_matrix, h_coeff=H.coeff_vec, hf=hf, psi_state=psi.state_matrix,
+        psi_coeff=psi.state_op.coeff_vec, tapered_symp=Ht.symp_matrix, tapered_coeff=Ht.coeff_vec,
+        out_state=proj.state_matrix, out_coeff=proj.state_op.coeff_vec)
+
 path = os.path.join(HERE, "api_vectors.npz")
 np.savez_compressed(path, **out)
 print(f"wrote {len(out)} arrays to {path} ({os.path.getsize(path) / 1024:.0f} KB)")
