@@ -40,12 +40,61 @@ class IndependentOp(PauliwordOp):
             raise ValueError('The supplied stabilizers are not independent')
 
     @classmethod
+    def _from_independent_rows(cls, xz, n_qubits: int) -> "IndependentOp":
+        """Wrap device rows that are independent by construction (distinct pivots of a GF(2) reduction) with unit
+        coefficients: the checks of `__init__` hold trivially, so no host round trip is needed."""
+        import torch
+        ones = torch.ones(xz.shape[0], dtype=torch.complex128, device=xz.device)
+        self = PauliwordOp._from_device(xz, ones, n_qubits)
+        self.__class__ = cls
+        self.target_sqp = 'Z'
+        return self
+
+    @classmethod
     def symmetry_generators(cls, PwordOp: PauliwordOp, commuting_override: bool = False,
                             largest_clique: bool = False) -> "IndependentOp":
-        """independent_op.py:90-144: column reduction of [[Z X],[I]]; the rows of I below the zero
-        columns of the reduced top block span the symmetry group. The GF(2) reduction and the
-        commutation check run on the device; the clique search (only when the generators do not
-        mutually commute) is host graph logic as in the reference."""
+        """independent_op.py:90-144: column reduction of [[Z X],[I]]; the rows of I below the zero columns of the
+        reduced top block span the symmetry group.
+
+        Device-resident (config C2): the packed rows are bit-transposed (column reduction = row reduction of the
+        transpose, utils.py:337-347), the identity block is appended directly in the packed-row layout (row of
+        Z-bit q carries the packed row of X_q and vice versa, so the reduced identity part IS the generator in
+        packed form), one bit-exact GF(2) reduction and one commutation kernel run back to back, and a single
+        small copy (pivots + commutation matrix) comes back to the host. The clique search (only when the
+        generators do not mutually commute) is host graph logic as in the reference."""
+        import torch
+        from . import ops
+        n, M = PwordOp.n_qubits, PwordOp.n_terms
+        if n == 0 or M == 0:
+            return cls._symmetry_generators_host(PwordOp, commuting_override, largest_clique)
+        W = ops.words_for(n)
+        T = ops.bit_transpose(PwordOp.device_rows)                       # [128 W bit positions][ceil(M/64)]
+        Cw_terms = T.shape[1]
+        reduced = torch.cat([torch.cat([T[64 * W:64 * W + n], T[:n]], dim=0), _single_qubit_rows(n, T.device)],
+                            dim=1).contiguous()
+        piv = ops.rref_packed(reduced, 64 * Cw_terms + 128 * W)
+        rows = reduced[:, Cw_terms:].contiguous()
+        adj = ops.commute(rows, rows)
+        back = torch.cat([piv.view(torch.uint8), adj.reshape(-1).view(torch.uint8)]).cpu().numpy()
+        piv_host = back[:8 * n].view(np.int32)
+        adj_host = back[8 * n:].view(bool).reshape(2 * n, 2 * n)
+        sel = np.flatnonzero(piv_host >= 64 * Cw_terms)                  # top block reduced to zero
+        if len(sel) == 0:
+            warnings.warn('The input PauliwordOp has no Z2 symmetries.')
+            return cls(np.zeros((0, 2 * n), dtype=bool), np.ones(0))
+        adj_sel = adj_host[np.ix_(sel, sel)]
+        if not (np.all(adj_sel) or commuting_override):
+            sel = sel[_largest_commuting_subset(adj_sel, largest_clique)]
+            adj_sel = adj_host[np.ix_(sel, sel)]
+        S = cls._from_independent_rows(rows.index_select(0, torch.as_tensor(sel, dtype=torch.int64, device=rows.device)), n)
+        S._cache['adjacency_matrix'] = adj_sel
+        return S
+
+    @classmethod
+    def _symmetry_generators_host(cls, PwordOp: PauliwordOp, commuting_override: bool = False,
+                                  largest_clique: bool = False) -> "IndependentOp":
+        """The same search through the array seams (`_cref_binary` on a host matrix, device reduction inside):
+        degenerate operands (no qubits / no terms), and the cross-check of the device-resident path in the tests."""
         n = PwordOp.n_qubits
         to_reduce = np.vstack([np.hstack([PwordOp.Z_block, PwordOp.X_block]), np.eye(2 * n, dtype=bool)])
         cref_matrix = _cref_binary(to_reduce)
@@ -57,18 +106,7 @@ class IndependentOp(PauliwordOp):
         adj = S.adjacency_matrix
         if np.all(adj) or commuting_override:
             return S
-        # largest mutually commuting subset (independent_op.py:132-144)
-        import networkx as nx
-        graph = nx.from_numpy_array(adj & ~np.eye(S.n_terms, dtype=bool))
-        if S.n_terms < 10 or largest_clique:
-            keep = sorted(max(nx.find_cliques(graph), key=len))
-        else:
-            colouring = nx.greedy_color(nx.complement(graph), strategy='independent_set')
-            groups = {}
-            for node, col in colouring.items():
-                groups.setdefault(col, []).append(node)
-            keep = sorted(groups[0])
-            warnings.warn('Greedy method may identify non-optimal commuting symmetry terms; might be able to taper again.')
+        keep = _largest_commuting_subset(adj, largest_clique)
         return cls(S.symp_matrix[keep], np.ones(len(keep), dtype=complex))
 
     # ------------------------------------------------------------------ container behaviour
@@ -194,3 +232,36 @@ def assign_value(S: PauliwordOp, ref_state: QuantumState, threshold: float = 0.5
         e = single_term_expval(PauliwordOp.__getitem__(S, i), ref_state)
         values.append(int(np.sign(e)) if abs(e) > threshold else 0)
     return values
+
+
+_SINGLE_QUBIT_ROWS = {}
+
+
+def _single_qubit_rows(n_qubits: int, device):
+    """Packed rows of X_0..X_{n-1}, Z_0..Z_{n-1} (int64[2n, 2W]), cached per (n, device)."""
+    import torch
+    key = (n_qubits, str(device))
+    if key not in _SINGLE_QUBIT_ROWS:
+        W = max(1, (n_qubits + 63) // 64)
+        rows = np.zeros((2 * n_qubits, 2 * W), dtype=np.uint64)
+        q = np.arange(n_qubits)
+        rows[q, q // 64] = np.uint64(1) << (q % 64).astype(np.uint64)
+        rows[n_qubits + q, W + q // 64] = np.uint64(1) << (q % 64).astype(np.uint64)
+        _SINGLE_QUBIT_ROWS[key] = torch.from_numpy(rows.view(np.int64)).to(device)
+    return _SINGLE_QUBIT_ROWS[key]
+
+
+def _largest_commuting_subset(adj: np.ndarray, largest_clique: bool) -> List[int]:
+    """independent_op.py:132-144: indices of a largest mutually commuting subset (exact clique search below ten
+    generators or on request, greedy colouring of the complement graph otherwise)."""
+    import networkx as nx
+    k = adj.shape[0]
+    graph = nx.from_numpy_array(adj & ~np.eye(k, dtype=bool))
+    if k < 10 or largest_clique:
+        return sorted(max(nx.find_cliques(graph), key=len))
+    colouring = nx.greedy_color(nx.complement(graph), strategy='independent_set')
+    groups = {}
+    for node, col in colouring.items():
+        groups.setdefault(col, []).append(node)
+    warnings.warn('Greedy method may identify non-optimal commuting symmetry terms; might be able to taper again.')
+    return sorted(groups[0])

@@ -350,6 +350,51 @@ def case_evolution_and_state_projection(api, G):
         _same_state(proj, g["out_state"], g["out_coeff"])
 
 
+def case_symmetry_generators_device_path(api, G):
+    """The device-resident search (bit transpose + packed identity block + one reduction) against the array-seam
+    form of the same search and the reference's generators (tests/golden/golden_vectors.npz, taper_vectors.npz)."""
+    import warnings as _w
+    from conftest import load_hamiltonian
+    from symmer_b200 import IndependentOp, PauliwordOp
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "golden_vectors.npz"))
+    for tag in ["H2O_STO3G", "Be_STO3G"]:
+        symp, coeff, _ = load_hamiltonian(tag)
+        H = PauliwordOp(symp, coeff)
+        S = IndependentOp.symmetry_generators(H)
+        ref = gold[f"symgen_{tag}/gen_symp"]
+        assert np.array_equal(S.symp_matrix, ref), tag                          # bit-exact, reference order
+        S_host = IndependentOp._symmetry_generators_host(H)
+        assert np.array_equal(S_host.symp_matrix, ref), tag
+        assert isinstance(S, IndependentOp) and S.target_sqp == 'Z' and np.all(S.coeff_vec == 1)
+        assert np.array_equal(S.adjacency_matrix, S_host.adjacency_matrix)
+        assert np.all(S.commutes_termwise(H))
+    # wide rows (two words per block) and a term count that is not a multiple of 64
+    np.random.seed(77)
+    gens = PauliwordOp.random(70, 5, diagonal=True)
+    pool = [gens[i] for i in range(5)]
+    terms = PauliwordOp.from_list(['I' * 70], [1.0])
+    for k in range(1, 32):
+        picks = [pool[j] for j in range(5) if (k >> j) & 1]
+        prod = picks[0]
+        for extra in picks[1:]:
+            prod = prod * extra
+        terms = terms.append(prod)
+    S = IndependentOp.symmetry_generators(terms)
+    S_host = IndependentOp._symmetry_generators_host(terms)
+    assert np.array_equal(S.symp_matrix, S_host.symp_matrix) and S.n_terms >= 65
+    # generators that do not mutually commute: largest commuting subset (independent_op.py:132-144)
+    lone = PauliwordOp.from_list(['ZI'])
+    S = IndependentOp.symmetry_generators(lone)
+    S_host = IndependentOp._symmetry_generators_host(lone)
+    assert np.array_equal(S.symp_matrix, S_host.symp_matrix) and np.all(S.adjacency_matrix)
+    S_all = IndependentOp.symmetry_generators(lone, commuting_override=True)
+    assert S_all.n_terms == 3 and not np.all(S_all.adjacency_matrix)
+    with _w.catch_warnings(record=True) as caught:
+        _w.simplefilter("always")
+        none = IndependentOp.symmetry_generators(PauliwordOp.from_list(['X', 'Z']))
+        assert none.n_terms == 0 and any('no Z2 symmetries' in str(w.message) for w in caught)
+
+
 def case_misc_methods(api, G):
     from symmer_b200 import PauliwordOp
     P = PauliwordOp.from_list(['XX', 'ZY', 'II'], [1, 2j, -0.5])
@@ -372,4 +417,4 @@ def case_misc_methods(api, G):
 
 CASES = [case_qwc, case_reindex, case_tensor, case_graphs, case_jordan, case_quantum_state_constructors,
          case_quantum_state_methods, case_projector_helpers, case_from_matrix,
-         case_evolution_and_state_projection, case_misc_methods]
+         case_evolution_and_state_projection, case_symmetry_generators_device_path, case_misc_methods]
