@@ -154,15 +154,23 @@ def main():
                 rec["cpu_expval_real"] = po.expval_dense(symp, coeff, psi).real
             emit(f"C4 matrix-free expval {tag}", **rec)
 
-    if "gf2" in which:
+    if "gf2" in which or "c2" in which:
+        from symmer_b200 import QubitTapering
         symp, coeff, n = load_ham("H2O_STO3G")
         H = PauliwordOp(symp, coeff)
-        t = gpu_time(lambda: IndependentOp.symmetry_generators(H), reps=10)
+        t = gpu_time(lambda: IndependentOp.symmetry_generators(H), reps=20, warm=3)
+        t_seam = gpu_time(lambda: IndependentOp._symmetry_generators_host(H), reps=20, warm=3)
         tc = cpu_time(lambda: po.symmetry_generator_rows(symp), reps=5)
         ta = gpu_time(lambda: ops.commute(H.device_rows, H.device_rows), reps=10)
         tca = cpu_time(lambda: po.commutes_termwise(symp, symp), reps=3)
-        emit("C2 symmetry generators H2O STO-3G (14q, 1086 terms)", gpu_s=t, cpu_port_s=tc,
-             adjacency_gpu_s=ta, adjacency_pairs_per_s=1086 * 1086 / ta, adjacency_cpu_s=tca)
+        hf = np.asarray(np.load(os.path.join("tests", "golden", "hamiltonians", "H2O_STO3G.npz"))["hf_array"], dtype=int)
+        t_taper = None
+        if hf is not None:
+            t_taper = gpu_time(lambda: QubitTapering(H).taper_it(ref_state=hf), reps=5, warm=2)
+        emit("C2 symmetry generators H2O STO-3G (14q, 1086 terms)", gpu_s=t, gpu_s_array_seam_form=t_seam, cpu_port_s=tc,
+             adjacency_gpu_s=ta, adjacency_pairs_per_s=1086 * 1086 / ta, adjacency_cpu_s=tca,
+             taper_it_end_to_end_gpu_s=t_taper)
+    if "gf2" in which:
         rng = np.random.default_rng(1)
         m = rng.random((2000, 100000)) < 0.3
         bits = ops.pack_matrix(torch.from_numpy(m))

@@ -771,9 +771,19 @@ class PauliwordOp:
     @property
     def generators(self) -> "PauliwordOp":
         """base.py:1436-1456: independent generating set via row reduction."""
-        red, piv = _rref_device(self.symp_matrix)
-        non_zero = red[piv >= 0]
-        gens = PauliwordOp(non_zero, np.ones(non_zero.shape[0], dtype=complex))
+        if self.n_terms == 0 or self.n_qubits == 0:
+            red, piv = _rref_device(self.symp_matrix)
+            non_zero = red[piv >= 0]
+            gens = PauliwordOp(non_zero, np.ones(non_zero.shape[0], dtype=complex))
+        else:
+            # reduce a copy of the packed rows in place (padding columns are zero and never pivot); only the pivot
+            # vector comes back, the generators stay on the device
+            rows = self._xz.clone()
+            piv = ops.rref_packed(rows, 64 * rows.shape[1])
+            keep = torch.nonzero(piv >= 0).reshape(-1)
+            gens = PauliwordOp._from_device(rows.index_select(0, keep),
+                                            torch.ones(keep.numel(), dtype=torch.complex128, device=rows.device),
+                                            self.n_qubits)
         assert gens.n_terms <= 2 * self.n_qubits, 'cannot have an independent generating set of size greaterthan 2 time num qubits'
         return gens
 

@@ -103,6 +103,12 @@ def check_independent(operators) -> bool:
     """utils.py:504-519 (accepts anything with n_terms, n_qubits, symp_matrix)."""
     if operators.n_terms > 2 * operators.n_qubits:
         return False
+    if hasattr(operators, 'device_rows') and operators.n_terms and operators.n_qubits:
+        # the packed rows ARE a packed bit matrix in the column order [X | padding | Z | padding]: all-zero padding
+        # columns never pivot, so reducing a copy of them in place is the reduction of bool[M, 2n]
+        rows = operators.device_rows.clone()
+        piv = ops.rref_packed(rows, 64 * rows.shape[1])
+        return bool((piv >= 0).all().item())
     _, piv = _rref_device(operators.symp_matrix)
     return bool(np.all(piv >= 0))
 

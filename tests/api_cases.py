@@ -368,6 +368,14 @@ def case_symmetry_generators_device_path(api, G):
         assert isinstance(S, IndependentOp) and S.target_sqp == 'Z' and np.all(S.coeff_vec == 1)
         assert np.array_equal(S.adjacency_matrix, S_host.adjacency_matrix)
         assert np.all(S.commutes_termwise(H))
+        gens = H.generators                                                     # device-resident reduction of the packed rows
+        assert np.array_equal(gens.symp_matrix, gold[f"recon_{tag}/gen_symp"]), tag
+        recon, mask = H.generator_reconstruction(gens)
+        assert np.array_equal(recon, gold[f"recon_{tag}/recon"]) and np.array_equal(mask, gold[f"recon_{tag}/mask"])
+    from symmer_b200.utils import check_independent
+    assert check_independent(PauliwordOp.from_list(['XX', 'ZZ', 'XI']))
+    assert not check_independent(PauliwordOp.from_list(['XX', 'ZZ', 'YY']))
+    assert not check_independent(PauliwordOp.from_list(['X', 'Z', 'Y']))
     # wide rows (two words per block) and a term count that is not a multiple of 64
     np.random.seed(77)
     gens = PauliwordOp.random(70, 5, diagonal=True)
