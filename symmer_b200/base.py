@@ -29,6 +29,8 @@ DENSE_STATE_MAX_QUBITS = 30
 # (ops.rotate_dedup: measured 4.7 vs 6.0 ms at 1e7 rows, equal at 1e6); smaller ones keep the two-step form,
 # which has fewer launches (0.30 vs 0.39 ms at 1e5 rows)
 FUSED_ROTATION_MIN_TERMS = 1 << 21
+# operators up to this many terms keep a host copy of their coefficients next to the device copy (1 MB at most)
+_HOST_COEFF_MAX_TERMS = 1 << 16
 
 
 class PauliwordOp:
@@ -57,7 +59,11 @@ class PauliwordOp:
         self._c = torch.from_numpy(np.ascontiguousarray(coeff)).to(dev)
         self._symp_host = symp_matrix
         self._symp_host.setflags(write=False)
-        self._c_host = None          # becomes authoritative once handed out (callers mutate it in place)
+        # The host coefficient view becomes authoritative once it exists (callers mutate it in place). Small operators
+        # keep the caller's array from the start, like the reference (base.py:70 aliases it), so reading `coeff_vec`
+        # never costs a device round trip; `_coeff_dev` re-uploads only when the snapshot shows it was changed.
+        self._c_host = coeff if n_terms <= _HOST_COEFF_MAX_TERMS else None
+        self._c_snapshot = coeff.copy() if self._c_host is not None else None
         self._cache = {}
 
     @classmethod
@@ -70,6 +76,7 @@ class PauliwordOp:
         self._c = c.contiguous()
         self._symp_host = None
         self._c_host = None
+        self._c_snapshot = None
         self._cache = {}
         return self
 
@@ -88,6 +95,7 @@ class PauliwordOp:
     def coeff_vec(self) -> np.ndarray:
         if self._c_host is None:
             self._c_host = self._c.cpu().numpy()
+            self._c_snapshot = self._c_host.copy() if self.n_terms <= _HOST_COEFF_MAX_TERMS else None
         return self._c_host
 
     @coeff_vec.setter
@@ -95,6 +103,7 @@ class PauliwordOp:
         value = np.asarray(value, dtype=complex)
         assert len(value) == self.n_terms, 'coeff list and Pauliwords not same length'
         self._c_host = value
+        self._c_snapshot = None
         self._cache.clear()
 
     @property
@@ -109,7 +118,11 @@ class PauliwordOp:
         """Device coefficients; refreshed from the host view if one was handed out (the reference's
         callers mutate coeff_vec in place: base.py:746, 1821; independent_op.py:35, 295)."""
         if self._c_host is not None:
-            self._c = torch.from_numpy(np.ascontiguousarray(self._c_host, dtype=complex)).to(self._xz.device)
+            host, snap = self._c_host, self._c_snapshot
+            if snap is not None and snap.shape == host.shape and np.array_equal(snap, host):
+                return self._c                                   # unchanged since the last upload
+            self._c = torch.from_numpy(np.ascontiguousarray(host, dtype=complex)).to(self._xz.device)
+            self._c_snapshot = np.array(host, dtype=complex) if host.size <= _HOST_COEFF_MAX_TERMS else None
         return self._c
 
     @property

@@ -16,14 +16,38 @@ class IndependentOp(PauliwordOp):
         symp_matrix = np.asarray(symp_matrix)
         if coeff_vec is None:
             coeff_vec = np.ones(symp_matrix.reshape(-1, symp_matrix.shape[-1]).shape[0], dtype=complex)
-        super().__init__(symp_matrix, coeff_vec)
         if target_sqp not in ['X', 'Z', 'Y']:
             raise ValueError('Target single-qubit Pauli not recognised - must be X or Z')
+        # the coefficient checks of independent_op.py:33-36, 146-151 run on the host array BEFORE it is uploaded
+        coeff = np.asarray(coeff_vec, dtype=complex)
+        if coeff.ndim == 1:
+            if not set(coeff).issubset({0, +1, -1}):
+                raise ValueError(f'Stabilizer coefficients not +/-1: {coeff}')
+            if np.all(coeff.imag == 0):
+                coeff = coeff.real.astype(int).astype(complex)
+        super().__init__(symp_matrix, coeff)
         self.target_sqp = target_sqp
-        self._check_stab()
-        self.coeff_vec = self.coeff_vec.real.astype(int).astype(complex) if np.all(self.coeff_vec.imag == 0) \
-            else self.coeff_vec
+        self.coeff_vec = coeff                    # host view authoritative from the start (callers set sectors in place)
         self._check_independent()
+
+    @classmethod
+    def _trusted(cls, xz, c, n_qubits: int, target_sqp: str = 'Z', nonzero=None) -> "IndependentOp":
+        """Wrap device rows known to satisfy the constructor's checks — a subset or a Clifford rotation of a valid
+        set is independent with coefficients in {0, +1, -1} — without the host round trip and the GF(2) reduction
+        the validating constructor costs. `nonzero`: the coefficients are known to be all non-zero."""
+        self = PauliwordOp._from_device(xz, c, n_qubits)
+        self.__class__ = cls
+        self.target_sqp = target_sqp
+        self._nz = nonzero
+        return self
+
+    def _all_nonzero(self) -> bool:
+        """No zero-valued sector: Clifford rotations then never need the reference's per-step cleanup."""
+        if self._c_host is not None:
+            return bool(np.all(np.abs(self._c_host) > 1e-15))
+        if getattr(self, '_nz', None) is None:
+            self._nz = bool((self._c.abs() > 1e-15).all().item())
+        return self._nz
 
     @classmethod
     def from_PauliwordOp(cls, PwordOp: PauliwordOp) -> "IndependentOp":
@@ -41,14 +65,10 @@ class IndependentOp(PauliwordOp):
 
     @classmethod
     def _from_independent_rows(cls, xz, n_qubits: int) -> "IndependentOp":
-        """Wrap device rows that are independent by construction (distinct pivots of a GF(2) reduction) with unit
-        coefficients: the checks of `__init__` hold trivially, so no host round trip is needed."""
+        """Device rows that are independent by construction (distinct pivots of a GF(2) reduction), unit coefficients."""
         import torch
         ones = torch.ones(xz.shape[0], dtype=torch.complex128, device=xz.device)
-        self = PauliwordOp._from_device(xz, ones, n_qubits)
-        self.__class__ = cls
-        self.target_sqp = 'Z'
-        return self
+        return cls._trusted(xz, ones, n_qubits, nonzero=True)
 
     @classmethod
     def symmetry_generators(cls, PwordOp: PauliwordOp, commuting_override: bool = False,
@@ -122,32 +142,51 @@ class IndependentOp(PauliwordOp):
     def __getitem__(self, key) -> "IndependentOp":
         """independent_op.py:316-350: indexing re-validates the selection as an IndependentOp."""
         sub = PauliwordOp.__getitem__(self, key)
-        return IndependentOp(sub.symp_matrix, sub.coeff_vec)
+        if sub.n_terms <= self.n_terms and not _has_repeats(key, self.n_terms):
+            return IndependentOp._trusted(sub.device_rows, sub.device_coeffs, self.n_qubits, self.target_sqp)
+        return IndependentOp(sub.symp_matrix, sub.coeff_vec)      # repeated indices: let the constructor reject them
 
     def __iter__(self):
         return iter([self[i] for i in range(self.n_terms)])
 
     # ------------------------------------------------------------------ Clifford rotations onto single-qubit Paulis
     def _rotate_by_single_Pword(self, Pword: PauliwordOp, angle: float = None) -> "IndependentOp":
-        """independent_op.py:186-190. The rotation search below picks pivots by row position, so the
-        row order of the reference's Clifford branch (anticommuting rows first, then the commuting
-        ones; base.py:1151-1154) is reproduced here — these operators have at most n rows, the
-        reordering is a host-side gather."""
-        rotated = PauliwordOp._rotate_by_single_Pword(self, Pword, angle)
+        """independent_op.py:186-190. The rotation search below picks pivots by row position, so the row order of
+        the reference's Clifford branch (anticommuting rows first, then the commuting ones; base.py:1151-1154) is
+        reproduced. With no zero-valued sector the whole step stays on the device (rotation kernel, commutation
+        kernel, stable partition) and the result is wrapped without re-validation: a Clifford rotation maps an
+        independent +/-1 set onto one."""
+        import torch
         multiple = (np.pi / 2 if angle is None else complex(angle).real) * 2 / np.pi
-        if rotated.n_terms == self.n_terms and abs(round(multiple) - multiple) <= 1e-18:
+        clifford = abs(round(multiple) - multiple) <= 1e-18
+        if clifford and self._all_nonzero():
+            rotated, _ = PauliwordOp._rotation_step(self, Pword, angle)
+            commutes = self.commutes_termwise_device(Pword)[:, 0]
+            order = torch.argsort(commutes.to(torch.int8), stable=True)          # anticommuting rows first
+            return IndependentOp._trusted(rotated.device_rows.index_select(0, order),
+                                          rotated.device_coeffs.index_select(0, order), self.n_qubits, self.target_sqp,
+                                          nonzero=True)
+        rotated = PauliwordOp._rotate_by_single_Pword(self, Pword, angle)
+        if rotated.n_terms == self.n_terms and clifford:
             commutes = self.commutes_termwise(Pword)[:, 0]
             if not commutes.all():
-                # the reference forms the anticommuting part with `*`, whose cleanup drops zero coefficients
-                anti = np.flatnonzero(~commutes & (abs(self.coeff_vec) > 1e-15))
-                rotated = rotated._take(np.concatenate([anti, np.flatnonzero(commutes)]))
+                anti = ~commutes
+                if round(multiple) % 2:
+                    # odd multiples form the anticommuting part with `*`, whose cleanup drops zero coefficients
+                    anti &= abs(self.coeff_vec) > 1e-15
+                rotated = rotated._take(np.concatenate([np.flatnonzero(anti), np.flatnonzero(commutes)]))
         return self.from_PauliwordOp(rotated)
 
     def perform_rotations(self, rotations: List[Tuple[PauliwordOp, float]]) -> "IndependentOp":
-        """independent_op.py:192-204 (a dedup after every rotation, like base.py:1184-1185)."""
+        """independent_op.py:192-204 (a dedup after every rotation, like base.py:1184-1185; a Clifford rotation of
+        a set without zero-valued sectors cannot create duplicates or zeros, so that dedup is the identity)."""
         op = self
         for generator, angle in rotations:
-            op = self.from_PauliwordOp(op._rotate_by_single_Pword(generator, angle).cleanup())
+            step = op._rotate_by_single_Pword(generator, angle)
+            if getattr(step, '_nz', None) and step._c_host is None:
+                op = step
+            else:
+                op = self.from_PauliwordOp(step.cleanup())
         return self.from_PauliwordOp(op) if op is self else op
 
     def _recursive_rotations(self, basis: "IndependentOp") -> None:
@@ -165,7 +204,7 @@ class IndependentOp(PauliwordOp):
         rest_symp, rest_coeff = symp[~single], coeff[~single]
         if rest_symp.shape[0] == 0:
             return None
-        rest = IndependentOp(rest_symp, rest_coeff)
+        rest = IndependentOp._trusted(*_subset(basis, np.flatnonzero(~single)), n, self.target_sqp)
         pivot_row = rest_symp[np.argsort(rest_symp.sum(axis=1))][0]
         candidates = np.setdiff1d(np.flatnonzero(pivot_row), np.array(self.used_indices))
         support = pivot_row * rest_symp.sum(axis=0)
@@ -184,8 +223,7 @@ class IndependentOp(PauliwordOp):
         assert (np.all(self.adjacency_matrix)), 'The basis is not commuting, hence the rotation is not possible'
         self.stabilizer_rotations = []
         self.used_indices = []
-        basis = self.copy()
-        basis = IndependentOp(basis.symp_matrix, basis.coeff_vec)
+        basis = IndependentOp._trusted(self.device_rows, self.device_coeffs, self.n_qubits)
         self._recursive_rotations(basis)
         rotated = basis.perform_rotations(self.stabilizer_rotations)
         n = self.n_qubits
@@ -208,6 +246,8 @@ class IndependentOp(PauliwordOp):
         op = PauliwordOp._from_device(self.device_rows, self.device_coeffs, self.n_qubits)
         for generator, angle in self.stabilizer_rotations:
             op, _ = op._rotation_step(generator, angle)
+        if self._all_nonzero():
+            return IndependentOp._trusted(op.device_rows, op.device_coeffs, self.n_qubits, self.target_sqp, nonzero=True)
         keep = np.flatnonzero(abs(op.coeff_vec) > 1e-15)    # the per-stabilizer cleanup of the reference
         return IndependentOp(op.symp_matrix[keep], op.coeff_vec[keep])
 
@@ -225,13 +265,39 @@ class IndependentOp(PauliwordOp):
 
 
 def assign_value(S: PauliwordOp, ref_state: QuantumState, threshold: float = 0.5) -> List[int]:
-    """independent_op.py:364-383, evaluated term by term on the device (never through
-    process.parallelize: no fork after CUDA initialisation)."""
-    values = []
-    for i in range(S.n_terms):
-        e = single_term_expval(PauliwordOp.__getitem__(S, i), ref_state)
-        values.append(int(np.sign(e)) if abs(e) > threshold else 0)
-    return values
+    """independent_op.py:364-383, evaluated term by term on the device (never through process.parallelize: no fork
+    after CUDA initialisation). With a dense state the per-generator kernels are queued back to back and their
+    results come back in one copy."""
+    import torch
+    from .base import DENSE_STATE_MAX_QUBITS
+    if 1 <= S.n_qubits <= DENSE_STATE_MAX_QUBITS and S.n_terms:
+        dense = ref_state.to_dense_device()
+        ones = torch.ones(1, dtype=torch.complex128, device=dense.device)
+        parts = []
+        for i in range(S.n_terms):
+            unit = PauliwordOp._from_device(S.device_rows[i:i + 1], ones, S.n_qubits)
+            parts.append(unit.expval_dense(dense))
+        expvals = torch.stack(parts).cpu().numpy().real
+    else:
+        expvals = [single_term_expval(PauliwordOp.__getitem__(S, i), ref_state) for i in range(S.n_terms)]
+    return [int(np.sign(e)) if abs(e) > threshold else 0 for e in expvals]
+
+
+def _subset(op: PauliwordOp, index: np.ndarray):
+    """(rows, coefficients) of the selected terms, gathered on the device."""
+    import torch
+    idx = torch.as_tensor(np.asarray(index, dtype=np.int64), device=op.device_rows.device)
+    return op.device_rows.index_select(0, idx), op.device_coeffs.index_select(0, idx)
+
+
+def _has_repeats(key, n_terms: int) -> bool:
+    if isinstance(key, (int, np.integer, slice)):
+        return False
+    idx = np.asarray(key)
+    if idx.dtype == bool:
+        return False
+    idx = np.where(idx < 0, idx + n_terms, idx)
+    return len(np.unique(idx)) != idx.size
 
 
 _SINGLE_QUBIT_ROWS = {}

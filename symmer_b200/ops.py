@@ -395,13 +395,19 @@ def term_masks_sorted(xz, c, n_qubits):
     cp = torch.empty(M, dtype=torch.complex128, device=dev)
     L = lib()
     _cabi.check(L.sym_term_masks(_p(xz), _p(_coeff(c)), M, int(n_qubits), _p(xm), _p(zm), _p(cp), _stream()))
-    order = sort_pairs(xm.clone(), torch.arange(M, dtype=torch.int32, device=dev), begin_bit=0)[1].to(torch.int64)
-    cp = cp[order].contiguous()
-    flags = torch.stack([(cp.imag == 0).all(), (c.imag == 0).all()]).cpu().tolist()    # one sync, once per operator
+    if M > 1:
+        order = sort_pairs(xm.clone(), torch.arange(M, dtype=torch.int32, device=dev), begin_bit=0)[1].to(torch.int64)
+        xm, zm, cp = xm[order].contiguous(), zm[order].contiguous(), cp[order].contiguous()
+    if M <= 32:
+        # a handful of terms (stabilizers measured one at a time): the fast paths would save nothing, and reading
+        # the flags back costs a stream synchronise per operator
+        flags = [False, False]
+    else:
+        flags = torch.stack([(cp.imag == 0).all(), (c.imag == 0).all()]).cpu().tolist()    # one sync, once per operator
     cp._sym_real = bool(flags[0])
     cp._sym_hermitian = bool(flags[0] and flags[1])
     cp._sym_table = None
-    return xm[order].contiguous(), zm[order].contiguous(), cp
+    return xm, zm, cp
 
 
 def _is_real(cp):

@@ -75,7 +75,13 @@ class S3Projection:
         self.stab_qubit_indices = np.where(self.rotated_stabilizers.symp_matrix)[1] % operator.n_qubits
         self.free_qubit_indices = np.setdiff1d(np.arange(operator.n_qubits), self.stab_qubit_indices)
         rotations = getattr(self.stabilizers, 'stabilizer_rotations', [])
-        op_rotated = operator.perform_rotations(rotations) if len(rotations) > 0 else operator
+        # the stabilizer rotations are Clifford: pure relabels of the rows on the device, and the dedup the reference
+        # runs after them (base.py:1185) is absorbed by the one that follows the projection
+        op_rotated = operator
+        for generator, angle in rotations:
+            op_rotated, status = op_rotated._rotation_step(generator, angle)
+            if status == 'dirty':
+                op_rotated = op_rotated.cleanup()
         self.rotated_flag = True
         return self._perform_projection(operator=op_rotated)
 

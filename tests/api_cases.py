@@ -403,6 +403,34 @@ def case_symmetry_generators_device_path(api, G):
         assert none.n_terms == 0 and any('no Z2 symmetries' in str(w.message) for w in caught)
 
 
+def case_tapering_intermediates(api, G):
+    """QubitTapering(H).taper_it against the reference's vectors (tests/golden/make_golden_taper.py): generators,
+    sector, the rotation list in order, rotated stabilizers and free qubits bit-exact, the tapered operator as a
+    term set — the regression net of the host-side stabilizer bookkeeping (independent_op.py:146-383)."""
+    from conftest import load_hamiltonian
+    from symmer_b200 import PauliwordOp, QubitTapering
+    data = np.load(os.path.join(ROOT, "tests", "golden", "taper_vectors.npz"))
+    for tag in ["H2O_STO3G", "Be_STO3G"]:
+        symp, coeff, _ = load_hamiltonian(tag)
+        for sqp in ["Z", "X"]:
+            g = {k.split("/", 1)[1]: data[k] for k in data.files if k.startswith(f"taper_{tag}_{sqp}/")}
+            nq = int(g["n_out_qubits"][0])
+            out_symp = np.unpackbits(g["out_symp"], axis=1)[:, :2 * nq].astype(bool)
+            H = PauliwordOp(symp, coeff)
+            qt = QubitTapering(H, target_sqp=sqp)
+            assert qt.n_taper == g["gen_symp"].shape[0]
+            assert np.array_equal(qt.symmetry_generators.symp_matrix, g["gen_symp"])
+            out = qt.taper_it(ref_state=g["hf"])
+            assert np.array_equal(qt.stabilizers.coeff_vec.real, g["sector"]), (tag, sqp)
+            rot = np.array([r.symp_matrix[0] for r, _ in qt.stabilizers.stabilizer_rotations]).reshape(-1, symp.shape[1])
+            assert np.array_equal(rot, g["rotations"]), (tag, sqp)
+            assert np.array_equal(qt.rotated_stabilizers.symp_matrix, g["rotated_symp"]), (tag, sqp)
+            assert np.array_equal(qt.rotated_stabilizers.coeff_vec.real, g["rotated_coeff"]), (tag, sqp)
+            assert np.array_equal(qt.free_qubit_indices, g["free"])
+            assert out.n_qubits == nq and out.n_terms == out_symp.shape[0]
+            _same_terms(out.symp_matrix, out.coeff_vec, out_symp, g["out_coeff"], scale=float(np.abs(coeff).max()))
+
+
 def case_misc_methods(api, G):
     from symmer_b200 import PauliwordOp
     P = PauliwordOp.from_list(['XX', 'ZY', 'II'], [1, 2j, -0.5])
@@ -425,4 +453,5 @@ def case_misc_methods(api, G):
 
 CASES = [case_qwc, case_reindex, case_tensor, case_graphs, case_jordan, case_quantum_state_constructors,
          case_quantum_state_methods, case_projector_helpers, case_from_matrix,
-         case_evolution_and_state_projection, case_symmetry_generators_device_path, case_misc_methods]
+         case_evolution_and_state_projection, case_symmetry_generators_device_path, case_tapering_intermediates,
+         case_misc_methods]

@@ -27,10 +27,29 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = False
     if has_gpu:
         return
+    # SYMMER_HOST_DOUBLE=1 (developer aid on the CPU box): run the API-level GPU tests against the NumPy test double
+    # of the kernels (tests/_host_double.py) instead of skipping them — host logic only, never a parity claim.
+    doubled = os.environ.get("SYMMER_HOST_DOUBLE") == "1"
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
         if "gpu" in item.keywords:
-            item.add_marker(skip)
+            if not (doubled and os.path.basename(str(item.fspath)) in _DOUBLED_FILES):
+                item.add_marker(skip)
+
+
+_DOUBLED_FILES = ("test_gpu_api.py", "test_gpu_api_ext.py")
+
+
+@pytest.fixture(autouse=True)
+def _host_double_ops(request):
+    import torch
+    if (os.environ.get("SYMMER_HOST_DOUBLE") == "1" and not torch.cuda.is_available() and "gpu" in request.keywords
+            and os.path.basename(str(request.node.fspath)) in _DOUBLED_FILES):
+        from _host_double import host_double
+        with host_double():
+            yield
+    else:
+        yield
 
 
 @pytest.fixture(scope="session")
