@@ -198,13 +198,13 @@ class PauliwordOp:
         from scipy.sparse import issparse
         if isinstance(matrix, np.matrix):
             matrix = np.array(matrix)
+        if not (issparse(matrix) or isinstance(matrix, np.ndarray)):
+            raise ValueError('Unrecognised matrix type, must be one of np.array or sp.sparse.csr_matrix')
         n_qubits = int(np.ceil(np.log2(max(matrix.shape))))
         if n_qubits > 30 and operator_basis is None:
             raise ValueError('Matrix too large! Will run into memory limitations.')
         if operator_basis is None and strategy not in ('full_basis', 'projector'):
             raise ValueError('Unrecognised strategy, must be one of full_basis or projector')
-        if not (issparse(matrix) or isinstance(matrix, np.ndarray)):
-            raise ValueError('Unrecognised matrix type, must be one of np.array or sp.sparse.csr_matrix')
         side = 1 << n_qubits
         dev = ops.device()
         basis = None
@@ -1142,7 +1142,7 @@ class QuantumState:
             cand = perm[pos]
             hit = (kr_sorted[pos] == kl) & (xr[cand] == xl).all(dim=1)
             lc, rc = left.state_op._coeff_dev(), right.state_op._coeff_dev()
-            return complex(torch.sum(lc[hit] * rc[cand[hit]]).cpu().numpy())
+            return np.complex128(torch.sum(lc[hit] * rc[cand[hit]]).cpu().numpy())     # NumPy scalar like the reference's
         if isinstance(mul_obj, PauliwordOp):
             new = self.state_op * mul_obj
             y = ops.ycount(new._xz).to(torch.int64)

@@ -106,6 +106,12 @@ class QubitTapering(S3Projection):
             self._symmetry_generators = stabilizers
         return self._symmetry_generators
 
+    @symmetry_generators.setter
+    def symmetry_generators(self, stabilizers: IndependentOp) -> None:
+        """The reference's cached_property is assignable (tests/test_projection/test_qubit_tapering.py:72): a caller
+        may taper with a subset of the symmetry generators; `taper_it` then re-initialises the parent projection."""
+        self._symmetry_generators = stabilizers
+
     def project_state(self, state_to_project: QuantumState) -> QuantumState:
         """qubit_tapering.py:108-111."""
         return self._project_state(state_to_project)

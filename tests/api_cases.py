@@ -431,6 +431,38 @@ def case_tapering_intermediates(api, G):
             _same_terms(out.symp_matrix, out.coeff_vec, out_symp, g["out_coeff"], scale=float(np.abs(coeff).max()))
 
 
+def case_symmer_utils(api, G):
+    from symmer_b200 import PauliwordOp, QuantumState
+    from symmer_b200.symmer_utils import (exact_gs_energy, get_entanglement_entropy, matrix_allclose, product_list,
+                                          tensor_list)
+    for tag in ["H3+", "Be"]:
+        g = G[f"gs_{tag}"]
+        H = PauliwordOp(g["h_symp"], g["h_coeff"])
+        N = PauliwordOp(g["n_symp"], g["n_coeff"])
+        e_ref = float(g["e0"][0])
+        # matrix-free: every H|v> of the Lanczos iteration through the device kernel
+        e_dev, psi_dev = exact_gs_energy(H)
+        assert abs(e_dev - e_ref) < 1e-8, (tag, e_dev, e_ref)
+        assert abs(H.expval(psi_dev) - e_ref) < 1e-8
+        # the reference's own call form (CSR matrix in)
+        e_csr, _ = exact_gs_energy(H.to_sparse_matrix)
+        assert abs(e_csr - e_ref) < 1e-8
+        e_n, psi_n = exact_gs_energy(H, n_particles=int(g["n_particles"][0]), number_operator=N, n_eigs=12)
+        assert abs(e_n - float(g["e_n"][0])) < 1e-8 and abs(e_n - float(g["fci"][0])) < 1e-6, (tag, e_n)
+        assert abs(N.expval(psi_n) - int(g["n_particles"][0])) < 1e-6
+    g = G["entropy"]
+    psi = QuantumState(g["state"], g["coeff"])
+    got = [get_entanglement_entropy(psi, [0, 1]), get_entanglement_entropy(psi, [2]), get_entanglement_entropy(psi, [0, 2, 4])]
+    assert np.allclose(got, g["out"], rtol=1e-10, atol=1e-12)
+    for name, fn in [("tensor_list", tensor_list), ("product_list", product_list)]:
+        g = G[name]
+        factors = [PauliwordOp(g[f"symp_{i}"], g[f"coeff_{i}"]) for i in range(3)]
+        out = fn(factors)
+        _same_terms(out.symp_matrix, out.coeff_vec, g["out_symp"], g["out_coeff"])
+    A = PauliwordOp.from_list(['XZ', 'YY'], [0.5, 2]).to_sparse_matrix
+    assert matrix_allclose(A, A.copy()) and matrix_allclose(A, A.toarray()) and not matrix_allclose(A, 2 * A)
+
+
 def case_misc_methods(api, G):
     from symmer_b200 import PauliwordOp
     P = PauliwordOp.from_list(['XX', 'ZY', 'II'], [1, 2j, -0.5])
@@ -454,4 +486,4 @@ def case_misc_methods(api, G):
 CASES = [case_qwc, case_reindex, case_tensor, case_graphs, case_jordan, case_quantum_state_constructors,
          case_quantum_state_methods, case_projector_helpers, case_from_matrix,
          case_evolution_and_state_projection, case_symmetry_generators_device_path, case_tapering_intermediates,
-         case_misc_methods]
+         case_symmer_utils, case_misc_methods]

@@ -251,6 +251,33 @@ for tag, fname in [("H3+", "H3+_STO-3G_SINGLET_JW.json"), ("Be", "Be_STO-3G_SING
         psi_coeff=psi.state_op.coeff_vec, tapered_symp=Ht.symp_matrix, tapered_coeff=Ht.coeff_vec,
         out_state=proj.state_matrix, out_coeff=proj.state_op.coeff_vec)
 
+# --- 9. symmer/utils.py helpers -----------------------------------------------------------------------
+from symmer.utils import exact_gs_energy, get_entanglement_entropy, tensor_list, product_list  # noqa: E402
+
+for tag, fname in [("H3+", "H3+_STO-3G_SINGLET_JW.json"), ("Be", "Be_STO-3G_SINGLET_JW.json")]:
+    with open(os.path.join("/root/reference/tests/hamiltonian_data", fname)) as f:
+        dd = json.load(f)
+    H = PauliwordOp.from_dictionary({k: complex(v[0], v[1]) for k, v in dd["hamiltonian"].items()})
+    N = PauliwordOp.from_dictionary({k: complex(v[0], v[1]) for k, v in dd["data"]["auxiliary_operators"]["number_operator"].items()})
+    e0, psi0 = exact_gs_energy(H.to_sparse_matrix)
+    n_part = int(dd["data"]["n_particles"])
+    e_n, psi_n = exact_gs_energy(H.to_sparse_matrix, n_particles=n_part, number_operator=N, n_eigs=12)
+    put(f"gs_{tag}", h_symp=H.symp_matrix, h_coeff=H.coeff_vec, n_symp=N.symp_matrix, n_coeff=N.coeff_vec,
+        e0=[e0], n_particles=[n_part], e_n=[e_n], fci=[dd["data"]["calculated_properties"]["FCI"]["energy"]])
+np.random.seed(51)
+psi = QuantumState.random(5, 12)
+put("entropy", state=psi.state_matrix, coeff=psi.state_op.coeff_vec,
+    out=[get_entanglement_entropy(psi, [0, 1]), get_entanglement_entropy(psi, [2]), get_entanglement_entropy(psi, [0, 2, 4])])
+np.random.seed(52)
+ops3 = [PauliwordOp.random(2, 3), PauliwordOp.random(1, 2), PauliwordOp.random(2, 2)]
+T3 = tensor_list(ops3)
+put("tensor_list", **{f"symp_{i}": o.symp_matrix for i, o in enumerate(ops3)}, **{f"coeff_{i}": o.coeff_vec for i, o in enumerate(ops3)},
+    out_symp=T3.symp_matrix, out_coeff=T3.coeff_vec)
+sq = [PauliwordOp.random(3, 4) for _ in range(3)]
+P3 = product_list(sq)
+put("product_list", **{f"symp_{i}": o.symp_matrix for i, o in enumerate(sq)}, **{f"coeff_{i}": o.coeff_vec for i, o in enumerate(sq)},
+    out_symp=P3.symp_matrix, out_coeff=P3.coeff_vec)
+
 path = os.path.join(HERE, "api_vectors.npz")
 np.savez_compressed(path, **out)
 print(f"wrote {len(out)} arrays to {path} ({os.path.getsize(path) / 1024:.0f} KB)")
