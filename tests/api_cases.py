@@ -454,7 +454,7 @@ def case_symmer_utils(api, G):
     psi = QuantumState(g["state"], g["coeff"])
     got = [get_entanglement_entropy(psi, [0, 1]), get_entanglement_entropy(psi, [2]), get_entanglement_entropy(psi, [0, 2, 4])]
     assert np.allclose(got, g["out"], rtol=1e-10, atol=1e-12)
-    for name, fn in [("tensor_list", tensor_list), ("product_list", product_list)]:
+    for name, fn in [("util_tensor_list", tensor_list), ("util_product_list", product_list)]:
         g = G[name]
         factors = [PauliwordOp(g[f"symp_{i}"], g[f"coeff_{i}"]) for i in range(3)]
         out = fn(factors)

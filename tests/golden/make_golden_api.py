@@ -271,11 +271,11 @@ put("entropy", state=psi.state_matrix, coeff=psi.state_op.coeff_vec,
 np.random.seed(52)
 ops3 = [PauliwordOp.random(2, 3), PauliwordOp.random(1, 2), PauliwordOp.random(2, 2)]
 T3 = tensor_list(ops3)
-put("tensor_list", **{f"symp_{i}": o.symp_matrix for i, o in enumerate(ops3)}, **{f"coeff_{i}": o.coeff_vec for i, o in enumerate(ops3)},
+put("util_tensor_list", **{f"symp_{i}": o.symp_matrix for i, o in enumerate(ops3)}, **{f"coeff_{i}": o.coeff_vec for i, o in enumerate(ops3)},
     out_symp=T3.symp_matrix, out_coeff=T3.coeff_vec)
 sq = [PauliwordOp.random(3, 4) for _ in range(3)]
 P3 = product_list(sq)
-put("product_list", **{f"symp_{i}": o.symp_matrix for i, o in enumerate(sq)}, **{f"coeff_{i}": o.coeff_vec for i, o in enumerate(sq)},
+put("util_product_list", **{f"symp_{i}": o.symp_matrix for i, o in enumerate(sq)}, **{f"coeff_{i}": o.coeff_vec for i, o in enumerate(sq)},
     out_symp=P3.symp_matrix, out_coeff=P3.coeff_vec)
 
 path = os.path.join(HERE, "api_vectors.npz")
