@@ -70,6 +70,56 @@ def get_entanglement_entropy(psi: QuantumState, qubits: List[int]) -> float:
     return -np.sum(eigvals * np.log(eigvals)).real
 
 
+def random_anitcomm_2n_1_PauliwordOp(n_qubits: int, complex_coeff: bool = False, apply_clifford: bool = True) -> PauliwordOp:
+    """symmer/utils.py:96-158: a maximal (2n+1)-term pairwise anticommuting operator with normal coefficients — the
+    Jordan-Wigner-like strings Z..Z Y_i and Z..Z X_i plus Z..Z — scrambled by 5n random Clifford rotations (device
+    kernel `sym_rotate`). Draws from the global NumPy RNG in the reference's order."""
+    q = np.arange(n_qubits)
+    z_below = q[:, None] > q[None, :]                       # Z on every qubit before i
+    here = np.eye(n_qubits, dtype=bool)
+    y_rows = np.hstack([here, z_below | here])
+    x_rows = np.hstack([here, z_below])
+    z_row = np.hstack([np.zeros(n_qubits, dtype=bool), np.ones(n_qubits, dtype=bool)])
+    symp = np.vstack([y_rows, x_rows, z_row])
+    coeff_vec = np.random.randn(symp.shape[0]).astype(complex)
+    if complex_coeff:
+        coeff_vec += 1j * np.random.randn(2 * n_qubits + 1).astype(complex)
+    P_anticomm = PauliwordOp(symp, coeff_vec)
+    if apply_clifford:
+        rotations = []
+        for _ in range(n_qubits * 5):
+            P_rand = PauliwordOp.random(n_qubits, n_terms=1)
+            P_rand.coeff_vec = [1]
+            rotations.append((P_rand, np.random.choice([np.pi / 2, -np.pi / 2])))
+        P_anticomm = P_anticomm.perform_rotations(rotations)
+    assert P_anticomm.n_terms == 2 * n_qubits + 1
+    return P_anticomm
+
+
+def gram_schmidt_from_quantum_state(state: Union[np.ndarray, list, QuantumState]) -> np.ndarray:
+    """symmer/utils.py:186-298: a unitary whose first column is the given state (the remaining columns come from a
+    Gram-Schmidt sweep over the identity); small dense host linear algebra, as in the reference."""
+    if isinstance(state, QuantumState):
+        n_qubits = state.n_qubits
+        state = state.to_sparse_matrix.toarray().reshape([-1])
+    else:
+        state = np.asarray(state).reshape([-1])
+        n_qubits = round(np.log2(state.shape[0]))
+        state = np.hstack((state, np.zeros(2 ** n_qubits - state.shape[0], dtype=complex)))
+    assert state.shape[0] == 2 ** n_qubits, 'state is not defined on power of two'
+    assert np.isclose(np.linalg.norm(state), 1), 'state is not normalized'
+    M = np.eye(2 ** n_qubits, dtype=complex)
+    if np.isclose(state[0], 0):
+        swap = np.argmax(state)
+        M[:, [0, swap]] = M[:, [swap, 0]]
+    M[:, 0] = state
+    for a in range(M.shape[0]):
+        for b in range(a):
+            M[:, a] -= (M[:, b].conj() @ M[:, a]) * M[:, b]
+        M[:, a] /= np.linalg.norm(M[:, a])
+    return M
+
+
 def tensor_list(factor_list: List[PauliwordOp]) -> PauliwordOp:
     """symmer/utils.py:160-171."""
     return reduce(lambda x, y: x.tensor(y), factor_list)

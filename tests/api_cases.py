@@ -459,6 +459,18 @@ def case_symmer_utils(api, G):
         factors = [PauliwordOp(g[f"symp_{i}"], g[f"coeff_{i}"]) for i in range(3)]
         out = fn(factors)
         _same_terms(out.symp_matrix, out.coeff_vec, g["out_symp"], g["out_coeff"])
+    from symmer_b200.symmer_utils import gram_schmidt_from_quantum_state, random_anitcomm_2n_1_PauliwordOp
+    for i in range(3):
+        g = G[f"anticomm_{i}"]
+        n, cplx, cliff, seed = [int(v) for v in g["args"]]
+        np.random.seed(seed)
+        AC = random_anitcomm_2n_1_PauliwordOp(n, complex_coeff=bool(cplx), apply_clifford=bool(cliff))
+        _same_terms(AC.symp_matrix, AC.coeff_vec, g["symp"], g["coeff"])       # same RNG draws as the reference
+        assert AC.n_terms == 2 * n + 1
+        assert np.array_equal(AC.adjacency_matrix, np.eye(AC.n_terms, dtype=bool))
+    g = G["gram_schmidt"]
+    U = gram_schmidt_from_quantum_state(QuantumState(g["state"], g["coeff"]))
+    assert np.allclose(U, g["out"], atol=1e-13) and np.allclose(U @ U.conj().T, np.eye(8), atol=1e-12)
     A = PauliwordOp.from_list(['XZ', 'YY'], [0.5, 2]).to_sparse_matrix
     assert matrix_allclose(A, A.copy()) and matrix_allclose(A, A.toarray()) and not matrix_allclose(A, 2 * A)
 

@@ -278,6 +278,16 @@ P3 = product_list(sq)
 put("util_product_list", **{f"symp_{i}": o.symp_matrix for i, o in enumerate(sq)}, **{f"coeff_{i}": o.coeff_vec for i, o in enumerate(sq)},
     out_symp=P3.symp_matrix, out_coeff=P3.coeff_vec)
 
+from symmer.utils import random_anitcomm_2n_1_PauliwordOp, gram_schmidt_from_quantum_state  # noqa: E402
+
+for i, (n, cplx, cliff, seed) in enumerate([(4, False, False, 61), (5, True, True, 62), (3, False, True, 63)]):
+    np.random.seed(seed)
+    AC = random_anitcomm_2n_1_PauliwordOp(n, complex_coeff=cplx, apply_clifford=cliff)
+    put(f"anticomm_{i}", args=[n, int(cplx), int(cliff), seed], symp=AC.symp_matrix, coeff=AC.coeff_vec)
+np.random.seed(64)
+psi = QuantumState.random(3, 5)
+put("gram_schmidt", state=psi.state_matrix, coeff=psi.state_op.coeff_vec, out=gram_schmidt_from_quantum_state(psi))
+
 path = os.path.join(HERE, "api_vectors.npz")
 np.savez_compressed(path, **out)
 print(f"wrote {len(out)} arrays to {path} ({os.path.getsize(path) / 1024:.0f} KB)")
