@@ -475,6 +475,68 @@ def case_symmer_utils(api, G):
     assert matrix_allclose(A, A.copy()) and matrix_allclose(A, A.toarray()) and not matrix_allclose(A, 2 * A)
 
 
+def case_circuit_symmerlator(api, G):
+    from symmer_b200 import PauliwordOp
+    from symmer_b200 import evolution as ev
+    from symmer_b200.circuit_symmerlator import CircuitSymmerlator
+    g = G["circuit_qasm"]
+    O = PauliwordOp(g["o_symp"], g["o_coeff"])
+    CS = CircuitSymmerlator.from_qasm(str(g["qasm"][0]))
+    assert len(CS.sequence) == int(g["n_steps"][0])
+    assert np.array_equal(np.vstack([p.symp_matrix for p, _ in CS.sequence]), g["seq_symp"])
+    assert np.allclose([a for _, a in CS.sequence], g["seq_angle"], rtol=1e-15, atol=0)
+    rot = CS.apply_sequence(O)
+    _same_terms(rot.symp_matrix, rot.coeff_vec, g["rot_symp"], g["rot_coeff"])
+    assert abs(CS.evaluate(O) - complex(g["expval"][0])) < 1e-12
+    # Heisenberg picture: apply_sequence(P) = U^dagger P U with U the gate-library operator, on all two-qubit Paulis
+    np.random.seed(5)
+    theta = float(np.random.random())
+    one = {'X': ev.X, 'Y': ev.Y, 'Z': ev.Z, 'H': ev.Had, 'S': ev.S}
+    letters = ['I', 'X', 'Y', 'Z']
+    for name, gate in one.items():
+        CS = CircuitSymmerlator(2)
+        getattr(CS, name)(1)
+        U = gate(2, 1)
+        for a in letters:
+            for b in letters:
+                P = PauliwordOp.from_list([a + b])
+                assert CS.apply_sequence(P) == (U.dagger * P * U).cleanup(zero_threshold=1e-12), (name, a + b)
+    for name, gate in {'CX': ev.CX, 'CY': ev.CY, 'CZ': ev.CZ}.items():
+        CS = CircuitSymmerlator(2)
+        getattr(CS, name)(0, 1)
+        U = gate(2, 0, 1)
+        for a in letters:
+            for b in letters:
+                P = PauliwordOp.from_list([a + b])
+                assert CS.apply_sequence(P) == (U.dagger * P * U).cleanup(zero_threshold=1e-12), (name, a + b)
+    for name, gate in {'RX': ev.RX, 'RY': ev.RY, 'RZ': ev.RZ}.items():
+        CS = CircuitSymmerlator(1)
+        getattr(CS, name)(0, theta)
+        U = gate(1, 0, theta)
+        for a in letters:
+            P = PauliwordOp.from_list([a])
+            assert CS.apply_sequence(P) == (U.dagger * P * U).cleanup(zero_threshold=1e-12), (name, a)
+    # expectation value against the dense state U|0...0>
+    CS = CircuitSymmerlator(3)
+    CS.H(0); CS.CX(0, 1); CS.S(1); CS.sqrtY(2); CS.CZ(1, 2); CS.SWAP(0, 2); CS.RY(1, 0.3)
+    np.random.seed(9)
+    O = PauliwordOp.random(3, 20, complex_coeffs=False)
+    gates = [ev.Had(3, 0), ev.CX(3, 0, 1), ev.S(3, 1), ev.RY(3, 2, -np.pi / 2), ev.CZ(3, 1, 2), ev.CX(3, 0, 2), ev.CX(3, 2, 0),
+             ev.CX(3, 0, 2), ev.RY(3, 1, 0.3)]
+    sv = np.zeros(8, dtype=complex)
+    sv[0] = 1
+    for gate in gates:
+        sv = gate.to_sparse_matrix @ sv
+    expect = np.vdot(sv, O.to_sparse_matrix @ sv)
+    assert abs(CS.evaluate(O) - expect) < 1e-12, (CS.evaluate(O), expect)
+    try:
+        CS.Toffoli(0, 1, 2)
+    except NotImplementedError:
+        pass
+    else:
+        raise AssertionError("Toffoli is not implemented in the reference either")
+
+
 def case_misc_methods(api, G):
     from symmer_b200 import PauliwordOp
     P = PauliwordOp.from_list(['XX', 'ZY', 'II'], [1, 2j, -0.5])
@@ -498,4 +560,4 @@ def case_misc_methods(api, G):
 CASES = [case_qwc, case_reindex, case_tensor, case_graphs, case_jordan, case_quantum_state_constructors,
          case_quantum_state_methods, case_projector_helpers, case_from_matrix,
          case_evolution_and_state_projection, case_symmetry_generators_device_path, case_tapering_intermediates,
-         case_symmer_utils, case_misc_methods]
+         case_symmer_utils, case_circuit_symmerlator, case_misc_methods]

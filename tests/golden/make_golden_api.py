@@ -288,6 +288,18 @@ np.random.seed(64)
 psi = QuantumState.random(3, 5)
 put("gram_schmidt", state=psi.state_matrix, coeff=psi.state_op.coeff_vec, out=gram_schmidt_from_quantum_state(psi))
 
+from symmer.evolution.circuit_symmerlator import CircuitSymmerlator  # noqa: E402
+
+QASM = ("OPENQASM 3.0;\ninclude \"stdgates.inc\";\nqubit[4] q;\nh q[0];\ncx q[0], q[1];\nrz(pi/3) q[1];\n"
+        "sdg q[2];\ncz q[1], q[3];\nry(-0.4) q[3];\nswap q[2], q[3];\nsx q[0];\ny q[2];\nrx(3*pi/2) q[0];\n")
+np.random.seed(71)
+O = PauliwordOp.random(4, 30, complex_coeffs=False)
+CS = CircuitSymmerlator.from_qasm(QASM)
+rot = CS.apply_sequence(O)
+put("circuit_qasm", qasm=[QASM], o_symp=O.symp_matrix, o_coeff=O.coeff_vec, n_steps=[len(CS.sequence)],
+    seq_symp=np.vstack([p.symp_matrix for p, _ in CS.sequence]), seq_angle=[a for _, a in CS.sequence],
+    rot_symp=rot.symp_matrix, rot_coeff=rot.coeff_vec, expval=[CS.evaluate(O)])
+
 path = os.path.join(HERE, "api_vectors.npz")
 np.savez_compressed(path, **out)
 print(f"wrote {len(out)} arrays to {path} ({os.path.getsize(path) / 1024:.0f} KB)")
