@@ -54,3 +54,34 @@ def test_double_matches_the_oracle_on_core_paths(golden, host_ops):
     assert P.n_terms == 1 and P.to_dictionary == {"YYY": 2}
     m = np.array([[1, 1, 0], [0, 1, 1], [1, 0, 1]], dtype=bool)
     assert np.array_equal(rref_binary(m), po.rref_binary(m))
+
+
+def test_compat_serves_import_symmer(host_ops):
+    """`symmer_b200.compat.install_as_symmer()`: code written against the reference's package names runs on this
+    engine (scripts/run_reference_tests.py drives the reference's own test files through the same alias)."""
+    import sys
+    from symmer_b200 import compat
+    assert "symmer" not in sys.modules
+    compat.install_as_symmer()
+    try:
+        from symmer import PauliwordOp, QuantumState, QubitTapering, process
+        from symmer.operators import IndependentOp, single_term_expval
+        from symmer.operators.utils import check_independent, symplectic_cleanup
+        from symmer.evolution import trotter
+        from symmer.evolution.gate_library import Had, CX
+        from symmer.evolution.circuit_symmerlator import CircuitSymmerlator
+        from symmer.utils import exact_gs_energy, tensor_list
+        import symmer.operators.utils as ref_utils
+        import symmer_b200
+        assert PauliwordOp is symmer_b200.PauliwordOp and process.method == 'single_thread'
+        assert ref_utils.check_independent is check_independent
+        H = PauliwordOp.from_list(['XX', 'ZZ'], [1, 1])
+        assert (H * H).to_dictionary == {'II': 2}
+        assert check_independent(IndependentOp.from_list(['ZI', 'IZ']))
+        assert np.isclose(exact_gs_energy(H.to_sparse_matrix)[0], -2)
+        assert CX(2, 0, 1).n_terms == 4 and Had(1, 0).n_terms == 2 and callable(trotter) and callable(tensor_list)
+        assert isinstance(QuantumState.zero(2), QuantumState) and callable(single_term_expval) and callable(symplectic_cleanup)
+        assert CircuitSymmerlator(2).n_qubits == 2 and QubitTapering.__name__ == 'QubitTapering'
+    finally:
+        compat.uninstall()
+    assert "symmer" not in sys.modules and "symmer.operators.utils" not in sys.modules
