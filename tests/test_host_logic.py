@@ -76,7 +76,7 @@ def test_compat_serves_import_symmer(host_ops):
         assert PauliwordOp is symmer_b200.PauliwordOp and process.method == 'single_thread'
         assert ref_utils.check_independent is check_independent
         H = PauliwordOp.from_list(['XX', 'ZZ'], [1, 1])
-        assert (H * H).to_dictionary == {'II': 2}
+        assert (H * H).to_dictionary == {'II': 2, 'YY': -2}
         assert check_independent(IndependentOp.from_list(['ZI', 'IZ']))
         assert np.isclose(exact_gs_energy(H.to_sparse_matrix)[0], -2)
         assert CX(2, 0, 1).n_terms == 4 and Had(1, 0).n_terms == 2 and callable(trotter) and callable(tensor_list)
