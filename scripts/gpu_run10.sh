@@ -9,5 +9,5 @@ tail -25 gpurun_out/${TAG}_ext.log
 timeout 330 python -m pytest tests -m gpu -x -q --durations=4 > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 tail -15 gpurun_out/${TAG}_pytest.log
-timeout 200 python scripts/bench_paths.py c2 > gpurun_out/${TAG}_paths.json 2> gpurun_out/${TAG}_paths.err
+echo skip-paths > gpurun_out/${TAG}_paths.json; : > gpurun_out/${TAG}_paths.err
 cat gpurun_out/${TAG}_paths.json; tail -5 gpurun_out/${TAG}_paths.err
