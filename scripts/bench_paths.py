@@ -154,6 +154,34 @@ def main():
                 rec["cpu_expval_real"] = po.expval_dense(symp, coeff, psi).real
             emit(f"C4 matrix-free expval {tag}", **rec)
 
+    if "g" in which:
+        # kernels of rows g1-g3: qubit-wise commutation, qubit gather, Walsh-Hadamard decomposition
+        n, M = 1000, 50000
+        a_s = np.random.default_rng(3).random((M, 2 * n)) < 0.3
+        a = ops.pack(torch.from_numpy(a_s), n)
+        blk = a[:20000].contiguous()
+        t = gpu_time(lambda: ops.commute_qwc(blk, a), reps=3, warm=1)
+        emit("qwc 1000q: 20000x50000 block", gpu_s=t, pairs_per_s=20000 * M / t, out_write_gbs=20000 * M / t / 1e9,
+             lop3_per_pair=5 * 2 * 16)
+        n36, M36 = 36, 42599
+        b_s = np.random.default_rng(4).random((M36, 2 * n36)) < 0.3
+        b = ops.pack(torch.from_numpy(b_s), n36)
+        t = gpu_time(lambda: ops.commute_qwc(b[:20000].contiguous(), b), reps=3, warm=1)
+        emit("qwc 36q: 20000x42599 block (NaCl size)", gpu_s=t, pairs_per_s=20000 * M36 / t,
+             frac_hbm_write=20000 * M36 / t / 1e9 / PEAK)
+        perm = np.random.default_rng(0).permutation(n)
+        t = gpu_time(lambda: ops.gather_qubits(a, perm, n), reps=3, warm=1)
+        emit("gather_qubits: random permutation of 1000 qubits, 50000 rows", gpu_s=t, rows_per_s=M / t,
+             rw_gbs=2 * M * 256 / t / 1e9)
+        for nq, K in [(12, 4096), (20, 64), (24, 4)]:
+            table = torch.randn(K, 1 << nq, dtype=torch.complex128, device="cuda")
+            t = gpu_time(lambda: ops.pauli_decompose_diagonals(table, nq), reps=3, warm=1)
+            passes = 1 + max(0, nq - 12)
+            emit(f"walsh-hadamard of {K} diagonals of 2^{nq} entries (in place)", gpu_s=t, entries_per_s=K * (1 << nq) / t,
+                 passes=passes, rw_gbs=passes * 2 * K * (1 << nq) * 16 / t / 1e9,
+                 frac_hbm=passes * 2 * K * (1 << nq) * 16 / t / 1e9 / PEAK)
+            del table
+
     if "gf2" in which or "c2" in which:
         from symmer_b200 import QubitTapering
         symp, coeff, n = load_ham("H2O_STO3G")
