@@ -333,7 +333,11 @@ class PauliwordOp:
         return self._take(np.ascontiguousarray(order))
 
     def _take(self, index) -> "PauliwordOp":
-        idx = torch.as_tensor(np.asarray(index, dtype=np.int64), device=self._xz.device)
+        index = np.asarray(index, dtype=np.int64).reshape(-1)
+        if index.size and (index.min() < -self.n_terms or index.max() >= self.n_terms):
+            raise IndexError(f'index out of bounds for an operator of {self.n_terms} terms')
+        index = np.where(index < 0, index + self.n_terms, index)          # NumPy's negative-index convention
+        idx = torch.as_tensor(index, device=self._xz.device)
         return PauliwordOp._from_device(self._xz.index_select(0, idx), self._coeff_dev().index_select(0, idx),
                                         self.n_qubits)
 

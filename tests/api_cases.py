@@ -546,6 +546,16 @@ def case_misc_methods(api, G):
         assert not caught
         P.set_processing_method('ray')
         assert len(caught) == 1
+    # NumPy index conventions of base.py:894-928: negative entries wrap, out-of-range raises IndexError
+    sub = P[[-1, 0]]
+    assert np.array_equal(sub.symp_matrix, P.symp_matrix[[-1, 0]]) and np.array_equal(sub.coeff_vec, P.coeff_vec[[-1, 0]])
+    assert P[-2:].n_terms == len(np.arange(-2, 3)) and P[np.array([True, False, True])].n_terms == 2
+    try:
+        P[[3]]
+    except IndexError:
+        pass
+    else:
+        raise AssertionError("index 3 of a 3-term operator must raise IndexError")
     df = P.to_dataframe()
     assert list(df['Pauli terms']) == ['XX', 'ZY', 'II']
     assert np.allclose(df['Coefficients (real)'], [1, 0, -0.5]) and np.allclose(df['Coefficients (imaginary)'], [0, 2, 0])
