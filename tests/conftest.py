@@ -37,7 +37,7 @@ def pytest_collection_modifyitems(config, items):
                 item.add_marker(skip)
 
 
-_DOUBLED_FILES = ("test_gpu_api.py", "test_gpu_api_ext.py", "test_gpu_ops_ext.py")
+_DOUBLED_FILES = ("test_gpu_api.py", "test_gpu_api_ext.py", "test_gpu_ops_ext.py", "test_gpu_replay.py")
 
 
 @pytest.fixture(autouse=True)

@@ -85,3 +85,19 @@ def test_compat_serves_import_symmer(host_ops):
     finally:
         compat.uninstall()
     assert "symmer" not in sys.modules and "symmer.operators.utils" not in sys.modules
+
+
+def test_replay_of_the_reference_on_host_double(host_ops):
+    """tests/replay_cases.py: the API script recorded on the REAL reference, replayed on this engine (host logic here;
+    tests/test_gpu_replay.py replays it on the CUDA kernels)."""
+    import os
+    import types
+    import replay_cases
+    import symmer_b200
+    stored = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "replay_vectors.npz")))
+    api = types.SimpleNamespace(PauliwordOp=symmer_b200.PauliwordOp, QuantumState=symmer_b200.QuantumState,
+                                IndependentOp=symmer_b200.IndependentOp, QubitTapering=symmer_b200.QubitTapering)
+    check = replay_cases.Checker(stored)
+    replay_cases.run(api, check)
+    assert check.checked == sum(1 for k in stored if k.endswith("/kind") and not k.endswith("stab_input/kind"))
+    assert check.checked > 700
