@@ -684,13 +684,14 @@ class PauliwordOp:
                     members[len(members)] = [t]
             return {key: ordered[idx] for key, idx in members.items()}
         import networkx as nx
-        graph = self.get_graph(edge_relation=edge_relation)
-        inverted_graph = nx.complement(graph)
-        col_map = nx.greedy_color(inverted_graph, strategy=strategy, interchange=colouring_interchange)
-        cliques = {}
-        for p_index, colour in col_map.items():
-            cliques[colour] = cliques.get(colour, PauliwordOp.from_list(['I' * self.n_qubits], [0])) + self[p_index]
-        return cliques
+        colour_of = nx.greedy_color(nx.complement(self.get_graph(edge_relation=edge_relation)), strategy=strategy,
+                                    interchange=colouring_interchange)
+        # the reference adds the terms of a colour one at a time to 0*I...I (a dedup per term); gathering the member
+        # rows on the device and merging once gives the same operator: same first-occurrence order, same sums
+        members: Dict[int, list] = {}
+        for term_index, colour in colour_of.items():
+            members.setdefault(colour, []).append(term_index)
+        return {colour: self[idx].cleanup() for colour, idx in members.items()}
 
     # ------------------------------------------------------------------ a8 rotations (base.py:1090-1186)
     def _rotation_step(self, Pword: "PauliwordOp", angle, threshold: float = 1e-18):
@@ -848,28 +849,34 @@ class PauliwordOp:
         raise NotImplementedError('not done yet. Full function at: from symmer.operators.anticommuting_op.conjugate_Pop_with_R')
 
     def jordan_generator_reconstruction(self, generators: "PauliwordOp"):
-        """base.py:562-602: reconstruction under the Jordan product PQ = {P,Q}/2 — the symmetry part of the
-        generators plus ONE anticommuting clique at a time, each through the device-resident
-        `generator_reconstruction`."""
+        """base.py:562-602: reconstruction under the Jordan product PQ = {P,Q}/2, where two anticommuting generators
+        may never be multiplied: the generators that commute with everything (symmetries) are combined with ONE
+        group of the remaining generators at a time, each pass through the device-resident
+        `generator_reconstruction`; a term counts as reconstructed if any pass succeeds.
+
+        The groups are the colour classes the reference obtains from `clique_cover(edge_relation='C')` on the
+        non-symmetry part (largest-first greedy colouring of the complement of their commutation graph; singletons
+        when they pairwise anticommute). They are formed here from ONE commutation matrix of the generators, by
+        index, instead of building an operator per group and searching its rows back in the generator list."""
+        import networkx as nx
         from .utils import check_jordan_independent
         assert check_jordan_independent(generators), 'The non-symmetry elements do not pairwise anticommute.'
-        symmetry_mask = np.all(generators.commutes_termwise(generators), axis=1)
-        if np.all(symmetry_mask):
+        commute = generators.adjacency_matrix
+        is_symmetry = commute.all(axis=1)
+        if is_symmetry.all():
             return self.generator_reconstruction(generators)
-        op_reconstruction = np.zeros([self.n_terms, generators.n_terms])
-        successfully_reconstructed = np.zeros(self.n_terms, dtype=bool)
-        ac_terms = generators[~symmetry_mask]
-        gen_symp = generators.symp_matrix
-        for _, clq in ac_terms.clique_cover(edge_relation='C').items():
-            clq_indices = [np.where(np.all(gen_symp == t, axis=1))[0][0] for t in clq.symp_matrix]
-            mask_symmetries_with_P = symmetry_mask.copy()
-            mask_symmetries_with_P[np.array(clq_indices)] = True
-            augmented_symmetries = generators[mask_symmetries_with_P]
-            recon_mat_P, successful_P = self.generator_reconstruction(augmented_symmetries)
-            row, col = np.ix_(successful_P, mask_symmetries_with_P)
-            op_reconstruction[row, col] = recon_mat_P[successful_P]
-            successfully_reconstructed = np.logical_or(successfully_reconstructed, successful_P)
-        return op_reconstruction.astype(int), successfully_reconstructed
+        symmetry_idx, other_idx = np.flatnonzero(is_symmetry), np.flatnonzero(~is_symmetry)
+        among_others = commute[np.ix_(other_idx, other_idx)] & ~np.eye(len(other_idx), dtype=bool)
+        colour_of = nx.greedy_color(nx.complement(nx.from_numpy_array(among_others)), strategy='largest_first')
+        recon = np.zeros((self.n_terms, generators.n_terms), dtype=int)
+        reconstructed = np.zeros(self.n_terms, dtype=bool)
+        for colour in sorted(set(colour_of.values())):
+            group = other_idx[[node for node, c in colour_of.items() if c == colour]]
+            columns = np.sort(np.concatenate([symmetry_idx, group]))       # generator order is kept inside a pass
+            part, ok = self.generator_reconstruction(generators[columns])
+            recon[np.ix_(ok, columns)] = part[ok]
+            reconstructed |= ok
+        return recon, reconstructed
 
 
 def _i_pow(k: torch.Tensor) -> torch.Tensor:
