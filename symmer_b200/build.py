@@ -45,8 +45,8 @@ def build(force=False, verbose=False):
                 sys.stderr.write(res.stdout + res.stderr)
             if res.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}")
-            with open(obj + ".ptxas.txt", "w") as f:
-                f.write(res.stderr)
+            with open(obj + ".ptxas.txt", "w") as f:      # register / spill report, without the per-run compile times
+                f.write("".join(ln for ln in res.stderr.splitlines(keepends=True) if "Compile time" not in ln))
         objs.append(obj)
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
