@@ -120,6 +120,24 @@ def main():
             same_op(f"{rnd} rotate {angle}", A_r.perform_rotations([(Q_r, angle)]), A_n.perform_rotations([(Q_n, angle)]),
                     ordered=False)
         same_op(f"{rnd} tensor", A_r.tensor(B_r), A_n.tensor(B_n), ordered=False)
+        from symmer.operators import utils as ru
+        from symmer_b200 import utils as nu
+        same(f"{rnd} single csr", ru.symplectic_to_sparse_matrix(A_r.symp_matrix[0], 0.7 - 0.2j).toarray(),
+             nu.symplectic_to_sparse_matrix(A_n.symp_matrix[0], 0.7 - 0.2j).toarray())
+        v_r, c_r = ru.mul_symplectic(A_r.symp_matrix[0], 0.5j, B_r.symp_matrix[0], 2.0)
+        v_n, c_n = nu.mul_symplectic(A_n.symp_matrix[0], 0.5j, B_n.symp_matrix[0], 2.0)
+        same(f"{rnd} mul_symplectic row", v_r, v_n)
+        same(f"{rnd} mul_symplectic coeff", c_r, c_n)
+        same(f"{rnd} safe dict", {k: complex(*v) for k, v in ru.safe_PauliwordOp_to_dict(A_r).items()},
+             {k: complex(*v) for k, v in nu.safe_PauliwordOp_to_dict(A_n).items()})
+        same(f"{rnd} bits to int", ru.binary_array_to_int(A_r.symp_matrix), nu.binary_array_to_int(A_n.symp_matrix))
+        same(f"{rnd} popcount", [ru.count1_in_int_bitstring(v) for v in (0, 1, 255, 2 ** 31 + 5, rnd * 977)],
+             [nu.count1_in_int_bitstring(v) for v in (0, 1, 255, 2 ** 31 + 5, rnd * 977)])
+        ang = np.random.default_rng(rnd).random(4) * 3
+        same(f"{rnd} sphere", ru.unit_n_sphere_cartesian_coords(ang), nu.unit_n_sphere_cartesian_coords(ang))
+        same(f"{rnd} binomial", ru.binomial_coefficient(4.5, 3), nu.binomial_coefficient(4.5, 3))
+        same_op(f"{rnd} noncontextual sweep", ru.perform_noncontextual_sweep(A_r.cleanup().sort()),
+                nu.perform_noncontextual_sweep(A_n.cleanup().sort()))
         # states
         np.random.seed(rnd + 7)
         psi_r = ref.QuantumState.random(n, 5)

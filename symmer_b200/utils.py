@@ -231,3 +231,72 @@ def unpack_rows_host(xz: np.ndarray, n_qubits: int) -> np.ndarray:
     by = (xz[:, :, None] >> (np.arange(8, dtype=np.uint64) * np.uint64(8))).astype(np.uint8)      # little-endian bytes
     bits = np.unpackbits(by, axis=-1, bitorder="little").reshape(M, 2, W * 64)
     return np.hstack([bits[:, 0, :n_qubits], bits[:, 1, :n_qubits]]).astype(bool)
+
+
+# ---------------------------------------------------------------------------------------------- small helpers
+def symplectic_to_sparse_matrix(symp_vec, coeff):
+    """utils.py:182-228: CSR matrix of one Pauli term (through the device CSR emitter of `to_sparse_matrix`)."""
+    from .base import PauliwordOp
+    return PauliwordOp(np.asarray(symp_vec, dtype=bool).reshape(1, -1), [coeff]).to_sparse_matrix
+
+
+def mul_symplectic(symp_vec1, coeff1, symp_vec2, coeff2):
+    """utils.py:429-470: product of two Pauli terms with its phase — one cross term of the device product kernel."""
+    from .base import PauliwordOp
+    left = PauliwordOp(np.asarray(symp_vec1, dtype=bool).reshape(1, -1), [coeff1])
+    right = PauliwordOp(np.asarray(symp_vec2, dtype=bool).reshape(1, -1), [coeff2])
+    out = left.cross_terms(right)
+    return out.symp_matrix[0], out.coeff_vec[0]
+
+
+def safe_PauliwordOp_to_dict(op):
+    """utils.py:401-413: {pauli string: (real, imag)}."""
+    return {term: (c.real, c.imag) for term, c in op.to_dictionary.items()}
+
+
+def safe_QuantumState_to_dict(psi):
+    """utils.py:415-427: {bit string: (real, imag)}."""
+    return {bits: (c.real, c.imag) for bits, c in psi.to_dictionary.items()}
+
+
+def count1_in_int_bitstring(i) -> int:
+    """utils.py:165-180: number of set bits of a 32-bit integer."""
+    return bin(int(i) & 0xFFFFFFFF).count('1')
+
+
+def binary_array_to_int(bin_arr) -> np.ndarray:
+    """utils.py:618-638: rows of bits (most significant first) as integers; floats from 64 columns on, like the reference."""
+    bin_arr = np.asarray(bin_arr)
+    width = bin_arr.shape[1]
+    weights = 2 ** np.arange(width - 1, -1, -1) if width < 64 else 2 ** np.arange(width - 1, -1, -1, dtype=float)
+    return bin_arr @ weights
+
+
+def unit_n_sphere_cartesian_coords(angles) -> np.ndarray:
+    """utils.py:472-485: the n+1 Cartesian coordinates of the point of the unit n-sphere with the given n angles."""
+    angles = np.asarray(angles, dtype=float)
+    sines = np.concatenate([[1.0], np.cumprod(np.sin(angles))])
+    return np.concatenate([sines[:-1] * np.cos(angles), sines[-1:]])
+
+
+def binomial_coefficient(n, k):
+    """utils.py:487-502: n choose k for non-integer n."""
+    out = 1
+    for r in range(k):
+        out *= (n - r) / (k - r)
+    return out
+
+
+def perform_noncontextual_sweep(operator):
+    """utils.py:592-616: one pass over an ordered operator keeping every term that leaves the kept set noncontextual.
+    The reference grows the commutation matrix term by term; here the whole matrix comes from ONE device call and
+    the sweep indexes into it."""
+    if operator.n_terms == 0:
+        return operator
+    adjacency = operator.adjacency_matrix
+    kept = [0]
+    for index in range(1, operator.n_terms):
+        trial = kept + [index]
+        if check_adjmat_noncontextual(adjacency[np.ix_(trial, trial)]):
+            kept = trial
+    return operator[kept]

@@ -556,6 +556,16 @@ def case_misc_methods(api, G):
         pass
     else:
         raise AssertionError("index 3 of a 3-term operator must raise IndexError")
+    from symmer_b200 import utils as u
+    row, c = u.mul_symplectic(np.array([1, 0, 0, 0], dtype=bool), 1.0, np.array([0, 0, 1, 0], dtype=bool), 1.0)   # X * Z = -iY
+    assert np.array_equal(row, [True, False, True, False]) and np.isclose(c, -1j)
+    assert np.allclose(u.symplectic_to_sparse_matrix(np.array([1, 1], dtype=bool), 2.0).toarray(), [[0, -2j], [2j, 0]])
+    assert u.safe_PauliwordOp_to_dict(P) == {'XX': (1.0, 0.0), 'ZY': (0.0, 2.0), 'II': (-0.5, 0.0)}
+    assert u.count1_in_int_bitstring(0b1011) == 3 and np.array_equal(u.binary_array_to_int(np.array([[1, 0, 1], [0, 1, 1]])), [5, 3])
+    assert np.isclose(np.linalg.norm(u.unit_n_sphere_cartesian_coords([0.3, 1.2, 2.0])), 1) and np.isclose(u.binomial_coefficient(5, 2), 10)
+    contextual = PauliwordOp.from_list(['XI', 'IX', 'ZI', 'IZ', 'II'], [5, 4, 3, 2, 1])
+    swept = u.perform_noncontextual_sweep(contextual)
+    assert swept.is_noncontextual and swept.n_terms == 4 and not contextual.is_noncontextual
     df = P.to_dataframe()
     assert list(df['Pauli terms']) == ['XX', 'ZY', 'II']
     assert np.allclose(df['Coefficients (real)'], [1, 0, -0.5]) and np.allclose(df['Coefficients (imaginary)'], [0, 2, 0])
