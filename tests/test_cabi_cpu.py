@@ -84,6 +84,8 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("pauli_oracle", "oracle") or "import oracle" not in src, f
                 assert "from oracle" not in src and "import oracle" not in src and "pauli_oracle" not in src, f
+                # ... nor the NumPy test double of the kernels (tests/_host_double.py) or its developer switch
+                assert "_host_double" not in src and "host_double" not in src and "SYMMER_HOST_DOUBLE" not in src, f
 
 
 def test_host_string_ingest():
