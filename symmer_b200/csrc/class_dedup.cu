@@ -1,0 +1,478 @@
+// Class-local duplicate detection for large products (ordered-tile mode) — replaces the global radix
+// sort of one 8-byte record per cross term (symmer/operators/utils.py:271, qiskit `unordered_unique`).
+//
+// The row sketch is GF(2)-linear, so any fixed set of its bits is a linear CLASS function:
+//   class(A[p] ^ B[q]) = class(A[p]) ^ class(B[q]).
+// With the rows of A grouped by class, the cross terms of class c are exactly the pairs
+// (p in A_a, q) with a = class(B[q]) ^ c — they can be ENUMERATED from two small L2-resident tables, and
+// equal rows (equal sketches) always fall into the same class. One CTA therefore owns one class
+// (~4000 cross terms): it lists the class's pairs in shared memory, hashes them into a shared-memory
+// table with plain stores (multi-round "last writer wins", no atomics) and learns which records have a
+// same-hash mate. Records without one are unique rows: nothing is written for them, no record of theirs
+// ever reaches HBM. Records with a mate (true duplicates, or the rare hash collision) are sorted by
+// (hash, t) inside the CTA and appended to the candidate array, which the exact group pass (link / phase /
+// sum in dedup.cu: word-by-word row compare, np.add.at order) consumes. A class that does not fit
+// the CTA (heavily duplicated or low-dimensional operands) spills its records to the overflow array,
+// which takes the ordinary global sort. No tensor cores: integer/bit work on L2-resident tables,
+// shared-memory bound.
+#include <algorithm>
+
+#include "rows.cuh"
+#include "sort.cuh"
+
+namespace symb {
+
+// GF(2)-linear in the sketch (XOR of shifted copies); independent of the parity functionals of owner.cu
+__host__ __device__ __forceinline__ uint32_t cd_class_of(uint64_t sk, int k) {
+    const uint64_t y = sk ^ (sk >> 21) ^ (sk >> 43);
+    return (uint32_t)(y >> 5) & ((1u << k) - 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// class tables. Table index of (block b, class a) = (b << (k + 1)) | a: XOR with a class only touches the low k bits.
+//   vkey[v]  = (b << (k+1)) | class(B[q_v])   visit v = row q_v of B in block b (all blocks, flattened)
+//   vq[v]    = q_v
+//   cnt8[i]  = min(255, rows of A in (block, class) i)      — 62 % of the visits end here, in L1
+//   off[i]   = first entry of (block, class) i in `look`;  look = rows of A grouped by (block, class)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cd_block_of(const uint32_t *base, int nblk, uint32_t e) {
+    int b = 0;
+    while (b + 1 < nblk && e >= base[b + 1]) ++b;
+    return b;
+}
+
+// threads [0, n_entries): histogram of the (block, class) of every row of A; threads [0, n_visits): visit keys
+__global__ void __launch_bounds__(256) cd_keys_kernel(ClassJob J, const uint64_t *__restrict__ a_sk, uint32_t *__restrict__ cnt,
+                                                       uint32_t *__restrict__ vkey, uint32_t *__restrict__ vq) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < J.n_entries) {
+        const int b = cd_block_of(J.entry_base, J.nblk, e);
+        const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
+        atomicAdd(cnt + (((uint32_t)b << (J.k + 1)) | cd_class_of(a_sk[p], J.k)), 1u);
+    }
+    if (e < J.n_visits) {
+        const int b = cd_block_of(J.visit_base, J.nblk, e);
+        const uint32_t q = J.q0[b] + (e - J.visit_base[b]);
+        vkey[e] = ((uint32_t)b << (J.k + 1)) | cd_class_of(J.b_sk[q], J.k);
+        vq[e] = q;
+    }
+}
+
+// threads [0, n_entries): place the rows of A; threads [0, table size): byte counts
+__global__ void __launch_bounds__(256) cd_place_kernel(ClassJob J, const uint64_t *__restrict__ a_sk, const uint32_t *__restrict__ off,
+                                                        uint32_t *__restrict__ cursor, uint4 *__restrict__ look,
+                                                        uint8_t *__restrict__ cnt8, uint32_t tab) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < J.n_entries) {
+        const int b = cd_block_of(J.entry_base, J.nblk, e);
+        const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
+        const uint64_t sk = a_sk[p];
+        const uint32_t key = ((uint32_t)b << (J.k + 1)) | cd_class_of(sk, J.k);
+        const uint32_t pos = off[key] + atomicAdd(cursor + key, 1u);
+        look[pos] = make_uint4((uint32_t)sk, (uint32_t)(sk >> 32), p, 0u);
+    }
+    if (e < tab) {
+        const uint32_t n = (e + 1 < tab ? off[e + 1] : J.n_entries) - off[e];
+        cnt8[e] = (uint8_t)(n < 255u ? n : 255u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the class kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t cd_look_sketch(const uint4 &le) { return ((uint64_t)le.y << 32) | le.x; }
+
+// Records are ordered by their position in the block-major enumeration of the cross terms (block, then q, then p)
+// — for a single block that IS t = q*M + p, the reference's order (base.py:783-792); for a block list it is the
+// order in which the tiled emission writes the survivors. ord <-> t:
+__device__ __forceinline__ uint32_t cd_ord_of(const ClassJob &J, int b, uint32_t p, uint32_t q) {
+    return J.rec_off[b] + (q - J.q0[b]) * J.m_blk[b] + (p - J.p0[b]);
+}
+__device__ __forceinline__ uint32_t cd_t_of_ord(const ClassJob &J, uint32_t ord) {
+    const int b = J.nblk == 1 ? 0 : cd_block_of(J.rec_off, J.nblk, ord);
+    const uint32_t local = ord - J.rec_off[b];
+    const uint32_t ql = local / J.m_blk[b];
+    return (J.q0[b] + ql) * J.M_total + J.p0[b] + (local - ql * J.m_blk[b]);
+}
+
+// Block-wide exclusive prefix of one value per thread (two barriers); *carry accumulates the block total.
+template <int THREADS>
+__device__ __forceinline__ uint32_t cd_block_prefix(uint32_t x, uint32_t *s_warp, uint32_t *carry) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t t = lane < THREADS / 32 ? s_warp[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += y;
+        }
+        s_warp[lane] = ti - t;
+        if (lane == 31) s_warp[32] = *carry + ti;   // new carry (written after everyone read the old one below)
+    }
+    __syncthreads();
+    const uint32_t base = *carry + s_warp[wid] + inc - x;
+    __syncthreads();
+    if (threadIdx.x == 0) *carry = s_warp[32];
+    return base;
+}
+
+// Enumerates the pairs of class c: every row q of B (all blocks) looks up the rows of A whose class is
+// class(B[q]) ^ c. Two steps per chunk of THREADS * VPT visits: every thread counts the pairs of its visits
+// (one coalesced key load and one byte from the L1-resident count table per visit), one block-wide prefix sum
+// gives it a private range of the list, then it writes its pairs — no atomics, no warp votes.
+// OVER = false: pairs go to the shared-memory list (beyond CAP they are only counted);
+// OVER = true: the records themselves go to the overflow array at over_base.
+template <int THREADS, int CAP, bool OVER>
+__device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, uint32_t *s_count, uint32_t *s_warp, uint2 *pairs,
+                                             uint64_t *__restrict__ over, uint32_t over_base) {
+    constexpr int VPT = 12;
+    const int tid = threadIdx.x;
+    for (uint32_t v0 = 0; v0 < J.n_visits; v0 += THREADS * VPT) {
+        uint32_t idx[VPT], n[VPT];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            const uint32_t v = v0 + u * THREADS + tid;
+            idx[u] = v < J.n_visits ? (__ldg(J.vkey + v) ^ c) : 0xffffffffu;
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            n[u] = idx[u] != 0xffffffffu ? (uint32_t)__ldg(J.cnt8 + idx[u]) : 0u;
+            if (n[u] == 255u) n[u] = __ldg(J.off + idx[u] + 1) - __ldg(J.off + idx[u]);
+            sum += n[u];
+        }
+        uint32_t pos = cd_block_prefix<THREADS>(sum, s_warp, s_count);
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            if (n[u] == 0u) continue;
+            uint32_t lo = __ldg(J.off + idx[u]);
+            const uint32_t q = __ldg(J.vq + v0 + u * THREADS + tid);
+            if (!OVER) {
+                for (uint32_t j = 0; j < n[u]; ++j, ++pos, ++lo)
+                    if (pos < (uint32_t)CAP) pairs[pos] = make_uint2(lo, q);
+            } else {
+                const uint64_t skq = J.b_sk[q];
+                for (uint32_t j = 0; j < n[u]; ++j, ++pos, ++lo) {
+                    const uint4 le = J.look[lo];
+                    const uint64_t hm = mix64(cd_look_sketch(le) ^ skq) & J.key_mask;
+                    const uint64_t ord = cd_ord_of(J, (int)(idx[u] >> (J.k + 1)), le.z, q);
+                    over[(size_t)over_base + pos] = (((hm & ~0xffffull) >> (J.tb + 2)) << (J.tb + 2)) | (ord << 2);
+                }
+            }
+        }
+    }
+}
+
+// slot of a record in round r: a function of its 48 hash bits only (records with equal hash bits share their whole
+// slot sequence, which is what makes the mate detection complete). xk = the hash bits folded to 32.
+__device__ __forceinline__ uint32_t cd_fold(uint64_t ent) {
+    return (uint32_t)(ent >> 32) ^ ((uint32_t)(ent >> 16) & 0xffffu) * 0x9E3779B1u;
+}
+
+// counters: [0] candidates written, [1] overflow records written, [2] overflowed classes, [3] = [0] + [1] (set afterwards)
+template <int THREADS, int CAP, int LOG_SLOTS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, ProductRows rows, TileMap tm, double thr,
+                                                                     uint64_t *__restrict__ cand, uint64_t *__restrict__ over,
+                                                                     uint32_t *__restrict__ counters) {
+    constexpr int SLOTS = 1 << LOG_SLOTS;
+    constexpr int RPT = CAP / THREADS;
+    static_assert(CAP % THREADS == 0 && CAP <= 65536 && CAP <= SLOTS, "record ids are 16 bits; candidates are sorted inside the table");
+    static_assert(RPT <= 16, "one state bit per record in a register");
+    extern __shared__ __align__(16) unsigned char cd_smem[];
+    uint64_t *table = reinterpret_cast<uint64_t *>(cd_smem);
+    uint2 *pairs = reinterpret_cast<uint2 *>(cd_smem + (size_t)SLOTS * 8);
+    uint8_t *mate = cd_smem + (size_t)SLOTS * 8 + (size_t)CAP * 8;
+    __shared__ uint32_t s_count, s_ncand, s_base;
+    __shared__ uint32_t s_warp[33];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t K = 1u << J.k;
+    const bool check_thr = !(thr < 0.0 || rows.all_pass());
+
+    for (uint32_t c = blockIdx.x; c < K; c += gridDim.x) {
+        if (tid == 0) {
+            s_count = 0;
+            s_ncand = 0;
+        }
+        for (int i = tid; i < CAP / 4; i += THREADS) reinterpret_cast<uint32_t *>(mate)[i] = 0u;
+        __syncthreads();
+        cd_enumerate<THREADS, CAP, false>(J, c, &s_count, s_warp, pairs, nullptr, 0u);
+        __syncthreads();
+        const uint32_t total = s_count;
+        if (total > (uint32_t)CAP) {   // the class does not fit: its records take the global sort
+            __syncthreads();           // everyone has read s_count
+            if (tid == 0) {
+                s_base = atomicAdd(counters + 1, total);
+                atomicAdd(counters + 2, 1u);
+                s_count = 0;
+            }
+            __syncthreads();
+            cd_enumerate<THREADS, CAP, true>(J, c, &s_count, s_warp, nullptr, over, s_base);
+            __syncthreads();
+            continue;
+        }
+        // ---- records of this thread: [hash : 48 | local id : 16]
+        uint64_t ent[RPT];
+        uint32_t xk[RPT];
+        uint32_t unres = 0, candm = 0, winm = 0;   // one bit per record: no slot yet / saw a same-hash record / holds a slot
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const uint32_t i = tid + j * THREADS;
+            ent[j] = 0;
+            xk[j] = 0;
+            if (i < total) {
+                const uint2 pr = pairs[i];
+                const uint4 le = __ldg(J.look + pr.x);
+                const uint64_t hm = mix64(cd_look_sketch(le) ^ __ldg(J.b_sk + pr.y)) & J.key_mask;
+                ent[j] = (hm & ~0xffffull) | i;
+                xk[j] = cd_fold(ent[j]);
+                unres |= 1u << j;
+            }
+        }
+        for (int round = 0; round < CD_MAX_ROUNDS; ++round) {
+            const uint32_t mult = 0x9E3779B1u + 2u * (uint32_t)round * 0x632BE5ABu;   // odd for every round
+            const uint32_t add = (uint32_t)round * 0x7F4A7C15u;
+            if (unres) {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j)
+                    if ((unres >> j) & 1u) table[(xk[j] * mult + add) >> (32 - LOG_SLOTS)] = ent[j];
+            }
+            if (!__syncthreads_or(unres != 0u)) break;
+            if (unres) {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    if ((unres >> j) & 1u) {
+                        const uint64_t v = table[(xk[j] * mult + add) >> (32 - LOG_SLOTS)];
+                        if (v == ent[j]) {
+                            winm |= 1u << j;
+                            unres &= ~(1u << j);
+                        } else if (((v ^ ent[j]) >> 16) == 0ull) {
+                            mate[v & 0xffffull] = 1;
+                            candm |= 1u << j;
+                            unres &= ~(1u << j);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- candidates: saw a mate, was seen by one, or never found a free slot (then its mates did not either)
+        candm |= unres;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j)
+            if (((winm >> j) & 1u) && mate[tid + j * THREADS] != 0) candm |= 1u << j;
+        const bool any_c = __any_sync(0xffffffffu, candm != 0u);
+        if (any_c || check_thr) {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const uint32_t i = tid + j * THREADS;
+                const bool cnd = (candm >> j) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, cnd);
+                uint32_t base = 0;
+                if (bal != 0u) {
+                    if (lane == 0) base = atomicAdd(&s_ncand, (uint32_t)__popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                }
+                if (cnd || (check_thr && i < total)) {
+                    const uint2 pr = pairs[i];
+                    const uint32_t p = J.look[pr.x].z;
+                    if (cnd) {
+                        const int b = J.nblk == 1 ? 0 : cd_block_of(J.entry_base, J.nblk, pr.x);
+                        table[base + __popc(bal & lt)] = ((ent[j] >> (64 - J.hbits)) << 32) | cd_ord_of(J, b, p, pr.y);
+                    } else {   // unique row: survives unless its own coefficient fails the threshold
+                        const uint32_t t = pr.y * J.M_total + p;
+                        double re, im;
+                        rows.coeff_unphased(t, re, im);
+                        if (!keep_test(re, im, thr)) tm.mark_dropped(t);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nc = s_ncand;
+        if (nc > 0u) {
+            uint32_t np = 2;
+            while (np < nc) np <<= 1;
+            for (uint32_t i = nc + tid; i < np; i += THREADS) table[i] = ~0ull;
+            // bitonic sort of [hash | ord]: equal-hash records become neighbours, in enumeration order
+            for (uint32_t size = 2; size <= np; size <<= 1) {
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    __syncthreads();
+                    for (uint32_t i = tid; i < (np >> 1); i += THREADS) {
+                        const uint32_t pos = 2 * i - (i & (stride - 1));
+                        const uint64_t a = table[pos], b = table[pos + stride];
+                        const bool up = (pos & size) == 0u;
+                        if ((a > b) == up) {
+                            table[pos] = b;
+                            table[pos + stride] = a;
+                        }
+                    }
+                }
+            }
+            if (tid == 0) s_base = atomicAdd(counters, nc);
+            __syncthreads();
+            const uint32_t gb = s_base;
+            for (uint32_t i = tid; i < nc; i += THREADS) {
+                const uint64_t key = table[i];
+                cand[(size_t)gb + i] = ((key >> 32) << (64 - J.hbits)) | ((uint64_t)cd_t_of_ord(J, (uint32_t)key) << 2);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void cd_total_kernel(uint32_t *counters) { counters[3] = counters[0] + counters[1]; }
+
+// overflow records were sorted on (hash, ord): put t back into their term field
+__global__ void __launch_bounds__(256) cd_ord_to_t_kernel(ClassJob J, uint64_t *__restrict__ recs, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t rec = recs[i];
+    const uint64_t field = ((1ull << J.tb) - 1ull) << 2;
+    recs[i] = (rec & ~field) | ((uint64_t)cd_t_of_ord(J, (uint32_t)((rec & field) >> 2)) << 2);
+}
+
+int class_ord_to_t(const ClassJob &J, uint64_t *recs, uint32_t n, cudaStream_t st) {
+    if (n == 0 || (J.nblk == 1 && J.p0[0] == 0 && J.q0[0] == 0 && J.m_blk[0] == J.M_total)) return SYM_OK;   // ord == t
+    cd_ord_to_t_kernel<<<(n + 255) / 256, 256, 0, st>>>(J, recs, n);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int g_class_dedup = 1;   // tuning knob 10: 1 (default) = class-local duplicate detection for ordered-tile products, 0 = global record sort
+
+extern int g_class_variant;
+static int class_cap(int variant) { return variant == 1 ? 9216 : 4608; }
+
+bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t T, int tb, uint64_t key_mask, ClassJob &J,
+                    bool ignore_knob) {   // ignore_knob: workspace sizing — the shape with the larger tables
+    if ((!g_class_dedup && !ignore_knob) || nblk < 1 || nblk > CD_MAX_BLOCKS || T < 1 || T >= ((int64_t)1 << 32)) return false;
+    int64_t entries = 0, visits = 0, recs = 0;
+    for (int b = 0; b < nblk; ++b) {
+        J.entry_base[b] = (uint32_t)entries;
+        J.visit_base[b] = (uint32_t)visits;
+        J.rec_off[b] = (uint32_t)recs;
+        J.p0[b] = blocks[b].p0;
+        J.q0[b] = blocks[b].q0;
+        J.m_blk[b] = blocks[b].m_blk > 0 ? blocks[b].m_blk : 1u;
+        entries += blocks[b].m_blk;
+        visits += blocks[b].nq;
+        recs += (int64_t)blocks[b].m_blk * blocks[b].nq;
+    }
+    for (int b = nblk; b <= CD_MAX_BLOCKS; ++b) {
+        J.entry_base[b] = (uint32_t)entries;
+        J.visit_base[b] = (uint32_t)visits;
+        J.rec_off[b] = (uint32_t)recs;
+        if (b < CD_MAX_BLOCKS) {
+            J.p0[b] = J.q0[b] = 0;
+            J.m_blk[b] = 1;
+        }
+    }
+    if (entries >= ((int64_t)1 << 31) || visits >= ((int64_t)1 << 31)) return false;
+    // classes: the average class fills at most 85 % of a CTA's pair list; small products still get enough classes
+    // to occupy the GPU
+    J.variant = ignore_knob ? 0 : g_class_variant;
+    int64_t target = (int64_t)(0.85 * class_cap(J.variant));
+    if (T / 1024 < target) target = T / 1024 > 256 ? T / 1024 : 256;
+    int k = 0;
+    while (k < 22 && (T >> k) > target) ++k;
+    // every class visits every row of B: give up when that costs far more than the records themselves
+    if ((visits << k) > 64 * T + ((int64_t)1 << 22)) return false;
+    J.k = k;
+    J.nblk = nblk;
+    J.n_entries = (uint32_t)entries;
+    J.n_visits = (uint32_t)visits;
+    J.M_total = (uint32_t)M_total;
+    J.key_mask = key_mask;
+    J.tb = tb;
+    J.hbits = 62 - tb < 32 ? 62 - tb : 32;
+    J.b_sk = nullptr;
+    J.off = nullptr;
+    J.look = nullptr;
+    return true;
+}
+
+static size_t cd_table_elems(const ClassJob &J) { return (size_t)J.nblk << (J.k + 1); }
+
+size_t class_job_ws_bytes(const ClassJob &J) {
+    const size_t tab = cd_table_elems(J);
+    return 2 * arena_need(tab, 4) + arena_need(tab, 1) + arena_need(scan_scratch_elems((int64_t)tab), 4) +
+           arena_need(J.n_entries ? J.n_entries : 1, 16) + 2 * arena_need(J.n_visits ? J.n_visits : 1, 4) + 1024;
+}
+
+int g_class_variant = 1;    // tuning knob 11: CTA shape of the class kernel (0: 512 threads x 2 CTAs/SM, 1 (default, measured faster): 1024 threads x 1)
+
+template <int THREADS, int CAP, int LOG_SLOTS, int MINB>
+static int cd_launch(const ClassJob &J, const ProductRows &rows, const TileMap &tm, double thr, uint64_t *cand, uint64_t *over,
+                     uint32_t *counters, cudaStream_t st) {
+    constexpr size_t smem = ((size_t)1 << LOG_SLOTS) * 8 + (size_t)CAP * 8 + CAP;
+    auto kern = class_dedup_kernel<THREADS, CAP, LOG_SLOTS, MINB>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        SYM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[dev] = true;
+    }
+    const uint32_t K = 1u << J.k;
+    const unsigned grid = (unsigned)std::min<uint32_t>(K, (uint32_t)num_sms() * (uint32_t)MINB);
+    kern<<<grid, THREADS, smem, st>>>(J, rows, tm, thr, cand, over, counters);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+// Builds the class tables in `ws` and runs the class kernel. cand / over: capacity T records each.
+int class_dedup_run(ClassJob &J, const uint64_t *a_sk, const uint64_t *b_sk, const ProductRows &rows, const TileMap &tm,
+                    double thr, uint64_t *cand, uint64_t *over, uint32_t *counters, void *ws, size_t ws_bytes,
+                    cudaStream_t st) {
+    Arena ar(ws, ws_bytes);
+    const size_t tab = cd_table_elems(J);
+    uint32_t *off = ar.take<uint32_t>(tab);
+    uint32_t *cursor = ar.take<uint32_t>(tab);
+    uint8_t *cnt8 = ar.take<uint8_t>(tab);
+    uint32_t *scratch = ar.take<uint32_t>(scan_scratch_elems((int64_t)tab));
+    uint4 *look = ar.take<uint4>(J.n_entries ? J.n_entries : 1);
+    uint32_t *vkey = ar.take<uint32_t>(J.n_visits ? J.n_visits : 1);
+    uint32_t *vq = ar.take<uint32_t>(J.n_visits ? J.n_visits : 1);
+    if (!vq) {
+        set_error("workspace arena exhausted (class tables)");
+        return SYM_E_WORKSPACE;
+    }
+    SYM_CUDA_OK(cudaMemsetAsync(off, 0, sizeof(uint32_t) * tab, st));
+    SYM_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * tab, st));
+    SYM_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 4, st));
+    J.b_sk = b_sk;
+    J.off = off;
+    J.look = look;
+    J.cnt8 = cnt8;
+    J.vkey = vkey;
+    J.vq = vq;
+    const uint32_t n1 = J.n_entries > J.n_visits ? J.n_entries : J.n_visits;
+    if (n1) {
+        cd_keys_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(J, a_sk, off, vkey, vq);
+        SYM_LAUNCH_OK();
+    }
+    SYM_TRY(scan_exclusive_u32(off, off, (int64_t)tab, nullptr, scratch, st));
+    const uint32_t n2 = J.n_entries > (uint32_t)tab ? J.n_entries : (uint32_t)tab;
+    cd_place_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(J, a_sk, off, cursor, look, cnt8, (uint32_t)tab);
+    SYM_LAUNCH_OK();
+    if (class_cap(J.variant) == 9216) SYM_TRY((cd_launch<1024, 9216, 14, 1>(J, rows, tm, thr, cand, over, counters, st)));
+    else SYM_TRY((cd_launch<512, 4608, 13, 2>(J, rows, tm, thr, cand, over, counters, st)));
+    cd_total_kernel<<<1, 1, 0, st>>>(counters);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+}  // namespace symb

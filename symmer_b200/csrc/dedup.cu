@@ -27,12 +27,13 @@ constexpr uint8_t FLAG_HEAD = 0, FLAG_PREV = 1, FLAG_LINK = 2;
 // PREV, further back -> LINK (position stored in link[]).
 template <class Rows>
 __device__ __forceinline__ void link_one(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t i,
-                                         int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
+                                         int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link,
+                                         int64_t lo = 0) {
     uint8_t f = FLAG_HEAD;
-    if (i > 0) {
+    if (i > lo) {
         const uint64_t ri = sr[i];
         const uint32_t ti = fmt.t(ri);
-        for (int64_t j = i - 1; j >= 0; --j) {
+        for (int64_t j = i - 1; j >= lo; --j) {
             const uint64_t rj = sr[j];
             if (((ri ^ rj) >> sort_shift) != 0) break;   // left the bucket
             if (fmt.same_hash(ri, rj) && rows.equal(ti, fmt.t(rj))) {
@@ -61,27 +62,41 @@ __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const 
 // `nreg` regions of `cap` entries with one counter each: CTA b of the classify pass appends to region
 // b % nreg, so no counter is hot (one global counter serialises ~2e6 same-address atomics: 1.5 ms)
 // and a region can never overflow (it receives from at most cap records).
+// Identity form (class mode, work == nullptr): every position of [begin, begin + counts[0]) is on the list,
+// begin and the count live in device memory (the host never learns them before the launch); region r covers
+// positions begin + [r * cap, (r + 1) * cap).
 struct WorkList {
     uint32_t *work;
     uint32_t *counts;
     uint32_t nreg, cap;
+    const uint32_t *begin_ptr = nullptr;
+    __device__ __forceinline__ uint32_t begin() const { return begin_ptr ? *begin_ptr : 0u; }
+    __device__ __forceinline__ uint32_t region_count(uint32_t r) const {
+        if (work) return counts[r];
+        const uint32_t n = counts[0];
+        const uint64_t lo = (uint64_t)r * cap;
+        return n > lo ? (uint32_t)(n - lo < cap ? n - lo : cap) : 0u;
+    }
+    __device__ __forceinline__ uint32_t entry(uint32_t r, uint32_t k) const {
+        return work ? work[(size_t)r * cap + k] : begin() + r * cap + k;
+    }
+    // bounds of the record array the listed positions refer to
+    __device__ __forceinline__ int64_t lo() const { return work ? 0 : (int64_t)begin(); }
+    __device__ __forceinline__ int64_t hi(int64_t T) const { return work ? T : (int64_t)begin() + counts[0]; }
 };
 // consumers: WORK_SPLIT CTAs per region (grid = nreg * WORK_SPLIT), each striding over the region's entries
 constexpr uint32_t WORK_SPLIT = 8;
 #define FOR_EACH_WORK(wl, i)                                                                                     \
     for (uint32_t _r = blockIdx.x / WORK_SPLIT, _k = (blockIdx.x % WORK_SPLIT) * blockDim.x + threadIdx.x,       \
-                  _n = (wl).counts[_r];                                                                          \
+                  _n = (wl).region_count(_r);                                                                    \
          _k < _n; _k += WORK_SPLIT * blockDim.x)                                                                 \
-        if (const uint32_t i = (wl).work[(size_t)_r * (wl).cap + _k]; true)
+        if (const uint32_t i = (wl).entry(_r, _k); true)
 
 template <class Rows>
 __global__ void __launch_bounds__(256) link_work_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int sort_shift,
                                                          WorkList wl, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
-    FOR_EACH_WORK(wl, i) link_one(rows, fmt, sr, (int64_t)i, sort_shift, flag, link);
-}
-
-__device__ __forceinline__ uint8_t keep_test(double re, double im, double thr) {
-    return (thr < 0.0) ? 1 : (hypot(re, im) > thr ? 1 : 0);
+    const int64_t lo = wl.lo();
+    FOR_EACH_WORK(wl, i) link_one(rows, fmt, sr, (int64_t)i, sort_shift, flag, link, lo);
 }
 
 __device__ __forceinline__ int64_t chain_root(const uint8_t *flag, const uint32_t *link, int64_t i) {
@@ -313,12 +328,13 @@ __global__ void __launch_bounds__(256) sum_work_kernel(Rows rows, RecFmt fmt, co
                                                         const uint32_t *__restrict__ link, double thr, double2 *__restrict__ acc,
                                                         uint8_t *__restrict__ multi, TileMap tm) {
     // whole warps walk the region together (a lane without an entry idles) so that they can finish long groups jointly
-    const uint32_t r = blockIdx.x / WORK_SPLIT, n = wl.counts[r];
+    const uint32_t r = blockIdx.x / WORK_SPLIT, n = wl.region_count(r);
+    const int64_t hi = wl.hi(T);
     for (uint32_t k0 = (blockIdx.x % WORK_SPLIT) * blockDim.x + (threadIdx.x & ~31u); k0 < n; k0 += WORK_SPLIT * blockDim.x) {
         const uint32_t k = k0 + (threadIdx.x & 31u);
         const bool valid = k < n;
-        const int64_t i = valid ? (int64_t)wl.work[(size_t)r * wl.cap + k] : 0;
-        sum_warp_step<Rows, false, true, true>(rows, fmt, sr, T, valid, i, sort_shift, flag, link, thr, acc, nullptr, multi, tm);
+        const int64_t i = valid ? (int64_t)wl.entry(r, k) : 0;
+        sum_warp_step<Rows, false, true, true>(rows, fmt, sr, hi, valid, i, sort_shift, flag, link, thr, acc, nullptr, multi, tm);
     }
 }
 
@@ -689,7 +705,7 @@ size_t dedup_ws_bytes(int64_t T) {
            + arena_need(n, 4)                        // slot
            + arena_need(n, 4)                        // kept
            + arena_need(scan_scratch_elems(T), 4)    // scan scratch
-           + arena_need(4, 4) + 4096;
+           + arena_need(16, 4) + 4096;
 }
 
 // Sort on log2(T) + g_sort_extra_bits hash bits, rounded up to whole 8-bit passes. A sort bucket then
@@ -738,7 +754,7 @@ static DedupLayout dedup_layout(void *ws, size_t ws_bytes, int64_t T) {
     L.slot = ar.take<uint32_t>((size_t)T);
     L.kept = ar.take<uint32_t>((size_t)T);
     L.scratch = ar.take<uint32_t>(scan_scratch_elems(T));
-    L.total = ar.take<uint32_t>(4);
+    L.total = ar.take<uint32_t>(16);   // [0] scan total, [2] pass_all flag, [8..11] class-mode counters
     L.ok = L.total != nullptr;
     return L;
 }
@@ -1065,16 +1081,99 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
     return SYM_OK;
 }
 
+// identity worklist over the candidate array of the class mode (capacity T positions)
+static WorkList class_worklist(const DedupLayout &L, int64_t T, uint32_t *count, const uint32_t *begin) {
+    const WorkList ref = tile_worklist(L, T);
+    WorkList wl;
+    wl.nreg = ref.nreg;
+    wl.cap = ref.cap;
+    wl.work = nullptr;
+    wl.counts = count;
+    wl.begin_ptr = begin;
+    return wl;
+}
+
+// exact group pass over the listed candidate positions: nearest earlier twin, phase stamps, sums in t order
+static int class_group_pass(const ProductRows &rows, const ProductRows &rows_sum, RecFmt fmt, uint64_t *sr, int64_t T,
+                            int sort_shift, const WorkList &wl, const DedupLayout &L, double thr, const TileMap &tm,
+                            cudaStream_t st) {
+    link_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, sort_shift, wl, L.flag, L.link);
+    SYM_LAUNCH_OK();
+    phase_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, wl, L.flag);
+    SYM_LAUNCH_OK();
+    sum_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows_sum, fmt, sr, T, sort_shift, wl, L.flag, L.link, thr,
+                                                                       L.acc, L.multi, tm);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+// Class mode of the ordered-tile product (class_dedup.cu): no record array, no global sort. The candidate
+// array (L.alt) holds, class by class, the records that have a same-hash mate, sorted by (hash, t); the
+// group pass runs over all of them with device-side counts, so the common case (no class overflow) costs
+// one stream synchronisation like the sort path. Overflowed classes take the global sort afterwards and
+// are appended to the candidate array.
+int dedup_product_plan_classes(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, ClassJob &job,
+                               const uint64_t *a_sk, const uint64_t *b_sk, void *class_ws, size_t class_ws_bytes, double thr,
+                               int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < dedup_ws_bytes(T)) {
+        set_error("workspace too small: need %zu bytes, got %zu", dedup_ws_bytes(T), ws_bytes);
+        return SYM_E_WORKSPACE;
+    }
+    DedupLayout L = dedup_layout(ws, ws_bytes, T);
+    if (!L.ok) {
+        set_error("workspace arena exhausted");
+        return SYM_E_WORKSPACE;
+    }
+    ProductRows rows_sum = rows;
+    if (thr >= 0.0 && rows.N > 0) {
+        SYM_TRY(launch_min_abs_flag(reinterpret_cast<const double2 *>(rows.Ac), (int64_t)rows.M,
+                                    reinterpret_cast<const double2 *>(rows.Bc), (int64_t)rows.N, thr,
+                                    reinterpret_cast<unsigned long long *>(L.scratch), L.total + 2, st));
+        rows_sum.pass_all = L.total + 2;
+    }
+    uint32_t *counters = L.total + 8;
+    uint64_t *cand = L.alt, *over = recs;
+    SYM_TRY(class_dedup_run(job, a_sk, b_sk, rows_sum, tm, thr, cand, over, counters, class_ws, class_ws_bytes, st));
+    const int sort_shift = 64 - job.hbits;
+    SYM_TRY(class_group_pass(rows, rows_sum, fmt, cand, T, sort_shift, class_worklist(L, T, counters, nullptr), L, thr, tm, st));
+    uint32_t host[12] = {0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        seg_count_kernel<<<(tm.n_seg + 255) / 256, 256, 0, st>>>(tm);
+        SYM_LAUNCH_OK();
+        SYM_TRY(scan_exclusive_u32(tm.segoff, tm.segoff, (int64_t)tm.n_seg, L.total, L.scratch, st));
+        SYM_CUDA_OK(cudaMemcpyAsync(host, L.total, sizeof(host), cudaMemcpyDeviceToHost, st));
+        SYM_CUDA_OK(cudaStreamSynchronize(st));
+        const uint32_t n_cand = host[8], n_over = host[9];
+        if (attempt == 1 || n_over == 0u) break;
+        // overflowed classes: global sort of their records on (hash, t), appended behind the candidates
+        if ((int64_t)n_cand + (int64_t)n_over > T) {
+            set_error("class dedup wrote more records than cross terms");
+            return SYM_E_CUDA;
+        }
+        uint64_t *sorted = nullptr;
+        SYM_TRY(radix_sort_records(over, reinterpret_cast<uint64_t *>(L.slot), (int64_t)n_over, 2, L.hist, &sorted, st));
+        SYM_CUDA_OK(cudaMemcpyAsync(cand + n_cand, sorted, sizeof(uint64_t) * (size_t)n_over, cudaMemcpyDeviceToDevice, st));
+        SYM_TRY(class_ord_to_t(job, cand + n_cand, n_over, st));
+        SYM_TRY(class_group_pass(rows, rows_sum, fmt, cand, T, sort_shift, class_worklist(L, T, counters + 1, counters), L, thr, tm, st));
+    }
+    if (n_out) {
+        total_to_i64_kernel<<<1, 1, 0, st>>>(L.total, n_out);
+        SYM_LAUNCH_OK();
+    }
+    if (n_out_host) *n_out_host = (int64_t)host[0];
+    return SYM_OK;
+}
+
 int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
                              const TileBlock *blocks_host, const int32_t *a_y, const int32_t *b_y, int64_t U,
-                             uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, cudaStream_t st) {
+                             uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, bool class_mode, cudaStream_t st) {
     if (T == 0 || U == 0) return SYM_OK;
     DedupLayout L = dedup_layout(ws, ws_bytes, T);
     if (!L.ok) {
         set_error("workspace arena exhausted");
         return SYM_E_WORKSPACE;
     }
-    const uint64_t *sr = (T > 1 && sorted_in_alt(sort_begin_bit(T, fmt))) ? L.alt : recs;
+    const uint64_t *sr = class_mode ? L.alt : ((T > 1 && sorted_in_alt(sort_begin_bit(T, fmt))) ? L.alt : recs);
     const int chunks = rows.words / 2;
     const double2 *Ac = reinterpret_cast<const double2 *>(rows.Ac), *Bc = reinterpret_cast<const double2 *>(rows.Bc);
     double2 *oc = reinterpret_cast<double2 *>(out_c);
@@ -1103,7 +1202,7 @@ int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const 
         SYM_LAUNCH_OK();
     }
     if (g_emit_ev1) SYM_CUDA_OK(cudaEventRecord(g_emit_ev1, st));
-    const WorkList wl = tile_worklist(L, T);
+    const WorkList wl = class_mode ? class_worklist(L, T, L.total + 11, nullptr) : tile_worklist(L, T);
     tile_fixup_kernel<<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(tm, fmt, sr, wl, L.multi, L.acc, oc);
     SYM_LAUNCH_OK();
     return SYM_OK;

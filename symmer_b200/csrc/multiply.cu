@@ -369,7 +369,7 @@ static int g_ordered_tiles = 1;
 // key costs two 64-bit multiplies and runs twice, in the histogram and in pass 0, against 0.15 ms
 // for pair_keys_kernel writing 1 GB once) = a separate kernel writes them first
 static int g_fused_keys = 0;
-namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; extern int g_rref_variant; extern int g_tile_qgroup; extern int g_onesweep; }
+namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; extern int g_rref_variant; extern int g_tile_qgroup; extern int g_onesweep; extern int g_class_dedup; extern int g_class_variant; }
 
 extern "C" int sym_set_tuning(int32_t which, int64_t value) {
     if (which == 0) {
@@ -412,6 +412,14 @@ extern "C" int sym_set_tuning(int32_t which, int64_t value) {
         g_fused_keys = (int)value;
         return SYM_OK;
     }
+    if (which == 10) {
+        symb::g_class_dedup = (int)value;
+        return SYM_OK;
+    }
+    if (which == 11) {
+        symb::g_class_variant = (int)value;
+        return SYM_OK;
+    }
     set_error("unknown tuning knob %d", which);
     return SYM_E_INVALID;
 }
@@ -439,6 +447,10 @@ struct MulBlocksPlan {
     TileBlock *d_blocks;
     uint32_t *drop;
     uint32_t *segoff;
+    bool class_mode;     // ordered tiles with class-local duplicate detection (class_dedup.cu) instead of the record sort
+    ClassJob job;
+    void *class_ws;
+    size_t class_ws_bytes;
     void *rest;
     size_t rest_bytes;
     size_t need;
@@ -493,12 +505,21 @@ static int mul_blocks_plan(int64_t M_total, int64_t N, int32_t W, const int64_t 
     P.d_blocks = nullptr;
     P.drop = nullptr;
     P.segoff = nullptr;
+    P.class_mode = false;
+    P.class_ws = nullptr;
+    P.class_ws_bytes = 0;
     if (P.mode == MODE_TILES) {
         const size_t sg = (size_t)P.n_seg;
         need += arena_need(256, sizeof(TileBlock)) + arena_need(4 * sg, 4) + arena_need(sg + 1, 4);
         P.d_blocks = ar.take<TileBlock>(256);
         P.drop = ar.take<uint32_t>(4 * sg);
         P.segoff = ar.take<uint32_t>(sg + 1);
+        P.class_mode = class_job_plan(M_total, P.blocks, nblk, P.T, t_bits_for(M_total * N), g_key_mask, P.job);
+        if (P.class_mode) {
+            P.class_ws_bytes = class_job_ws_bytes(P.job);
+            need += arena_need(P.class_ws_bytes, 1);
+            P.class_ws = ar.take<unsigned char>(P.class_ws_bytes);
+        }
     }
     P.rest = ws ? (void *)(ar.base + ar.off) : nullptr;
     P.rest_bytes = (ws && ws_bytes > ar.off) ? ws_bytes - ar.off : 0;
@@ -567,7 +588,7 @@ extern "C" int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a
     }
     // ordered-tile mode with few blocks: the first radix pass generates the records itself
     ProductKeySrc ksrc;
-    const bool fused_keys = P.mode == MODE_TILES && P.nblk <= PKS_MAX_BLOCKS && g_fused_keys != 0;
+    const bool fused_keys = P.mode == MODE_TILES && !P.class_mode && P.nblk <= PKS_MAX_BLOCKS && g_fused_keys != 0;
     if (fused_keys) {
         ksrc.a_sk = P.a_sk;
         ksrc.b_sk = P.b_sk;
@@ -587,7 +608,7 @@ extern "C" int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a
         }
     }
     size_t off = 0;
-    for (int b = 0; b < P.nblk && !fused_keys; ++b) {
+    for (int b = 0; b < P.nblk && !fused_keys && !P.class_mode; ++b) {
         const TileBlock &tb = P.blocks[b];
         if (P.mode == MODE_TILES) {
             if (tb.m_blk > 0 && tb.nq > 0) {
@@ -608,6 +629,14 @@ extern "C" int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a
         off += (size_t)tb.m_blk * tb.nq;
     }
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
+    if (P.class_mode) {
+        if (P.class_ws == nullptr) {
+            set_error("workspace arena exhausted (class tables)");
+            return SYM_E_WORKSPACE;
+        }
+        return dedup_product_plan_classes(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.job, P.a_sk, P.b_sk, P.class_ws,
+                                          P.class_ws_bytes, zero_threshold, n_out, n_out_host, P.rest, P.rest_bytes, st);
+    }
     if (P.mode == MODE_TILES)
         return dedup_product_plan_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), fused_keys ? &ksrc : nullptr,
                                         zero_threshold, n_out, n_out_host, P.rest, P.rest_bytes, st);
@@ -630,7 +659,7 @@ extern "C" int sym_mul_blocks_emit(const uint64_t *a_xz, const double *a_c, int6
     RecFmt fmt{t_bits_for(M_total * N)};
     if (P.mode == MODE_TILES)
         return dedup_product_emit_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.blocks, P.a_y, P.b_y, U, out_xz,
-                                        out_c, P.rest, P.rest_bytes, (cudaStream_t)stream);
+                                        out_c, P.rest, P.rest_bytes, P.class_mode, (cudaStream_t)stream);
     return dedup_product_emit(P.recs, P.T, fmt, rows, P.mode == MODE_BY_T, U, out_xz, out_c, P.rest, P.rest_bytes,
                               (cudaStream_t)stream);
 }
@@ -642,7 +671,14 @@ extern "C" size_t sym_mul_cleanup_ws_bytes(int64_t M, int64_t N, int32_t W) {
     const int64_t T = M * N > 0 ? M * N : 1;
     const size_t segs = (size_t)(N > 0 ? N : 1) * (size_t)((M + TILE_ROWS - 1) / TILE_ROWS + 1);
     (void)blk;
-    return sym_pair_records_ws_bytes(M, N, W) + arena_need((size_t)T, 8) + dedup_ws_bytes(T) +
+    size_t class_bytes = 0;
+    {
+        TileBlock tb{0u, (uint32_t)(M > 0 ? M : 0), 0u, (uint32_t)(N > 0 ? N : 0), 0u, 0u};
+        ClassJob job;
+        if (M > 0 && N > 0 && class_job_plan(M, &tb, 1, T, t_bits_for(T), ~0ull, job, true))
+            class_bytes = arena_need(class_job_ws_bytes(job), 1);
+    }
+    return sym_pair_records_ws_bytes(M, N, W) + arena_need((size_t)T, 8) + dedup_ws_bytes(T) + class_bytes +
            arena_need(256, sizeof(TileBlock)) + arena_need(4 * segs, 4) + arena_need(segs + 1, 4) + 2048;
 }
 

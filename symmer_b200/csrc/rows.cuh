@@ -208,6 +208,49 @@ struct TileMap {
 #endif
 };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ uint8_t keep_test(double re, double im, double thr) {
+    return (thr < 0.0) ? 1 : (hypot(re, im) > thr ? 1 : 0);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Class-local duplicate detection of an ordered-tile product (class_dedup.cu): the cross terms are
+// enumerated class by class (a GF(2)-linear function of the row sketch) from the class-grouped rows
+// of A and the sketches of B; only records that have a same-hash mate are ever written to memory.
+constexpr int CD_MAX_BLOCKS = 16;
+constexpr int CD_MAX_ROUNDS = 8;
+struct ClassJob {
+    int k;                                     // 2^k classes
+    int nblk;
+    uint32_t n_entries;                        // rows of A over all blocks
+    uint32_t n_visits;                         // rows of B over all blocks
+    uint32_t entry_base[CD_MAX_BLOCKS + 1];    // first entry / visit of every block
+    uint32_t visit_base[CD_MAX_BLOCKS + 1];
+    uint32_t p0[CD_MAX_BLOCKS], q0[CD_MAX_BLOCKS], m_blk[CD_MAX_BLOCKS];
+    uint32_t rec_off[CD_MAX_BLOCKS + 1];       // first cross term of every block in block-major order
+    uint32_t M_total;                          // t = q * M_total + p
+    uint64_t key_mask;
+    int tb;                                    // RecFmt::tb of the product
+    int hbits;                                 // hash bits of a candidate record = min(32, 62 - tb): its sort bucket
+    int variant;                               // CTA shape of the class kernel (tuning knob 11)
+    const uint64_t *b_sk;                      // sketches of B (global row index)
+    const uint32_t *off;                       // [(b << (k+1)) | class]: first entry of the class of block b in `look`
+    const uint8_t *cnt8;                       // same index: min(255, rows in the class)
+    const uint32_t *vkey, *vq;                 // per row of B of every block (flattened): (b << (k+1)) | class, and q
+    const uint4 *look;                         // rows of A grouped by (block, class): {sketch lo, sketch hi, p, 0}
+};
+// false: this product takes the global record sort instead (too many blocks, B much larger than A, knob 10 = 0)
+bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t T, int tb, uint64_t key_mask, ClassJob &J,
+                    bool ignore_knob = false);
+size_t class_job_ws_bytes(const ClassJob &J);
+// overflow records carry their enumeration position in the term field while they are sorted; this puts t back
+int class_ord_to_t(const ClassJob &J, uint64_t *recs, uint32_t n, cudaStream_t st);
+// cand / over: T records each; counters: device uint32[4] = {candidates, overflow records, overflowed classes, sum}
+int class_dedup_run(ClassJob &J, const uint64_t *a_sk, const uint64_t *b_sk, const ProductRows &rows, const TileMap &tm,
+                    double thr, uint64_t *cand, uint64_t *over, uint32_t *counters, void *ws, size_t ws_bytes,
+                    cudaStream_t st);
+
 // Dedup driver (dedup.cu), split where the survivor count is known so the caller can allocate
 // exact-size outputs. `recs` holds T records (clobbered). by_t: the t fields are a permutation of
 // 0..T-1 and the output is written in increasing-t (first occurrence) order; otherwise the output
@@ -228,8 +271,13 @@ struct ProductKeySrc;   // sort.cuh: records generated inside the first radix pa
 int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
                              const ProductKeySrc *ksrc, double thr, int64_t *n_out, int64_t *n_out_host, void *ws,
                              size_t ws_bytes, cudaStream_t st);
+// class mode: `recs` is only scratch (the overflow array); a_sk / b_sk are the operand sketch tables and
+// class_ws holds the class tables (class_job_ws_bytes)
+int dedup_product_plan_classes(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, ClassJob &job,
+                               const uint64_t *a_sk, const uint64_t *b_sk, void *class_ws, size_t class_ws_bytes, double thr,
+                               int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
 int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
                              const TileBlock *blocks_host, const int32_t *a_y, const int32_t *b_y, int64_t U,
-                             uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, cudaStream_t st);
+                             uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, bool class_mode, cudaStream_t st);
 
 }  // namespace symb
