@@ -30,10 +30,11 @@ __host__ __device__ __forceinline__ uint32_t cd_class_of(uint64_t sk, int k) {
 
 // ------------------------------------------------------------------------------------------------
 // class tables. Table index of (block b, class a) = (b << (k + 1)) | a: XOR with a class only touches the low k bits.
-//   vkey[v]  = (b << (k+1)) | class(B[q_v])   visit v = row q_v of B in block b (all blocks, flattened)
-//   vq[v]    = q_v
-//   cnt8[i]  = min(255, rows of A in (block, class) i)      — 62 % of the visits end here, in L1
-//   off[i]   = first entry of (block, class) i in `look`;  look = rows of A grouped by (block, class)
+// Both operands are grouped by (block, class):
+//   look8 / lookp  rows of A: sketch and row index p; off[i] = first row of (block, class) i, off[tab] = rows of A
+//   bits           bit i set <=> (block, class) i of A is not empty — about half of the visits end at this bit
+//   vkey / vq / vsk  rows of B in (block, class) order ("visits"): table index, row index q, sketch
+// Visiting B in class order keeps the lookups of neighbouring visits in neighbouring table entries.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cd_block_of(const uint32_t *base, int nblk, uint32_t e) {
     int b = 0;
@@ -41,9 +42,9 @@ __device__ __forceinline__ int cd_block_of(const uint32_t *base, int nblk, uint3
     return b;
 }
 
-// threads [0, n_entries): histogram of the (block, class) of every row of A; threads [0, n_visits): visit keys
-__global__ void __launch_bounds__(256) cd_keys_kernel(ClassJob J, const uint64_t *__restrict__ a_sk, uint32_t *__restrict__ cnt,
-                                                       uint32_t *__restrict__ vkey, uint32_t *__restrict__ vq) {
+// cnt[0, tab): rows of A per table index; cnt[tab, 2 tab): rows of B per table index
+__global__ void __launch_bounds__(256) cd_hist_kernel(ClassJob J, const uint64_t *__restrict__ a_sk, uint32_t *__restrict__ cnt,
+                                                       uint32_t tab) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < J.n_entries) {
         const int b = cd_block_of(J.entry_base, J.nblk, e);
@@ -53,35 +54,50 @@ __global__ void __launch_bounds__(256) cd_keys_kernel(ClassJob J, const uint64_t
     if (e < J.n_visits) {
         const int b = cd_block_of(J.visit_base, J.nblk, e);
         const uint32_t q = J.q0[b] + (e - J.visit_base[b]);
-        vkey[e] = ((uint32_t)b << (J.k + 1)) | cd_class_of(J.b_sk[q], J.k);
-        vq[e] = q;
+        atomicAdd(cnt + tab + (((uint32_t)b << (J.k + 1)) | cd_class_of(J.b_sk[q], J.k)), 1u);
     }
 }
 
-// threads [0, n_entries): place the rows of A; threads [0, table size): byte counts
+// off = exclusive scan of cnt over both halves, so off[tab + i] - n_entries = first visit of table index i
 __global__ void __launch_bounds__(256) cd_place_kernel(ClassJob J, const uint64_t *__restrict__ a_sk, const uint32_t *__restrict__ off,
-                                                        uint32_t *__restrict__ cursor, uint4 *__restrict__ look,
-                                                        uint8_t *__restrict__ cnt8, uint32_t tab) {
+                                                        uint32_t *__restrict__ cursor, uint32_t tab, uint64_t *__restrict__ look8,
+                                                        uint32_t *__restrict__ lookp, uint32_t *__restrict__ vkey,
+                                                        uint32_t *__restrict__ vq, uint64_t *__restrict__ vsk,
+                                                        uint32_t *__restrict__ bits, uint32_t n_visits_padded) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= J.n_visits && e < n_visits_padded) vkey[e] = 1u << J.k;   // never matches: classes stop at 2^k - 1
     if (e < J.n_entries) {
         const int b = cd_block_of(J.entry_base, J.nblk, e);
         const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
         const uint64_t sk = a_sk[p];
         const uint32_t key = ((uint32_t)b << (J.k + 1)) | cd_class_of(sk, J.k);
         const uint32_t pos = off[key] + atomicAdd(cursor + key, 1u);
-        look[pos] = make_uint4((uint32_t)sk, (uint32_t)(sk >> 32), p, 0u);
+        look8[pos] = sk;
+        lookp[pos] = p;
     }
-    if (e < tab) {
-        const uint32_t n = (e + 1 < tab ? off[e + 1] : J.n_entries) - off[e];
-        cnt8[e] = (uint8_t)(n < 255u ? n : 255u);
+    if (e < J.n_visits) {
+        const int b = cd_block_of(J.visit_base, J.nblk, e);
+        const uint32_t q = J.q0[b] + (e - J.visit_base[b]);
+        const uint64_t sk = J.b_sk[q];
+        const uint32_t key = ((uint32_t)b << (J.k + 1)) | cd_class_of(sk, J.k);
+        const uint32_t pos = off[tab + key] - J.n_entries + atomicAdd(cursor + tab + key, 1u);
+        vkey[pos] = key;
+        vq[pos] = q;
+        vsk[pos] = sk;
+    }
+    if (e < (tab + 31) / 32) {
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < 32; ++i) {
+            const uint32_t t = e * 32 + i;
+            if (t < tab && off[t + 1] > off[t]) w |= 1u << i;
+        }
+        bits[e] = w;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the class kernel
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t cd_look_sketch(const uint4 &le) { return ((uint64_t)le.y << 32) | le.x; }
-
 // Records are ordered by their position in the block-major enumeration of the cross terms (block, then q, then p)
 // — for a single block that IS t = q*M + p, the reference's order (base.py:783-792); for a block list it is the
 // order in which the tiled emission writes the survivors. ord <-> t:
@@ -95,9 +111,17 @@ __device__ __forceinline__ uint32_t cd_t_of_ord(const ClassJob &J, uint32_t ord)
     return (J.q0[b] + ql) * J.M_total + J.p0[b] + (local - ql * J.m_blk[b]);
 }
 
-// Block-wide exclusive prefix of one value per thread (two barriers); *carry accumulates the block total.
+constexpr int CD_VPT = 12;          // consecutive visits per thread and chunk (a multiple of 4: 16-byte key loads)
+constexpr int CD_MAX_THREADS = 1024;
+// vkey is padded to whole chunks of the largest CTA with keys that never match: entry K of block 0 is the (empty) end marker
+static inline size_t cd_padded_visits(uint32_t n_visits) {
+    const size_t chunk = (size_t)CD_MAX_THREADS * CD_VPT;
+    return ((size_t)n_visits + chunk - 1) / chunk * chunk + chunk;
+}
+
+// Block-wide exclusive prefix of one value per thread (three barriers); *carry accumulates the block total.
 template <int THREADS>
-__device__ __forceinline__ uint32_t cd_block_prefix(uint32_t x, uint32_t *s_warp, uint32_t *carry) {
+__device__ __forceinline__ uint32_t cd_block_prefix(uint32_t x, uint32_t *s_warp, uint32_t *carry, uint32_t &running_total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = x;
 #pragma unroll
@@ -116,55 +140,86 @@ __device__ __forceinline__ uint32_t cd_block_prefix(uint32_t x, uint32_t *s_warp
             if (lane >= o) ti += y;
         }
         s_warp[lane] = ti - t;
-        if (lane == 31) s_warp[32] = *carry + ti;   // new carry (written after everyone read the old one below)
+        if (lane == 31) s_warp[32] = *carry + ti;   // the new carry, stored once everyone has read the old one
     }
     __syncthreads();
     const uint32_t base = *carry + s_warp[wid] + inc - x;
+    running_total = s_warp[32];
     __syncthreads();
-    if (threadIdx.x == 0) *carry = s_warp[32];
+    if (threadIdx.x == 0) *carry = running_total;
     return base;
 }
 
 // Enumerates the pairs of class c: every row q of B (all blocks) looks up the rows of A whose class is
-// class(B[q]) ^ c. Two steps per chunk of THREADS * VPT visits: every thread counts the pairs of its visits
-// (one coalesced key load and one byte from the L1-resident count table per visit), one block-wide prefix sum
-// gives it a private range of the list, then it writes its pairs — no atomics, no warp votes.
-// OVER = false: pairs go to the shared-memory list (beyond CAP they are only counted);
-// OVER = true: the records themselves go to the overflow array at over_base.
+// class(B[q]) ^ c. A thread owns VPT consecutive visits; per chunk of THREADS * VPT visits: count the pairs of the
+// own visits (one bit test per visit, the two table words of the non-empty ones), one block-wide prefix sum hands
+// every thread a private range of the list, then it writes its pairs — no atomics, no warp votes, and the list
+// ends up in visit order. OVER = false: pairs (entry of A, visit) go to the shared-memory list (beyond CAP they are
+// only counted); OVER = true: the records themselves go to the overflow array at over_base.
 template <int THREADS, int CAP, bool OVER>
-__device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, uint32_t *s_count, uint32_t *s_warp, uint2 *pairs,
-                                             uint64_t *__restrict__ over, uint32_t over_base) {
-    constexpr int VPT = 12;
+__device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, const uint32_t *bm, bool bm_shared, uint32_t *s_count,
+                                             uint32_t *s_warp, uint2 *pairs, uint64_t *__restrict__ over, uint32_t over_base) {
+    constexpr int VPT = CD_VPT;
     const int tid = threadIdx.x;
-    for (uint32_t v0 = 0; v0 < J.n_visits; v0 += THREADS * VPT) {
-        uint32_t idx[VPT], n[VPT];
+    for (uint32_t v0 = 0; v0 < J.n_visits; v0 += THREADS * VPT) {   // vkey is padded with never-matching keys to whole chunks
+        const uint32_t vb = v0 + tid * VPT;
+        uint32_t key[VPT];
+        const uint4 *src = reinterpret_cast<const uint4 *>(J.vkey + vb);
 #pragma unroll
-        for (int u = 0; u < VPT; ++u) {
-            const uint32_t v = v0 + u * THREADS + tid;
-            idx[u] = v < J.n_visits ? (__ldg(J.vkey + v) ^ c) : 0xffffffffu;
+        for (int g = 0; g < VPT / 4; ++g) {
+            const uint4 w = __ldg(src + g);
+            key[4 * g] = w.x;
+            key[4 * g + 1] = w.y;
+            key[4 * g + 2] = w.z;
+            key[4 * g + 3] = w.w;
         }
+        uint32_t lo[VPT], n[VPT];
         uint32_t sum = 0;
 #pragma unroll
         for (int u = 0; u < VPT; ++u) {
-            n[u] = idx[u] != 0xffffffffu ? (uint32_t)__ldg(J.cnt8 + idx[u]) : 0u;
-            if (n[u] == 255u) n[u] = __ldg(J.off + idx[u] + 1) - __ldg(J.off + idx[u]);
+            const uint32_t idx = key[u] ^ c;
+            const uint32_t w = bm_shared ? bm[idx >> 5] : __ldg(J.bits + (idx >> 5));
+            lo[u] = 0;
+            n[u] = 0;
+            if ((w >> (idx & 31u)) & 1u) {
+                lo[u] = __ldg(J.off + idx);
+                n[u] = __ldg(J.off + idx + 1) - lo[u];
+            }
             sum += n[u];
         }
-        uint32_t pos = cd_block_prefix<THREADS>(sum, s_warp, s_count);
+        uint32_t running;
+        uint32_t pos = cd_block_prefix<THREADS>(sum, s_warp, s_count, running);
+        if (sum == 0u) continue;
+        if (!OVER) {
+            if (running <= (uint32_t)CAP) {   // block-uniform: the whole chunk fits, no bound checks
 #pragma unroll
-        for (int u = 0; u < VPT; ++u) {
-            if (n[u] == 0u) continue;
-            uint32_t lo = __ldg(J.off + idx[u]);
-            const uint32_t q = __ldg(J.vq + v0 + u * THREADS + tid);
-            if (!OVER) {
-                for (uint32_t j = 0; j < n[u]; ++j, ++pos, ++lo)
-                    if (pos < (uint32_t)CAP) pairs[pos] = make_uint2(lo, q);
+                for (int u = 0; u < VPT; ++u) {
+                    if (n[u] == 0u) continue;
+                    const uint32_t v = vb + u;
+                    pairs[pos++] = make_uint2(lo[u], v);
+                    if (n[u] > 1u) {
+                        pairs[pos++] = make_uint2(lo[u] + 1, v);
+                        for (uint32_t j = 2; j < n[u]; ++j) pairs[pos++] = make_uint2(lo[u] + j, v);
+                    }
+                }
             } else {
-                const uint64_t skq = J.b_sk[q];
-                for (uint32_t j = 0; j < n[u]; ++j, ++pos, ++lo) {
-                    const uint4 le = J.look[lo];
-                    const uint64_t hm = mix64(cd_look_sketch(le) ^ skq) & J.key_mask;
-                    const uint64_t ord = cd_ord_of(J, (int)(idx[u] >> (J.k + 1)), le.z, q);
+#pragma unroll
+                for (int u = 0; u < VPT; ++u) {
+                    const uint32_t v = vb + u;
+                    for (uint32_t j = 0; j < n[u]; ++j, ++pos)
+                        if (pos < (uint32_t)CAP) pairs[pos] = make_uint2(lo[u] + j, v);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < VPT; ++u) {
+                if (n[u] == 0u) continue;
+                const uint32_t v = vb + u;
+                const uint64_t skq = J.vsk[v];
+                const uint32_t q = J.vq[v];
+                for (uint32_t j = 0; j < n[u]; ++j, ++pos) {
+                    const uint64_t hm = mix64(J.look8[lo[u] + j] ^ skq) & J.key_mask;
+                    const uint64_t ord = cd_ord_of(J, (int)(key[u] >> (J.k + 1)), J.lookp[lo[u] + j], q);
                     over[(size_t)over_base + pos] = (((hm & ~0xffffull) >> (J.tb + 2)) << (J.tb + 2)) | (ord << 2);
                 }
             }
@@ -177,6 +232,8 @@ __device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, uint
 __device__ __forceinline__ uint32_t cd_fold(uint64_t ent) {
     return (uint32_t)(ent >> 32) ^ ((uint32_t)(ent >> 16) & 0xffffu) * 0x9E3779B1u;
 }
+
+constexpr int CD_BM_WORDS = 2048;   // shared-memory copy of the non-empty bitmap when the table has <= 65536 entries
 
 // counters: [0] candidates written, [1] overflow records written, [2] overflowed classes, [3] = [0] + [1] (set afterwards)
 template <int THREADS, int CAP, int LOG_SLOTS, int MINB>
@@ -191,12 +248,17 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
     uint64_t *table = reinterpret_cast<uint64_t *>(cd_smem);
     uint2 *pairs = reinterpret_cast<uint2 *>(cd_smem + (size_t)SLOTS * 8);
     uint8_t *mate = cd_smem + (size_t)SLOTS * 8 + (size_t)CAP * 8;
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(cd_smem + (size_t)SLOTS * 8 + (size_t)CAP * 8 + CAP);
     __shared__ uint32_t s_count, s_ncand, s_base;
     __shared__ uint32_t s_warp[33];
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t K = 1u << J.k;
     const bool check_thr = !(thr < 0.0 || rows.all_pass());
+    const uint32_t bm_words = (((uint32_t)J.nblk << (J.k + 1)) + 31u) / 32u;
+    const bool bm_shared = bm_words <= (uint32_t)CD_BM_WORDS;
+    if (bm_shared)
+        for (uint32_t i = tid; i < bm_words; i += THREADS) s_bits[i] = J.bits[i];
 
     for (uint32_t c = blockIdx.x; c < K; c += gridDim.x) {
         if (tid == 0) {
@@ -205,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
         }
         for (int i = tid; i < CAP / 4; i += THREADS) reinterpret_cast<uint32_t *>(mate)[i] = 0u;
         __syncthreads();
-        cd_enumerate<THREADS, CAP, false>(J, c, &s_count, s_warp, pairs, nullptr, 0u);
+        cd_enumerate<THREADS, CAP, false>(J, c, s_bits, bm_shared, &s_count, s_warp, pairs, nullptr, 0u);
         __syncthreads();
         const uint32_t total = s_count;
         if (total > (uint32_t)CAP) {   // the class does not fit: its records take the global sort
@@ -216,11 +278,12 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
                 s_count = 0;
             }
             __syncthreads();
-            cd_enumerate<THREADS, CAP, true>(J, c, &s_count, s_warp, nullptr, over, s_base);
+            cd_enumerate<THREADS, CAP, true>(J, c, s_bits, bm_shared, &s_count, s_warp, nullptr, over, s_base);
             __syncthreads();
             continue;
         }
-        // ---- records of this thread: [hash : 48 | local id : 16]
+        // ---- records of this thread: [hash : 48 | local id : 16]; neighbouring lanes hold neighbouring list entries,
+        // i.e. neighbouring visits and table entries
         uint64_t ent[RPT];
         uint32_t xk[RPT];
         uint32_t unres = 0, candm = 0, winm = 0;   // one bit per record: no slot yet / saw a same-hash record / holds a slot
@@ -231,8 +294,7 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
             xk[j] = 0;
             if (i < total) {
                 const uint2 pr = pairs[i];
-                const uint4 le = __ldg(J.look + pr.x);
-                const uint64_t hm = mix64(cd_look_sketch(le) ^ __ldg(J.b_sk + pr.y)) & J.key_mask;
+                const uint64_t hm = mix64(__ldg(J.look8 + pr.x) ^ __ldg(J.vsk + pr.y)) & J.key_mask;
                 ent[j] = (hm & ~0xffffull) | i;
                 xk[j] = cd_fold(ent[j]);
                 unres |= 1u << j;
@@ -284,12 +346,12 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
                 }
                 if (cnd || (check_thr && i < total)) {
                     const uint2 pr = pairs[i];
-                    const uint32_t p = J.look[pr.x].z;
+                    const uint32_t p = J.lookp[pr.x], q = J.vq[pr.y];
                     if (cnd) {
-                        const int b = J.nblk == 1 ? 0 : cd_block_of(J.entry_base, J.nblk, pr.x);
-                        table[base + __popc(bal & lt)] = ((ent[j] >> (64 - J.hbits)) << 32) | cd_ord_of(J, b, p, pr.y);
+                        const int b = J.nblk == 1 ? 0 : (int)(J.vkey[pr.y] >> (J.k + 1));
+                        table[base + __popc(bal & lt)] = ((ent[j] >> (64 - J.hbits)) << 32) | cd_ord_of(J, b, p, q);
                     } else {   // unique row: survives unless its own coefficient fails the threshold
-                        const uint32_t t = pr.y * J.M_total + p;
+                        const uint32_t t = q * J.M_total + p;
                         double re, im;
                         rows.coeff_unphased(t, re, im);
                         if (!keep_test(re, im, thr)) tm.mark_dropped(t);
@@ -354,7 +416,7 @@ int class_ord_to_t(const ClassJob &J, uint64_t *recs, uint32_t n, cudaStream_t s
 int g_class_dedup = 1;   // tuning knob 10: 1 (default) = class-local duplicate detection for ordered-tile products, 0 = global record sort
 
 extern int g_class_variant;
-static int class_cap(int variant) { return variant == 1 ? 9216 : 4608; }
+static int class_cap(int variant) { return variant == 1 ? 9216 : 4096; }
 
 bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t T, int tb, uint64_t key_mask, ClassJob &J,
                     bool ignore_knob) {   // ignore_knob: workspace sizing — the shape with the larger tables
@@ -399,8 +461,8 @@ bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t 
     J.tb = tb;
     J.hbits = 62 - tb < 32 ? 62 - tb : 32;
     J.b_sk = nullptr;
-    J.off = nullptr;
-    J.look = nullptr;
+    J.off = J.bits = J.lookp = J.vkey = J.vq = nullptr;
+    J.look8 = J.vsk = nullptr;
     return true;
 }
 
@@ -408,8 +470,9 @@ static size_t cd_table_elems(const ClassJob &J) { return (size_t)J.nblk << (J.k 
 
 size_t class_job_ws_bytes(const ClassJob &J) {
     const size_t tab = cd_table_elems(J);
-    return 2 * arena_need(tab, 4) + arena_need(tab, 1) + arena_need(scan_scratch_elems((int64_t)tab), 4) +
-           arena_need(J.n_entries ? J.n_entries : 1, 16) + 2 * arena_need(J.n_visits ? J.n_visits : 1, 4) + 1024;
+    const size_t ne = J.n_entries ? J.n_entries : 1, nv = J.n_visits ? J.n_visits : 1;
+    return 2 * arena_need(2 * tab + 64, 4) + arena_need(tab / 32 + 64, 4) + arena_need(scan_scratch_elems((int64_t)(2 * tab)), 4) +
+           arena_need(ne, 8) + arena_need(ne, 4) + arena_need(cd_padded_visits(J.n_visits), 4) + arena_need(nv, 4) + arena_need(nv, 8) + 1024;
 }
 
 int g_class_variant = 1;    // tuning knob 11: CTA shape of the class kernel (0: 512 threads x 2 CTAs/SM, 1 (default, measured faster): 1024 threads x 1)
@@ -417,7 +480,7 @@ int g_class_variant = 1;    // tuning knob 11: CTA shape of the class kernel (0:
 template <int THREADS, int CAP, int LOG_SLOTS, int MINB>
 static int cd_launch(const ClassJob &J, const ProductRows &rows, const TileMap &tm, double thr, uint64_t *cand, uint64_t *over,
                      uint32_t *counters, cudaStream_t st) {
-    constexpr size_t smem = ((size_t)1 << LOG_SLOTS) * 8 + (size_t)CAP * 8 + CAP;
+    constexpr size_t smem = ((size_t)1 << LOG_SLOTS) * 8 + (size_t)CAP * 8 + CAP + (size_t)CD_BM_WORDS * 4;
     auto kern = class_dedup_kernel<THREADS, CAP, LOG_SLOTS, MINB>;
     static bool attr_done[64] = {};
     int dev = 0;
@@ -439,37 +502,45 @@ int class_dedup_run(ClassJob &J, const uint64_t *a_sk, const uint64_t *b_sk, con
                     cudaStream_t st) {
     Arena ar(ws, ws_bytes);
     const size_t tab = cd_table_elems(J);
-    uint32_t *off = ar.take<uint32_t>(tab);
-    uint32_t *cursor = ar.take<uint32_t>(tab);
-    uint8_t *cnt8 = ar.take<uint8_t>(tab);
-    uint32_t *scratch = ar.take<uint32_t>(scan_scratch_elems((int64_t)tab));
-    uint4 *look = ar.take<uint4>(J.n_entries ? J.n_entries : 1);
-    uint32_t *vkey = ar.take<uint32_t>(J.n_visits ? J.n_visits : 1);
-    uint32_t *vq = ar.take<uint32_t>(J.n_visits ? J.n_visits : 1);
-    if (!vq) {
+    const size_t ne = J.n_entries ? J.n_entries : 1, nv = J.n_visits ? J.n_visits : 1;
+    uint32_t *off = ar.take<uint32_t>(2 * tab + 64);
+    uint32_t *cursor = ar.take<uint32_t>(2 * tab + 64);
+    uint32_t *bits = ar.take<uint32_t>(tab / 32 + 64);
+    uint32_t *scratch = ar.take<uint32_t>(scan_scratch_elems((int64_t)(2 * tab)));
+    uint64_t *look8 = ar.take<uint64_t>(ne);
+    uint32_t *lookp = ar.take<uint32_t>(ne);
+    const size_t nvp = cd_padded_visits(J.n_visits);
+    uint32_t *vkey = ar.take<uint32_t>(nvp);
+    uint32_t *vq = ar.take<uint32_t>(nv);
+    uint64_t *vsk = ar.take<uint64_t>(nv);
+    if (!vsk) {
         set_error("workspace arena exhausted (class tables)");
         return SYM_E_WORKSPACE;
     }
-    SYM_CUDA_OK(cudaMemsetAsync(off, 0, sizeof(uint32_t) * tab, st));
-    SYM_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * tab, st));
+    SYM_CUDA_OK(cudaMemsetAsync(off, 0, sizeof(uint32_t) * (2 * tab + 64), st));
+    SYM_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * (2 * tab + 64), st));
     SYM_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 4, st));
     J.b_sk = b_sk;
     J.off = off;
-    J.look = look;
-    J.cnt8 = cnt8;
+    J.bits = bits;
+    J.look8 = look8;
+    J.lookp = lookp;
     J.vkey = vkey;
     J.vq = vq;
+    J.vsk = vsk;
     const uint32_t n1 = J.n_entries > J.n_visits ? J.n_entries : J.n_visits;
     if (n1) {
-        cd_keys_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(J, a_sk, off, vkey, vq);
+        cd_hist_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(J, a_sk, off, (uint32_t)tab);
         SYM_LAUNCH_OK();
     }
-    SYM_TRY(scan_exclusive_u32(off, off, (int64_t)tab, nullptr, scratch, st));
-    const uint32_t n2 = J.n_entries > (uint32_t)tab ? J.n_entries : (uint32_t)tab;
-    cd_place_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(J, a_sk, off, cursor, look, cnt8, (uint32_t)tab);
+    SYM_TRY(scan_exclusive_u32(off, off, (int64_t)(2 * tab), nullptr, scratch, st));
+    uint32_t n2 = n1 > (uint32_t)((tab + 31) / 32) ? n1 : (uint32_t)((tab + 31) / 32);
+    if (n2 < (uint32_t)nvp) n2 = (uint32_t)nvp;
+    cd_place_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(J, a_sk, off, cursor, (uint32_t)tab, look8, lookp, vkey, vq, vsk, bits,
+                                                     (uint32_t)nvp);
     SYM_LAUNCH_OK();
     if (class_cap(J.variant) == 9216) SYM_TRY((cd_launch<1024, 9216, 14, 1>(J, rows, tm, thr, cand, over, counters, st)));
-    else SYM_TRY((cd_launch<512, 4608, 13, 2>(J, rows, tm, thr, cand, over, counters, st)));
+    else SYM_TRY((cd_launch<512, 4096, 13, 2>(J, rows, tm, thr, cand, over, counters, st)));
     cd_total_kernel<<<1, 1, 0, st>>>(counters);
     SYM_LAUNCH_OK();
     return SYM_OK;

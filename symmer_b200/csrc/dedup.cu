@@ -62,18 +62,20 @@ __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const 
 // `nreg` regions of `cap` entries with one counter each: CTA b of the classify pass appends to region
 // b % nreg, so no counter is hot (one global counter serialises ~2e6 same-address atomics: 1.5 ms)
 // and a region can never overflow (it receives from at most cap records).
-// Identity form (class mode, work == nullptr): every position of [begin, begin + counts[0]) is on the list,
-// begin and the count live in device memory (the host never learns them before the launch); region r covers
-// positions begin + [r * cap, (r + 1) * cap).
+// Identity form (class mode, work == nullptr): every position of [begin, end) is on the list; begin and end live
+// in device memory (the host never learns them before the launch); region r covers positions
+// begin + [r * cap, (r + 1) * cap). begin_ptr / end_ptr also bound the record array for a stored list.
 struct WorkList {
     uint32_t *work;
     uint32_t *counts;
     uint32_t nreg, cap;
     const uint32_t *begin_ptr = nullptr;
+    const uint32_t *end_ptr = nullptr;
     __device__ __forceinline__ uint32_t begin() const { return begin_ptr ? *begin_ptr : 0u; }
     __device__ __forceinline__ uint32_t region_count(uint32_t r) const {
         if (work) return counts[r];
-        const uint32_t n = counts[0];
+        const uint32_t b = begin(), e = *end_ptr;
+        const uint32_t n = e > b ? e - b : 0u;
         const uint64_t lo = (uint64_t)r * cap;
         return n > lo ? (uint32_t)(n - lo < cap ? n - lo : cap) : 0u;
     }
@@ -81,8 +83,8 @@ struct WorkList {
         return work ? work[(size_t)r * cap + k] : begin() + r * cap + k;
     }
     // bounds of the record array the listed positions refer to
-    __device__ __forceinline__ int64_t lo() const { return work ? 0 : (int64_t)begin(); }
-    __device__ __forceinline__ int64_t hi(int64_t T) const { return work ? T : (int64_t)begin() + counts[0]; }
+    __device__ __forceinline__ int64_t lo() const { return (int64_t)begin(); }
+    __device__ __forceinline__ int64_t hi(int64_t T) const { return end_ptr ? (int64_t)*end_ptr : T; }
 };
 // consumers: WORK_SPLIT CTAs per region (grid = nreg * WORK_SPLIT), each striding over the region's entries
 constexpr uint32_t WORK_SPLIT = 8;
@@ -1081,28 +1083,209 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
     return SYM_OK;
 }
 
-// identity worklist over the candidate array of the class mode (capacity T positions)
-static WorkList class_worklist(const DedupLayout &L, int64_t T, uint32_t *count, const uint32_t *begin) {
+// identity worklist over positions [*begin, *end) of the candidate array of the class mode (capacity T positions)
+static WorkList class_worklist(const DedupLayout &L, int64_t T, const uint32_t *begin, const uint32_t *end) {
     const WorkList ref = tile_worklist(L, T);
     WorkList wl;
     wl.nreg = ref.nreg;
     wl.cap = ref.cap;
     wl.work = nullptr;
-    wl.counts = count;
+    wl.counts = nullptr;
     wl.begin_ptr = begin;
+    wl.end_ptr = end;
     return wl;
 }
 
-// exact group pass over the listed candidate positions: nearest earlier twin, phase stamps, sums in t order
-static int class_group_pass(const ProductRows &rows, const ProductRows &rows_sum, RecFmt fmt, uint64_t *sr, int64_t T,
-                            int sort_shift, const WorkList &wl, const DedupLayout &L, double thr, const TileMap &tm,
-                            cudaStream_t st) {
-    link_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, sort_shift, wl, L.flag, L.link);
+// ---------------------------------------------------------------------------------------------
+// Group pass of the class mode: exact duplicate resolution of the candidate array, one kernel.
+// The array is a concatenation of runs sorted by (hash, enumeration order); a BUCKET is a maximal run of
+// records with equal top hash bits. Eight lanes own a bucket: lane j holds 16-byte chunk j of the X block
+// and of the Z block of a row, so one pass over the members compares rows word by word (the exact
+// test: hash equality is only a filter), computes the phase exponent of every member (base.py:785-788)
+// and adds the coefficients in array order — the reference's np.add.at order (utils.py:271-278) — with the
+// commutative complex product, so anticommuting twins cancel to exact zero. Non-heads and heads whose sum
+// fails |c| > thr set their drop bit; a surviving head leaves its sum in acc[] / multi[] for the fix-up after
+// the emission. Buckets of more than 32 records (squares, molecular H*H) go to the generic worklist path
+// (link / phase / sum kernels above). HBM/L2-bound: 512 B of operand rows per member, from L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int GRP_MAX = 32;
+
+// WIDE: W >= 2, lane j < W/2 holds words 2j, 2j+1 of the X block and of the Z block; else W == 1 and lane 0 holds the word
+template <bool WIDE>
+__device__ __forceinline__ void grp_load(const ProductRows &rows, uint32_t t, int j, bool active, uint64_t &ox0, uint64_t &ox1,
+                                         uint64_t &oz0, uint64_t &oz1, uint32_t &ph) {
+    ox0 = ox1 = oz0 = oz1 = 0ull;
+    ph = 0;
+    if (!active) return;
+    uint32_t p, q;
+    rows.split(t, p, q);
+    const int W = rows.words >> 1;
+    const uint64_t *ra = rows.A + (size_t)p * rows.words, *rb = rows.B + (size_t)q * rows.words;
+    if (WIDE) {
+        const uint4 xa = *reinterpret_cast<const uint4 *>(ra + 2 * j), za = *reinterpret_cast<const uint4 *>(ra + W + 2 * j);
+        const uint4 xb = *reinterpret_cast<const uint4 *>(rb + 2 * j), zb = *reinterpret_cast<const uint4 *>(rb + W + 2 * j);
+        const uint64_t xa0 = ((uint64_t)xa.y << 32) | xa.x, xa1 = ((uint64_t)xa.w << 32) | xa.z;
+        const uint64_t za0 = ((uint64_t)za.y << 32) | za.x, za1 = ((uint64_t)za.w << 32) | za.z;
+        const uint64_t xb0 = ((uint64_t)xb.y << 32) | xb.x, xb1 = ((uint64_t)xb.w << 32) | xb.z;
+        const uint64_t zb0 = ((uint64_t)zb.y << 32) | zb.x, zb1 = ((uint64_t)zb.w << 32) | zb.z;
+        ox0 = xa0 ^ xb0;
+        ox1 = xa1 ^ xb1;
+        oz0 = za0 ^ zb0;
+        oz1 = za1 ^ zb1;
+        ph = (uint32_t)(__popcll(ox0 & oz0) + __popcll(ox1 & oz1) + 2 * (__popcll(xa0 & zb0) + __popcll(xa1 & zb1)));
+    } else {
+        const uint64_t xa0 = ra[0], za0 = ra[1], xb0 = rb[0], zb0 = rb[1];
+        ox0 = xa0 ^ xb0;
+        oz0 = za0 ^ zb0;
+        ph = (uint32_t)(__popcll(ox0 & oz0) + 2 * __popcll(xa0 & zb0));
+    }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) group_kernel(ProductRows rows, const int32_t *__restrict__ a_y, const int32_t *__restrict__ b_y,
+                                                     RecFmt fmt, const uint64_t *__restrict__ sr, int sort_shift, WorkList wl,
+                                                     double thr, double2 *__restrict__ acc, uint8_t *__restrict__ multi, TileMap tm,
+                                                     WorkList big) {
+    const int lane = threadIdx.x & 31, grp = lane >> 3, j = lane & 7;
+    const uint32_t gmask = 0xffu << (8 * grp);
+    const int64_t lo = wl.lo(), hi = wl.hi(0);
+    const int W = rows.words >> 1;
+    const bool active = WIDE ? (2 * j < W) : (j == 0);
+    const bool check_thr = !(thr < 0.0 || rows.all_pass());
+    const int64_t nwin = (hi - lo + 31) / 32;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t win = warp0; win < nwin; win += nwarps) {
+        const int64_t pos = lo + win * 32 + lane;
+        const uint64_t rec = pos < hi ? sr[pos] : 0ull;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, rec, 1);
+        if (lane == 0 && pos > lo) prev = sr[pos - 1];
+        const bool start = pos < hi && (pos == lo || ((rec ^ prev) >> sort_shift) != 0ull);
+        uint32_t starts = __ballot_sync(0xffffffffu, start);
+        while (starts) {
+            // the four lane groups take the next four bucket starts of the window
+            uint32_t m = starts;
+            int mine = -1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (m) {
+                    const int b = __ffs(m) - 1;
+                    if (g == grp) mine = b;
+                    m &= m - 1u;
+                }
+            }
+            starts = m;
+            if (mine < 0) continue;
+            const int64_t s = lo + win * 32 + mine;
+            const uint64_t r0 = sr[s];
+            // bucket length: lanes look at 8 positions at a time
+            uint32_t g_len = 1;
+            bool open = true;
+            for (int64_t b0 = s + 1; open; b0 += 8) {
+                const int64_t x = b0 + j;
+                const bool in = x < hi && ((sr[x] ^ r0) >> sort_shift) == 0ull;
+                const uint32_t out = (~__ballot_sync(gmask, in) & gmask) >> (8 * grp);
+                const uint32_t run = out ? (uint32_t)(__ffs(out) - 1) : 8u;
+                g_len += run;
+                open = run == 8u;
+            }
+            if (g_len > (uint32_t)GRP_MAX) {   // long bucket: its positions go on the generic list
+                for (uint32_t x = j; x < g_len; x += 8) {
+                    const uint32_t px = (uint32_t)(s + x);
+                    const uint32_t r = (px / CLS_TILE) % big.nreg;
+                    const uint32_t slot = atomicAdd(big.counts + r, 1u);
+                    big.work[(size_t)r * big.cap + slot] = px;
+                }
+                continue;
+            }
+            uint32_t done = 0;
+            for (uint32_t h = 0; h < g_len; ++h) {
+                if ((done >> h) & 1u) continue;
+                const uint64_t rh = sr[s + h];
+                const uint32_t th = fmt.t(rh);
+                uint64_t hx0, hx1, hz0, hz1;
+                uint32_t ph_h;
+                grp_load<WIDE>(rows, th, j, active, hx0, hx1, hz0, hz1, ph_h);
+                double sre = 0.0, sim = 0.0;
+                bool have = false;
+                for (uint32_t mm = h + 1; mm < g_len; ++mm) {
+                    if ((done >> mm) & 1u) continue;
+                    const uint64_t rm = sr[s + mm];
+                    if (!fmt.same_hash(rh, rm)) continue;
+                    const uint32_t tmm = fmt.t(rm);
+                    uint64_t ox0, ox1, oz0, oz1;
+                    uint32_t ph_m;
+                    grp_load<WIDE>(rows, tmm, j, active, ox0, ox1, oz0, oz1, ph_m);
+                    const bool eq = (ox0 == hx0) & (ox1 == hx1) & (oz0 == hz0) & (oz1 == hz1);
+                    if ((__ballot_sync(gmask, eq) & gmask) != gmask) continue;
+                    done |= 1u << mm;
+                    if (!have) {   // the head's own term first (np.add.at order)
+                        uint32_t phs = ph_h;
+                        phs += __shfl_xor_sync(gmask, phs, 1);
+                        phs += __shfl_xor_sync(gmask, phs, 2);
+                        phs += __shfl_xor_sync(gmask, phs, 4);
+                        if (j == 0) {
+                            uint32_t p, q;
+                            rows.split(th, p, q);
+                            rows.coeff(th, (int)((phs + 3u * (uint32_t)(a_y[p] + b_y[q])) & 3u), sre, sim);
+                        }
+                        have = true;
+                    }
+                    ph_m += __shfl_xor_sync(gmask, ph_m, 1);
+                    ph_m += __shfl_xor_sync(gmask, ph_m, 2);
+                    ph_m += __shfl_xor_sync(gmask, ph_m, 4);
+                    if (j == 0) {
+                        uint32_t p, q;
+                        rows.split(tmm, p, q);
+                        double cr, ci;
+                        rows.coeff(tmm, (int)((ph_m + 3u * (uint32_t)(a_y[p] + b_y[q])) & 3u), cr, ci);
+                        sre += cr;
+                        sim += ci;
+                        tm.mark_dropped(tmm);
+                        multi[s + mm] = 0;
+                    }
+                }
+                if (j == 0) {
+                    multi[s + h] = 0;
+                    if (have) {
+                        if (keep_test(sre, sim, thr)) {
+                            acc[s + h] = make_double2(sre, sim);
+                            multi[s + h] = 1;
+                        } else {
+                            tm.mark_dropped(th);
+                        }
+                    } else if (check_thr) {
+                        double re, im;
+                        rows.coeff_unphased(th, re, im);
+                        if (!keep_test(re, im, thr)) tm.mark_dropped(th);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// exact group pass over positions [*begin, *end) of the candidate array
+static int class_group_pass(const ProductRows &rows, const ProductRows &rows_sum, const int32_t *a_y, const int32_t *b_y, RecFmt fmt,
+                            uint64_t *sr, int64_t T, int sort_shift, const uint32_t *begin, const uint32_t *end,
+                            const DedupLayout &L, double thr, const TileMap &tm, cudaStream_t st) {
+    const WorkList wl = class_worklist(L, T, begin, end);
+    WorkList big = tile_worklist(L, T);
+    big.begin_ptr = begin;
+    big.end_ptr = end;
+    SYM_CUDA_OK(cudaMemsetAsync(big.counts, 0, sizeof(uint32_t) * big.nreg, st));
+    const unsigned grid = (unsigned)std::min<int64_t>((T + 255) / 256, (int64_t)num_sms() * 16);
+    if (rows.words >= 4)
+        group_kernel<true><<<grid, 256, 0, st>>>(rows_sum, a_y, b_y, fmt, sr, sort_shift, wl, thr, L.acc, L.multi, tm, big);
+    else
+        group_kernel<false><<<grid, 256, 0, st>>>(rows_sum, a_y, b_y, fmt, sr, sort_shift, wl, thr, L.acc, L.multi, tm, big);
     SYM_LAUNCH_OK();
-    phase_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, wl, L.flag);
+    // long buckets (rare): nearest earlier twin, phase stamps, sums in array order
+    link_work_kernel<ProductRows><<<big.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, sort_shift, big, L.flag, L.link);
     SYM_LAUNCH_OK();
-    sum_work_kernel<ProductRows><<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(rows_sum, fmt, sr, T, sort_shift, wl, L.flag, L.link, thr,
-                                                                       L.acc, L.multi, tm);
+    phase_work_kernel<ProductRows><<<big.nreg * WORK_SPLIT, 256, 0, st>>>(rows, fmt, sr, big, L.flag);
+    SYM_LAUNCH_OK();
+    sum_work_kernel<ProductRows><<<big.nreg * WORK_SPLIT, 256, 0, st>>>(rows_sum, fmt, sr, T, sort_shift, big, L.flag, L.link, thr,
+                                                                        L.acc, L.multi, tm);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }
@@ -1113,8 +1296,9 @@ static int class_group_pass(const ProductRows &rows, const ProductRows &rows_sum
 // one stream synchronisation like the sort path. Overflowed classes take the global sort afterwards and
 // are appended to the candidate array.
 int dedup_product_plan_classes(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, ClassJob &job,
-                               const uint64_t *a_sk, const uint64_t *b_sk, void *class_ws, size_t class_ws_bytes, double thr,
-                               int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st) {
+                               const uint64_t *a_sk, const uint64_t *b_sk, const int32_t *a_y, const int32_t *b_y, void *class_ws,
+                               size_t class_ws_bytes, double thr, int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes,
+                               cudaStream_t st) {
     if (ws_bytes < dedup_ws_bytes(T)) {
         set_error("workspace too small: need %zu bytes, got %zu", dedup_ws_bytes(T), ws_bytes);
         return SYM_E_WORKSPACE;
@@ -1135,7 +1319,7 @@ int dedup_product_plan_classes(uint64_t *recs, int64_t T, RecFmt fmt, const Prod
     uint64_t *cand = L.alt, *over = recs;
     SYM_TRY(class_dedup_run(job, a_sk, b_sk, rows_sum, tm, thr, cand, over, counters, class_ws, class_ws_bytes, st));
     const int sort_shift = 64 - job.hbits;
-    SYM_TRY(class_group_pass(rows, rows_sum, fmt, cand, T, sort_shift, class_worklist(L, T, counters, nullptr), L, thr, tm, st));
+    SYM_TRY(class_group_pass(rows, rows_sum, a_y, b_y, fmt, cand, T, sort_shift, nullptr, counters, L, thr, tm, st));
     uint32_t host[12] = {0};
     for (int attempt = 0; attempt < 2; ++attempt) {
         seg_count_kernel<<<(tm.n_seg + 255) / 256, 256, 0, st>>>(tm);
@@ -1154,7 +1338,7 @@ int dedup_product_plan_classes(uint64_t *recs, int64_t T, RecFmt fmt, const Prod
         SYM_TRY(radix_sort_records(over, reinterpret_cast<uint64_t *>(L.slot), (int64_t)n_over, 2, L.hist, &sorted, st));
         SYM_CUDA_OK(cudaMemcpyAsync(cand + n_cand, sorted, sizeof(uint64_t) * (size_t)n_over, cudaMemcpyDeviceToDevice, st));
         SYM_TRY(class_ord_to_t(job, cand + n_cand, n_over, st));
-        SYM_TRY(class_group_pass(rows, rows_sum, fmt, cand, T, sort_shift, class_worklist(L, T, counters + 1, counters), L, thr, tm, st));
+        SYM_TRY(class_group_pass(rows, rows_sum, a_y, b_y, fmt, cand, T, sort_shift, counters, counters + 3, L, thr, tm, st));
     }
     if (n_out) {
         total_to_i64_kernel<<<1, 1, 0, st>>>(L.total, n_out);
@@ -1202,7 +1386,7 @@ int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const 
         SYM_LAUNCH_OK();
     }
     if (g_emit_ev1) SYM_CUDA_OK(cudaEventRecord(g_emit_ev1, st));
-    const WorkList wl = class_mode ? class_worklist(L, T, L.total + 11, nullptr) : tile_worklist(L, T);
+    const WorkList wl = class_mode ? class_worklist(L, T, nullptr, L.total + 11) : tile_worklist(L, T);
     tile_fixup_kernel<<<wl.nreg * WORK_SPLIT, 256, 0, st>>>(tm, fmt, sr, wl, L.multi, L.acc, oc);
     SYM_LAUNCH_OK();
     return SYM_OK;

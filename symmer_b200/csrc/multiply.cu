@@ -634,8 +634,8 @@ extern "C" int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a
             set_error("workspace arena exhausted (class tables)");
             return SYM_E_WORKSPACE;
         }
-        return dedup_product_plan_classes(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.job, P.a_sk, P.b_sk, P.class_ws,
-                                          P.class_ws_bytes, zero_threshold, n_out, n_out_host, P.rest, P.rest_bytes, st);
+        return dedup_product_plan_classes(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.job, P.a_sk, P.b_sk, P.a_y, P.b_y,
+                                          P.class_ws, P.class_ws_bytes, zero_threshold, n_out, n_out_host, P.rest, P.rest_bytes, st);
     }
     if (P.mode == MODE_TILES)
         return dedup_product_plan_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), fused_keys ? &ksrc : nullptr,

@@ -235,10 +235,13 @@ struct ClassJob {
     int hbits;                                 // hash bits of a candidate record = min(32, 62 - tb): its sort bucket
     int variant;                               // CTA shape of the class kernel (tuning knob 11)
     const uint64_t *b_sk;                      // sketches of B (global row index)
-    const uint32_t *off;                       // [(b << (k+1)) | class]: first entry of the class of block b in `look`
-    const uint8_t *cnt8;                       // same index: min(255, rows in the class)
-    const uint32_t *vkey, *vq;                 // per row of B of every block (flattened): (b << (k+1)) | class, and q
-    const uint4 *look;                         // rows of A grouped by (block, class): {sketch lo, sketch hi, p, 0}
+    // class tables (class_dedup.cu); table index = (block << (k+1)) | class
+    const uint32_t *off;                       // first row of the table entry in look8 / lookp
+    const uint32_t *bits;                      // bit per table entry: A has rows there
+    const uint64_t *look8;                     // rows of A grouped by table entry: sketch
+    const uint32_t *lookp;                     //                                    row index p
+    const uint32_t *vkey, *vq;                 // rows of B ("visits") in table-entry order: table index, row index q
+    const uint64_t *vsk;                       //                                           sketch
 };
 // false: this product takes the global record sort instead (too many blocks, B much larger than A, knob 10 = 0)
 bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t T, int tb, uint64_t key_mask, ClassJob &J,
@@ -274,8 +277,9 @@ int dedup_product_plan_tiles(uint64_t *recs, int64_t T, RecFmt fmt, const Produc
 // class mode: `recs` is only scratch (the overflow array); a_sk / b_sk are the operand sketch tables and
 // class_ws holds the class tables (class_job_ws_bytes)
 int dedup_product_plan_classes(uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm, ClassJob &job,
-                               const uint64_t *a_sk, const uint64_t *b_sk, void *class_ws, size_t class_ws_bytes, double thr,
-                               int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes, cudaStream_t st);
+                               const uint64_t *a_sk, const uint64_t *b_sk, const int32_t *a_y, const int32_t *b_y, void *class_ws,
+                               size_t class_ws_bytes, double thr, int64_t *n_out, int64_t *n_out_host, void *ws, size_t ws_bytes,
+                               cudaStream_t st);
 int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const ProductRows &rows, const TileMap &tm,
                              const TileBlock *blocks_host, const int32_t *a_y, const int32_t *b_y, int64_t U,
                              uint64_t *out_xz, double *out_c, void *ws, size_t ws_bytes, bool class_mode, cudaStream_t st);
