@@ -47,6 +47,8 @@ def main():
     sa_s, sa_c = span_operator(gens, rows_a, rng)
     sb_s, sb_c = span_operator(gens, rows_b, rng)
     for name, (xs, xc, ys, yc) in (("collision-free", (a_s, a_c, b_s, b_c)), ("span-28", (sa_s, sa_c, sb_s, sb_c))):
+        if os.environ.get("PROBE_SPAN_ONLY") and name != "span-28":
+            continue
         a, ac = ops.pack(torch.from_numpy(xs), N_QUBITS), torch.from_numpy(xc).to(dev)
         b, bc = ops.pack(torch.from_numpy(ys), N_QUBITS), torch.from_numpy(yc).to(dev)
         for label, knobs in (("sort", {10: 0}), ("class512", {10: 1, 11: 0}), ("class1024", {10: 1, 11: 1})):

@@ -233,7 +233,8 @@ __device__ __forceinline__ uint32_t cd_fold(uint64_t ent) {
     return (uint32_t)(ent >> 32) ^ ((uint32_t)(ent >> 16) & 0xffffu) * 0x9E3779B1u;
 }
 
-constexpr int CD_BM_WORDS = 2048;   // shared-memory copy of the non-empty bitmap when the table has <= 65536 entries
+constexpr int CD_BM_WORDS = 2048;
+constexpr int CD_SMALL_GROUP = 16;  // hash groups up to this size are ordered by insertion inside the class kernel   // shared-memory copy of the non-empty bitmap when the table has <= 65536 entries
 
 // counters: [0] candidates written, [1] overflow records written, [2] overflowed classes, [3] = [0] + [1] (set afterwards)
 template <int THREADS, int CAP, int LOG_SLOTS, int MINB>
@@ -286,12 +287,14 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
         // i.e. neighbouring visits and table entries
         uint64_t ent[RPT];
         uint32_t xk[RPT];
+        uint32_t rr[RPT];                          // local id of the record that represents this record's hash group
         uint32_t unres = 0, candm = 0, winm = 0;   // one bit per record: no slot yet / saw a same-hash record / holds a slot
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             const uint32_t i = tid + j * THREADS;
             ent[j] = 0;
             xk[j] = 0;
+            rr[j] = i;
             if (i < total) {
                 const uint2 pr = pairs[i];
                 const uint64_t hm = mix64(__ldg(J.look8 + pr.x) ^ __ldg(J.vsk + pr.y)) & J.key_mask;
@@ -318,7 +321,8 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
                             winm |= 1u << j;
                             unres &= ~(1u << j);
                         } else if (((v ^ ent[j]) >> 16) == 0ull) {
-                            mate[v & 0xffffull] = 1;
+                            rr[j] = (uint32_t)(v & 0xffffull);
+                            mate[rr[j]] = 1;
                             candm |= 1u << j;
                             unres &= ~(1u << j);
                         }
@@ -332,59 +336,125 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
 #pragma unroll
         for (int j = 0; j < RPT; ++j)
             if (((winm >> j) & 1u) && mate[tid + j * THREADS] != 0) candm |= 1u << j;
-        const bool any_c = __any_sync(0xffffffffu, candm != 0u);
-        if (any_c || check_thr) {
+        if (check_thr) {   // unique rows survive unless their own coefficient fails the threshold
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
                 const uint32_t i = tid + j * THREADS;
-                const bool cnd = (candm >> j) & 1u;
-                const uint32_t bal = __ballot_sync(0xffffffffu, cnd);
-                uint32_t base = 0;
-                if (bal != 0u) {
-                    if (lane == 0) base = atomicAdd(&s_ncand, (uint32_t)__popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                }
-                if (cnd || (check_thr && i < total)) {
+                if (i < total && !((candm >> j) & 1u)) {
                     const uint2 pr = pairs[i];
-                    const uint32_t p = J.lookp[pr.x], q = J.vq[pr.y];
-                    if (cnd) {
-                        const int b = J.nblk == 1 ? 0 : (int)(J.vkey[pr.y] >> (J.k + 1));
-                        table[base + __popc(bal & lt)] = ((ent[j] >> (64 - J.hbits)) << 32) | cd_ord_of(J, b, p, q);
-                    } else {   // unique row: survives unless its own coefficient fails the threshold
-                        const uint32_t t = q * J.M_total + p;
-                        double re, im;
-                        rows.coeff_unphased(t, re, im);
-                        if (!keep_test(re, im, thr)) tm.mark_dropped(t);
-                    }
+                    const uint32_t t = J.vq[pr.y] * J.M_total + J.lookp[pr.x];
+                    double re, im;
+                    rows.coeff_unphased(t, re, im);
+                    if (!keep_test(re, im, thr)) tm.mark_dropped(t);
                 }
             }
         }
-        __syncthreads();
-        const uint32_t nc = s_ncand;
-        if (nc > 0u) {
-            uint32_t np = 2;
-            while (np < nc) np <<= 1;
-            for (uint32_t i = nc + tid; i < np; i += THREADS) table[i] = ~0ull;
-            // bitonic sort of [hash | ord]: equal-hash records become neighbours, in enumeration order
-            for (uint32_t size = 2; size <= np; size <<= 1) {
-                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                    __syncthreads();
-                    for (uint32_t i = tid; i < (np >> 1); i += THREADS) {
-                        const uint32_t pos = 2 * i - (i & (stride - 1));
-                        const uint64_t a = table[pos], b = table[pos + stride];
-                        const bool up = (pos & size) == 0u;
-                        if ((a > b) == up) {
-                            table[pos] = b;
-                            table[pos + stride] = a;
+        if (__syncthreads_or(candm != 0u)) {
+            // Candidates leave grouped by hash, each group in enumeration order. Fast path: counting sort by the
+            // group representative (one shared-memory atomic per candidate hands out its rank in the group), then
+            // the thread that owns the representative orders the (2-3 member) group by insertion. A class with a
+            // group of more than CD_SMALL_GROUP records, or with records that never found a slot, takes a bitonic
+            // sort of all its candidates instead.
+            uint32_t *cnt = reinterpret_cast<uint32_t *>(table);   // CAP words, then CAP keys
+            uint64_t *outk = table + CAP / 2;
+            for (int i = tid; i < CAP; i += THREADS) cnt[i] = 0u;
+            __syncthreads();
+            bool slow = (candm & unres) != 0u;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                if (((candm & ~unres) >> j) & 1u) rr[j] |= atomicAdd(cnt + rr[j], 1u) << 16;
+            __syncthreads();
+            uint32_t co[RPT];   // groups represented by this thread's records: [count : 16 | offset : 16]
+            uint32_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                co[j] = cnt[tid + j * THREADS];
+                slow |= co[j] > (uint32_t)CD_SMALL_GROUP;
+                sum += co[j];
+            }
+            if (!__syncthreads_or(slow)) {
+                uint32_t running;
+                uint32_t base = cd_block_prefix<THREADS>(sum, s_warp, &s_ncand, running);
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    cnt[tid + j * THREADS] = base;
+                    const uint32_t c = co[j];
+                    co[j] = (c << 16) | base;
+                    base += c;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    if ((candm >> j) & 1u) {
+                        const uint2 pr = pairs[tid + j * THREADS];
+                        const int b = J.nblk == 1 ? 0 : (int)(J.vkey[pr.y] >> (J.k + 1));
+                        outk[cnt[rr[j] & 0xffffu] + (rr[j] >> 16)] =
+                            ((ent[j] >> (64 - J.hbits)) << 32) | cd_ord_of(J, b, J.lookp[pr.x], J.vq[pr.y]);
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    const uint32_t c = co[j] >> 16;
+                    if (c >= 2u) {
+                        uint64_t *seg = outk + (co[j] & 0xffffu);
+                        for (uint32_t a = 1; a < c; ++a) {
+                            const uint64_t key = seg[a];
+                            uint32_t bpos = a;
+                            while (bpos > 0 && seg[bpos - 1] > key) {
+                                seg[bpos] = seg[bpos - 1];
+                                --bpos;
+                            }
+                            seg[bpos] = key;
                         }
                     }
                 }
+                __syncthreads();
+            } else {
+                outk = table;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    const bool cnd = (candm >> j) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, cnd);
+                    uint32_t base = 0;
+                    if (bal != 0u) {
+                        if (lane == 0) base = atomicAdd(&s_ncand, (uint32_t)__popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                    }
+                    if (cnd) {
+                        const uint2 pr = pairs[tid + j * THREADS];
+                        const int b = J.nblk == 1 ? 0 : (int)(J.vkey[pr.y] >> (J.k + 1));
+                        table[base + __popc(bal & lt)] = ((ent[j] >> (64 - J.hbits)) << 32) | cd_ord_of(J, b, J.lookp[pr.x], J.vq[pr.y]);
+                    }
+                }
+                __syncthreads();
+                const uint32_t n_all = s_ncand;
+                uint32_t np = 2;
+                while (np < n_all) np <<= 1;
+                for (uint32_t i = n_all + tid; i < np; i += THREADS) table[i] = ~0ull;
+                // bitonic sort of [hash | ord]: equal-hash records become neighbours, in enumeration order
+                for (uint32_t size = 2; size <= np; size <<= 1) {
+                    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                        __syncthreads();
+                        for (uint32_t i = tid; i < (np >> 1); i += THREADS) {
+                            const uint32_t pos = 2 * i - (i & (stride - 1));
+                            const uint64_t a = table[pos], b = table[pos + stride];
+                            const bool up = (pos & size) == 0u;
+                            if ((a > b) == up) {
+                                table[pos] = b;
+                                table[pos + stride] = a;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
             }
+            const uint32_t nc = s_ncand;
             if (tid == 0) s_base = atomicAdd(counters, nc);
             __syncthreads();
             const uint32_t gb = s_base;
             for (uint32_t i = tid; i < nc; i += THREADS) {
-                const uint64_t key = table[i];
+                const uint64_t key = outk[i];
                 cand[(size_t)gb + i] = ((key >> 32) << (64 - J.hbits)) | ((uint64_t)cd_t_of_ord(J, (uint32_t)key) << 2);
             }
         }

@@ -1146,8 +1146,10 @@ __global__ void __launch_bounds__(256) group_kernel(ProductRows rows, const int3
                                                      RecFmt fmt, const uint64_t *__restrict__ sr, int sort_shift, WorkList wl,
                                                      double thr, double2 *__restrict__ acc, uint8_t *__restrict__ multi, TileMap tm,
                                                      WorkList big) {
+    // The four lane groups of a warp work on four buckets in LOCKSTEP (uniform loops, per-group predicates):
+    // divergent per-group loops would serialise the groups and quadruple the instruction count.
+    const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, grp = lane >> 3, j = lane & 7;
-    const uint32_t gmask = 0xffu << (8 * grp);
     const int64_t lo = wl.lo(), hi = wl.hi(0);
     const int W = rows.words >> 1;
     const bool active = WIDE ? (2 * j < W) : (j == 0);
@@ -1157,10 +1159,10 @@ __global__ void __launch_bounds__(256) group_kernel(ProductRows rows, const int3
     for (int64_t win = warp0; win < nwin; win += nwarps) {
         const int64_t pos = lo + win * 32 + lane;
         const uint64_t rec = pos < hi ? sr[pos] : 0ull;
-        uint64_t prev = __shfl_up_sync(0xffffffffu, rec, 1);
+        uint64_t prev = __shfl_up_sync(FULL, rec, 1);
         if (lane == 0 && pos > lo) prev = sr[pos - 1];
         const bool start = pos < hi && (pos == lo || ((rec ^ prev) >> sort_shift) != 0ull);
-        uint32_t starts = __ballot_sync(0xffffffffu, start);
+        uint32_t starts = __ballot_sync(FULL, start);
         while (starts) {
             // the four lane groups take the next four bucket starts of the window
             uint32_t m = starts;
@@ -1174,77 +1176,79 @@ __global__ void __launch_bounds__(256) group_kernel(ProductRows rows, const int3
                 }
             }
             starts = m;
-            if (mine < 0) continue;
-            const int64_t s = lo + win * 32 + mine;
-            const uint64_t r0 = sr[s];
-            // bucket length: lanes look at 8 positions at a time
-            uint32_t g_len = 1;
-            bool open = true;
-            for (int64_t b0 = s + 1; open; b0 += 8) {
+            const int64_t s = lo + win * 32 + (mine < 0 ? 0 : mine);
+            const uint64_t r0 = mine < 0 ? 0ull : sr[s];
+            // bucket length: the lanes of a group look at 8 positions at a time
+            uint32_t g_len = mine < 0 ? 0u : 1u;
+            bool open = mine >= 0;
+            for (int64_t b0 = s + 1; __any_sync(FULL, open); b0 += 8) {
                 const int64_t x = b0 + j;
-                const bool in = x < hi && ((sr[x] ^ r0) >> sort_shift) == 0ull;
-                const uint32_t out = (~__ballot_sync(gmask, in) & gmask) >> (8 * grp);
+                const bool in = open && x < hi && ((sr[x] ^ r0) >> sort_shift) == 0ull;
+                const uint32_t out = (~(__ballot_sync(FULL, in) >> (8 * grp))) & 0xffu;
                 const uint32_t run = out ? (uint32_t)(__ffs(out) - 1) : 8u;
-                g_len += run;
-                open = run == 8u;
+                if (open) g_len += run;
+                open = open && run == 8u;
             }
-            if (g_len > (uint32_t)GRP_MAX) {   // long bucket: its positions go on the generic list
+            if (g_len > (uint32_t)GRP_MAX) {   // long bucket (rare): its positions go on the generic list
                 for (uint32_t x = j; x < g_len; x += 8) {
                     const uint32_t px = (uint32_t)(s + x);
                     const uint32_t r = (px / CLS_TILE) % big.nreg;
                     const uint32_t slot = atomicAdd(big.counts + r, 1u);
                     big.work[(size_t)r * big.cap + slot] = px;
                 }
-                continue;
+                g_len = 0;
             }
-            uint32_t done = 0;
-            for (uint32_t h = 0; h < g_len; ++h) {
-                if ((done >> h) & 1u) continue;
-                const uint64_t rh = sr[s + h];
+            // bit i of `todo`: member i of the bucket is neither a head yet nor merged into one
+            uint32_t todo = g_len == 0u ? 0u : (g_len == 32u ? FULL : ((1u << g_len) - 1u));
+            while (__any_sync(FULL, todo != 0u)) {
+                const int h = todo ? __ffs(todo) - 1 : -1;
+                if (h >= 0) todo &= todo - 1u;
+                const uint64_t rh = h >= 0 ? sr[s + h] : 0ull;
                 const uint32_t th = fmt.t(rh);
                 uint64_t hx0, hx1, hz0, hz1;
                 uint32_t ph_h;
-                grp_load<WIDE>(rows, th, j, active, hx0, hx1, hz0, hz1, ph_h);
+                grp_load<WIDE>(rows, th, j, active && h >= 0, hx0, hx1, hz0, hz1, ph_h);
+                ph_h += __shfl_xor_sync(FULL, ph_h, 1);
+                ph_h += __shfl_xor_sync(FULL, ph_h, 2);
+                ph_h += __shfl_xor_sync(FULL, ph_h, 4);
                 double sre = 0.0, sim = 0.0;
                 bool have = false;
-                for (uint32_t mm = h + 1; mm < g_len; ++mm) {
-                    if ((done >> mm) & 1u) continue;
-                    const uint64_t rm = sr[s + mm];
-                    if (!fmt.same_hash(rh, rm)) continue;
+                uint32_t pend = h >= 0 ? todo : 0u;   // later members that may be twins of this head
+                while (__any_sync(FULL, pend != 0u)) {
+                    const int mm = pend ? __ffs(pend) - 1 : -1;
+                    if (mm >= 0) pend &= pend - 1u;
+                    const uint64_t rm = mm >= 0 ? sr[s + mm] : 0ull;
+                    const bool cmp = mm >= 0 && fmt.same_hash(rh, rm);
                     const uint32_t tmm = fmt.t(rm);
                     uint64_t ox0, ox1, oz0, oz1;
                     uint32_t ph_m;
-                    grp_load<WIDE>(rows, tmm, j, active, ox0, ox1, oz0, oz1, ph_m);
+                    grp_load<WIDE>(rows, tmm, j, active && cmp, ox0, ox1, oz0, oz1, ph_m);
                     const bool eq = (ox0 == hx0) & (ox1 == hx1) & (oz0 == hz0) & (oz1 == hz1);
-                    if ((__ballot_sync(gmask, eq) & gmask) != gmask) continue;
-                    done |= 1u << mm;
-                    if (!have) {   // the head's own term first (np.add.at order)
-                        uint32_t phs = ph_h;
-                        phs += __shfl_xor_sync(gmask, phs, 1);
-                        phs += __shfl_xor_sync(gmask, phs, 2);
-                        phs += __shfl_xor_sync(gmask, phs, 4);
+                    const uint32_t eq_all = __ballot_sync(FULL, eq);   // every lane votes: never inside a short-circuit
+                    const bool twin = cmp && ((eq_all >> (8 * grp)) & 0xffu) == 0xffu;
+                    ph_m += __shfl_xor_sync(FULL, ph_m, 1);
+                    ph_m += __shfl_xor_sync(FULL, ph_m, 2);
+                    ph_m += __shfl_xor_sync(FULL, ph_m, 4);
+                    if (twin) {
+                        todo &= ~(1u << mm);
                         if (j == 0) {
                             uint32_t p, q;
-                            rows.split(th, p, q);
-                            rows.coeff(th, (int)((phs + 3u * (uint32_t)(a_y[p] + b_y[q])) & 3u), sre, sim);
+                            if (!have) {   // the head's own term first (np.add.at order)
+                                rows.split(th, p, q);
+                                rows.coeff(th, (int)((ph_h + 3u * (uint32_t)(a_y[p] + b_y[q])) & 3u), sre, sim);
+                            }
+                            rows.split(tmm, p, q);
+                            double cr, ci;
+                            rows.coeff(tmm, (int)((ph_m + 3u * (uint32_t)(a_y[p] + b_y[q])) & 3u), cr, ci);
+                            sre += cr;
+                            sim += ci;
+                            tm.mark_dropped(tmm);
+                            multi[s + mm] = 0;
                         }
                         have = true;
                     }
-                    ph_m += __shfl_xor_sync(gmask, ph_m, 1);
-                    ph_m += __shfl_xor_sync(gmask, ph_m, 2);
-                    ph_m += __shfl_xor_sync(gmask, ph_m, 4);
-                    if (j == 0) {
-                        uint32_t p, q;
-                        rows.split(tmm, p, q);
-                        double cr, ci;
-                        rows.coeff(tmm, (int)((ph_m + 3u * (uint32_t)(a_y[p] + b_y[q])) & 3u), cr, ci);
-                        sre += cr;
-                        sim += ci;
-                        tm.mark_dropped(tmm);
-                        multi[s + mm] = 0;
-                    }
                 }
-                if (j == 0) {
+                if (j == 0 && h >= 0) {
                     multi[s + h] = 0;
                     if (have) {
                         if (keep_test(sre, sim, thr)) {
