@@ -31,6 +31,9 @@ DENSE_STATE_MAX_QUBITS = 30
 FUSED_ROTATION_MIN_TERMS = 1 << 21
 # operators up to this many terms keep a host copy of their coefficients next to the device copy (1 MB at most)
 _HOST_COEFF_MAX_TERMS = 1 << 16
+# symplectic matrices up to this many entries keep a private host copy; larger ones are uploaded straight from the
+# caller's array and the host view is rebuilt lazily from the packed rows
+_HOST_VIEW_MAX_BYTES = 1 << 20
 
 
 class PauliwordOp:
@@ -54,11 +57,23 @@ class PauliwordOp:
         self.n_qubits = symp_matrix.shape[1] // 2
         self.n_terms = n_terms
         dev = ops.device()
-        symp_matrix = np.array(symp_matrix, dtype=bool, order='C', copy=True)   # private, read-only host view
-        self._xz = ops.pack(torch.from_numpy(symp_matrix).to(dev), self.n_qubits)
-        self._c = torch.from_numpy(np.ascontiguousarray(coeff)).to(dev)
-        self._symp_host = symp_matrix
-        self._symp_host.setflags(write=False)
+        if symp_matrix.size <= _HOST_VIEW_MAX_BYTES:
+            symp_matrix = np.array(symp_matrix, dtype=bool, order='C', copy=True)   # private, read-only host view
+            self._xz = ops.pack(torch.from_numpy(symp_matrix).to(dev), self.n_qubits)
+            self._c = torch.from_numpy(np.ascontiguousarray(coeff)).to(dev)
+            self._symp_host = symp_matrix
+            self._symp_host.setflags(write=False)
+        else:
+            # large operator: no private host copy (the view is rebuilt from the packed rows when asked for); page-locked
+            # caller memory goes over PCIe by DMA, and the copy has landed before the constructor returns
+            src = torch.from_numpy(np.ascontiguousarray(symp_matrix))
+            csrc = torch.from_numpy(np.ascontiguousarray(coeff))
+            pinned = src.is_pinned() and csrc.is_pinned()
+            self._xz = ops.pack(src.to(dev, non_blocking=pinned), self.n_qubits)
+            self._c = csrc.to(dev, non_blocking=pinned)
+            if pinned:
+                torch.cuda.current_stream().synchronize()
+            self._symp_host = None
         # The host coefficient view becomes authoritative once it exists (callers mutate it in place). Small operators
         # keep the caller's array from the start, like the reference (base.py:70 aliases it), so reading `coeff_vec`
         # never costs a device round trip; `_coeff_dev` re-uploads only when the snapshot shows it was changed.
@@ -87,14 +102,14 @@ class PauliwordOp:
             if self.n_qubits == 0:
                 self._symp_host = np.zeros((self.n_terms, 0), dtype=bool)
             else:
-                self._symp_host = ops.unpack(self._xz, self.n_qubits).cpu().numpy()
+                self._symp_host = ops.to_host(ops.unpack(self._xz, self.n_qubits))
             self._symp_host.setflags(write=False)
         return self._symp_host
 
     @property
     def coeff_vec(self) -> np.ndarray:
         if self._c_host is None:
-            self._c_host = self._c.cpu().numpy()
+            self._c_host = ops.to_host(self._c)
             self._c_snapshot = self._c_host.copy() if self.n_terms <= _HOST_COEFF_MAX_TERMS else None
         return self._c_host
 

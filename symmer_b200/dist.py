@@ -84,16 +84,19 @@ def exchange_records(part: torch.Tensor, counts: torch.Tensor, group=None) -> to
     return out
 
 
-def all_gather_operator(xz: torch.Tensor, c: torch.Tensor, group=None):
+def all_gather_operator(xz: torch.Tensor, c: torch.Tensor, group=None, sizes: Optional[List[int]] = None):
     """All-gather an operator whose rows are sharded by blocks: (xz_full, c_full, offsets). One size
-    exchange for both tensors; equal blocks (the common case) gather straight into the result."""
+    exchange for both tensors (skipped when the caller already knows every rank's row count: `sizes`);
+    equal blocks (the common case) gather straight into the result."""
     rank, world = _world(group)
     if world == 1:
         return xz, c, [0, xz.shape[0]]
-    n_local = torch.tensor([xz.shape[0]], dtype=torch.int64, device=xz.device)
-    sizes_t = torch.empty(world, dtype=torch.int64, device=xz.device)
-    dist.all_gather_into_tensor(sizes_t, n_local, group=group)
-    sizes = [int(v) for v in sizes_t.cpu().tolist()]
+    if sizes is None:
+        n_local = torch.tensor([xz.shape[0]], dtype=torch.int64, device=xz.device)
+        sizes_t = torch.empty(world, dtype=torch.int64, device=xz.device)
+        dist.all_gather_into_tensor(sizes_t, n_local, group=group)
+        sizes = [int(v) for v in sizes_t.cpu().tolist()]
+    assert len(sizes) == world and sizes[rank] == xz.shape[0], "row counts of the ranks do not match the local block"
     offsets = [0]
     for sz in sizes:
         offsets.append(offsets[-1] + sz)
@@ -122,20 +125,48 @@ def owner_blocks(a_counts: List[int], b_counts: List[int], owner: int) -> List[T
     return [(a_off[a], a_off[a + 1], b_off[a ^ owner], b_off[(a ^ owner) + 1]) for a in range(parts)]
 
 
+def partition_by_owner(xz: torch.Tensor, c: torch.Tensor, log2_parts: int):
+    """Operator grouped by owner class: (xz', c', counts as a host list). One small device->host read."""
+    p_xz, p_c, _, counts = ops.class_partition(xz, c, log2_parts)
+    return p_xz, p_c, [int(v) for v in counts.cpu().tolist()]
+
+
 def owned_product(a_xz: torch.Tensor, a_c: torch.Tensor, b_xz: torch.Tensor, b_c: torch.Tensor, log2_parts: int,
-                  owner: int, zero_threshold: Optional[float] = 1e-15):
+                  owner: int, zero_threshold: Optional[float] = 1e-15, a_part=None, b_part=None):
     """The part of (A * B).cleanup() owned by `owner` out of 2**log2_parts, computed locally from the
-    full operands with no exchange. Returns (xz, c, info)."""
-    a_p, a_cp, _, a_counts = ops.class_partition(a_xz, a_c, log2_parts)
-    b_p, b_cp, _, b_counts = ops.class_partition(b_xz, b_c, log2_parts)
-    counts = torch.stack([a_counts, b_counts]).cpu().tolist()      # one small device->host read
-    blocks = owner_blocks(counts[0], counts[1], owner)
+    full operands with no exchange. a_part / b_part: results of `partition_by_owner` when the caller
+    already has them (a replicated operand that does not change between calls, or the other owners'
+    parts of the same product). Returns (xz, c, info); info carries the class-grouped operands and
+    the blocks, so that a caller can check output rows against their operands."""
+    a_p, a_cp, a_counts = a_part if a_part is not None else partition_by_owner(a_xz, a_c, log2_parts)
+    b_p, b_cp, b_counts = b_part if b_part is not None else partition_by_owner(b_xz, b_c, log2_parts)
+    blocks = owner_blocks(a_counts, b_counts, owner)
     out_xz, out_c, n_recs = ops.mul_blocks_cleanup(a_p, a_cp, b_p, b_cp, blocks, zero_threshold)
-    return out_xz, out_c, {"cross_terms_generated": n_recs, "records_owned": n_recs, "rows_total_a": int(a_xz.shape[0])}
+    return out_xz, out_c, {"cross_terms_generated": n_recs, "records_owned": n_recs, "rows_total_a": int(a_xz.shape[0]),
+                           "blocks": blocks, "a_part": (a_p, a_cp, a_counts), "b_part": (b_p, b_cp, b_counts)}
+
+
+def streamed_product(a_xz: torch.Tensor, a_c: torch.Tensor, b_xz: torch.Tensor, b_c: torch.Tensor, log2_parts: int,
+                     consumer, zero_threshold: Optional[float] = 1e-15):
+    """(A * B).cleanup() of a product whose result does not fit the device (config C5 on one GPU:
+    1e9 cross terms = 272 GB): the result is generated in 2**log2_parts hash partitions, one after
+    the other, and each is handed to `consumer(part_index, xz, c)` and dropped. The partitions are
+    the owner classes of the multi-GPU product, so equal rows always fall into the same partition:
+    every partition is final (fully merged, thresholded) when it is handed over, and their union is
+    the whole result. Returns the list of what the consumer returned."""
+    a_part = partition_by_owner(a_xz, a_c, log2_parts)
+    b_part = partition_by_owner(b_xz, b_c, log2_parts)
+    out = []
+    for part in range(1 << log2_parts):
+        xz, c, _ = owned_product(a_xz, a_c, b_xz, b_c, log2_parts, part, zero_threshold, a_part=a_part, b_part=b_part)
+        out.append(consumer(part, xz, c))
+        del xz, c
+    return out
 
 
 def sharded_product(a_block_xz: torch.Tensor, a_block_c: torch.Tensor, b_xz: torch.Tensor, b_c: torch.Tensor,
-                    zero_threshold: Optional[float] = 1e-15, group=None, method: str = "owner"):
+                    zero_threshold: Optional[float] = 1e-15, group=None, method: str = "owner",
+                    block_sizes: Optional[List[int]] = None, cache: Optional[dict] = None):
     """(A * B).cleanup() with A's rows sharded over the ranks (this rank holds a_block) and B
     replicated. Returns this rank's hash partition of the result as (xz, c) device tensors plus a
     dict of sizes. Rows are unique across ranks.
@@ -144,12 +175,21 @@ def sharded_product(a_block_xz: torch.Tensor, a_block_c: torch.Tensor, b_xz: tor
       after one all-gather of A (25.6 MB at config C5) every rank generates exactly the cross
       terms it owns (sym_class_partition + sym_pair_records_blocks) — no record crosses NVLink.
     method="alltoall": every rank generates the records of its own block of A, partitions them by
-      owner (top hash bits) and routes them with one variable-size all-to-all (8 B per cross term)."""
+      owner (top hash bits) and routes them with one variable-size all-to-all (8 B per cross term).
+    block_sizes: row count of every rank's block of A when the caller knows them (saves the size exchange
+    and its host synchronisation). cache: a dict the caller keeps between calls; the owner-class grouping
+    of the replicated operand B is stored there and reused while B is the same tensor."""
     rank, world = _world(group)
     lg = log2_exact(world)
-    a_full, a_c_full, offsets = all_gather_operator(a_block_xz, a_block_c, group)
+    a_full, a_c_full, offsets = all_gather_operator(a_block_xz, a_block_c, group, sizes=block_sizes)
     if method == "owner":
-        return owned_product(a_full, a_c_full, b_xz, b_c, lg, rank, zero_threshold)
+        b_part = None
+        if cache is not None:
+            key = ("b_part", b_xz.data_ptr(), b_c.data_ptr(), tuple(b_xz.shape), b_xz._version, b_c._version, lg)
+            if cache.get("b_key") != key:
+                cache["b_key"], cache["b_part"] = key, partition_by_owner(b_xz, b_c, lg)
+            b_part = cache["b_part"]
+        return owned_product(a_full, a_c_full, b_xz, b_c, lg, rank, zero_threshold, b_part=b_part)
     if method != "alltoall":
         raise ValueError(f"unknown method {method!r}")
     recs = ops.pair_records(a_full, offsets[rank], offsets[rank + 1], b_xz)

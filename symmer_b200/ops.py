@@ -91,6 +91,17 @@ def release_workspace():
     _ws_cache.clear()
 
 
+def to_host(t):
+    """Device tensor -> NumPy array. Large results land in page-locked memory by DMA (torch caches the pinned block,
+    so repeated downloads do not pay the allocation again); `.cpu()` would stage them through pageable memory."""
+    if not t.is_cuda or t.numel() * t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
 def words_for(n_qubits):
     return max(1, (int(n_qubits) + 63) // 64)
 
