@@ -133,6 +133,12 @@ int sym_commute_mma(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64
  * instead of per-byte stores (measured 10x at 36 qubits); bytes N..out_pitch-1 of a row are scratch. */
 int sym_commute_mma_pitched(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,
                             uint8_t *out, int64_t out_pitch, void *ws, size_t ws_bytes, void *stream);
+/* Mirrors the blocks on and above the block diagonal (square blocks of `block_rows` rows, a multiple of 32) of a
+ * symmetric byte matrix into its lower triangle, in place. With it `adjacency_matrix`
+ * (symmer/operators/base.py:1054-1062: commutes_termwise of an operator with itself) computes only the upper block
+ * triangle: sym_commute* on A[i0:i1) x A[i0:M) for every block row, then one mirror pass. */
+int sym_mirror_upper(uint8_t *matrix, int64_t M, int64_t pitch, int64_t block_rows, void *stream);
+
 /* Same symplectic inner product, bit-packed output: out_bits[i][j/32] bit j%32 (row stride
  * ceil(N/32) uint32). Used when the matrix is consumed on the device (masks, graph colouring). */
 int sym_commute_bits(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W,

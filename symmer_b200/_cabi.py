@@ -42,6 +42,7 @@ SIGNATURES = {
     "sym_commute_mma_ws_bytes": (c_sz, [c_i64, c_i64, c_i32]),
     "sym_commute_mma": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
     "sym_commute_mma_pitched": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_i64, c_p, c_sz, c_p]),
+    "sym_mirror_upper": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p]),
     "sym_commute_bits": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p]),
     "sym_commute_qwc": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p]),
     "sym_gather_qubits": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i32, c_p, c_p]),

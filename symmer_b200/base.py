@@ -607,7 +607,8 @@ class PauliwordOp:
     @property
     def adjacency_matrix(self) -> np.ndarray:
         if 'adjacency_matrix' not in self._cache:
-            self._cache['adjacency_matrix'] = self.commutes_termwise(self)
+            # symmetric: large operators compute the upper block triangle only (ops.commute_self)
+            self._cache['adjacency_matrix'] = ops.to_host(ops.commute_self(self._xz))
         return self._cache['adjacency_matrix']
 
     @property

@@ -206,9 +206,44 @@ static int qwc_launch(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int
     return SYM_OK;
 }
 
+// Symmetric matrices (adjacency of an operator with itself, base.py:1054-1062): only the blocks on and above the
+// block diagonal are computed; this kernel mirrors them into the lower triangle. 32 x 32 byte tiles through shared
+// memory, so both the reads and the writes are 32-byte row segments. HBM-bound: reads and writes M^2/2 bytes.
+__global__ void __launch_bounds__(256) mirror_upper_kernel(uint8_t *__restrict__ m, uint32_t M, size_t pitch, uint32_t blk) {
+    __shared__ uint8_t tile[32][33];
+    const uint32_t tj = blockIdx.x, ti = blockIdx.y;   // tile (ti, tj) of the upper triangle -> tile (tj, ti)
+    // everything right of the block diagonal is mirrored; inside a diagonal block only the strict upper tiles are
+    const uint32_t bi = (ti * 32) / blk, bj = (tj * 32) / blk;
+    if (bj < bi || (bj == bi && tj <= ti)) return;
+    const uint32_t x = threadIdx.x & 31, y0 = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t y = y0 + 8 * r;
+        const uint32_t row = ti * 32 + y, col = tj * 32 + x;
+        tile[y][x] = (row < M && col < M) ? m[(size_t)row * pitch + col] : (uint8_t)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t y = y0 + 8 * r;
+        const uint32_t row = tj * 32 + y, col = ti * 32 + x;
+        if (row < M && col < M) m[(size_t)row * pitch + col] = tile[x][y];
+    }
+}
+
 }  // namespace symb
 
 using namespace symb;
+
+extern "C" int sym_mirror_upper(uint8_t *matrix, int64_t M, int64_t pitch, int64_t block_rows, void *stream) {
+    SYM_REQUIRE(M >= 0 && pitch >= M && block_rows >= 32 && block_rows % 32 == 0, "bad size (block_rows must be a multiple of 32)");
+    SYM_REQUIRE(M < ((int64_t)1 << 21), "matrix too large for one mirror launch");
+    if (M == 0) return SYM_OK;
+    const unsigned nt = (unsigned)((M + 31) / 32);
+    mirror_upper_kernel<<<dim3(nt, nt), 256, 0, (cudaStream_t)stream>>>(matrix, (uint32_t)M, (size_t)pitch, (uint32_t)block_rows);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
 
 extern "C" int sym_commute(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int32_t W, uint8_t *out,
                            void *stream) {

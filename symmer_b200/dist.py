@@ -267,6 +267,22 @@ def sharded_commute(a_xz: torch.Tensor, b_xz: torch.Tensor, group=None):
     return ops.commute(a_xz[lo:hi].contiguous(), b_xz), lo
 
 
+def sharded_adjacency(a_xz: torch.Tensor, group=None, block_rows: int = 4096):
+    """This rank's share of adjacency_matrix(A) (base.py:1054-1062), upper block triangle only: the block rows
+    i with i % world == rank (cyclic, so the triangle is balanced), each as (row_begin, bool[rows, M - row_begin])
+    = commutes_termwise(A[i0:i1), A[i0:]). The matrix is symmetric: the lower triangle is the mirror image and is
+    never computed. Inputs are replicated; no collective."""
+    rank, world = _world(group)
+    M = a_xz.shape[0]
+    out = []
+    for k, i0 in enumerate(range(0, M, block_rows)):
+        if k % world != rank:
+            continue
+        i1 = min(M, i0 + block_rows)
+        out.append((i0, ops.commute(a_xz[i0:i1], a_xz[i0:])))
+    return out
+
+
 def sharded_expval(xm: torch.Tensor, zm: torch.Tensor, cp: torch.Tensor, n_qubits: int, psi: torch.Tensor,
                    group=None) -> complex:
     """<psi|H|psi> with the 2^n basis rows sharded over the ranks (psi and the terms replicated) and

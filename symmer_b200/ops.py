@@ -285,6 +285,33 @@ def commute_mma(a_xz, b_xz):
     return out.view(torch.bool)[:, :N]
 
 
+# self-commutation of at least this many rows computes the upper block triangle only and mirrors it (the matrix is
+# symmetric); below, one full launch is cheaper than several block launches plus the mirror pass
+SELF_COMMUTE_MIN_ROWS = 8192
+
+
+def commute_self(a_xz, row_begin=0, row_end=None, block_rows=None):
+    """adjacency_matrix (base.py:1054-1062): bool[M, M], True where A[i] commutes with A[j]. Symmetric, so for large
+    operators only the blocks on and above the block diagonal are computed (sym_commute* on A[i0:i1) x A[i0:M)) and
+    one pass mirrors them into the lower triangle. row_begin / row_end / block_rows: internal (multi-GPU shares)."""
+    M, W = _rows(a_xz)
+    if M < SELF_COMMUTE_MIN_ROWS or W < 2:
+        return commute(a_xz, a_xz)
+    blk = block_rows or max(2048, ((M + 31) // 32 + 31) // 32 * 32)      # at most ~32 block rows, multiples of 32
+    pitch = (M + 31) // 32 * 32
+    out = torch.empty((M, pitch), dtype=torch.uint8, device=a_xz.device)
+    L = lib()
+    for i0 in range(0, M, blk):
+        i1 = min(M, i0 + blk)
+        a_blk, b_blk = a_xz[i0:i1], a_xz[i0:]
+        ws = workspace(L.sym_commute_mma_ws_bytes(i1 - i0, M - i0, W))
+        sub = out[i0:i1, i0:]                                            # starts on a 32-byte boundary of its row
+        _cabi.check(L.sym_commute_mma_pitched(_p(a_blk), i1 - i0, _p(b_blk), M - i0, W, _p(sub), pitch, _p(ws), ws.numel(),
+                                              _stream()))
+    _cabi.check(L.sym_mirror_upper(_p(out), M, pitch, blk, _stream()))
+    return out.view(torch.bool)[:, :M]
+
+
 def commute_bits(a_xz, b_xz):
     M, W = _rows(a_xz)
     N, _ = _rows(b_xz)

@@ -1,0 +1,110 @@
+"""Config-size parity (BASELINE.json configs C3 and C4) and the symmetric adjacency path, on the GPU.
+
+C3: one general and one Clifford rotation of PauliwordOp.random(1000 q, 100 000 terms) against the CPU oracle
+    (symmer/operators/base.py:1090-1186 restated) on the WHOLE operator.
+C4: matrix-free <psi|H|psi> of HOOH STO-3G (24 q, 14 905 terms) on a dense 2^24 state against three independent
+    evaluations: a product state (the expectation value factorises over qubits: O(terms * n) on the CPU), the sum
+    of 8 basis shards against the unsharded value, and the Hartree-Fock basis state against the diagonal terms.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pauli_oracle as po
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import symmer_b200.ops as o
+    o.device()
+    return o
+
+
+def test_commute_self_upper_triangle_matches_full(ops):
+    """adjacency_matrix of a large operator computes the upper block triangle and mirrors it (sym_mirror_upper)."""
+    for n, M, blk in [(130, 9001, 2048), (1000, 8200, 4096), (64, 8192, 2048)]:
+        s, _ = po.random_operator(n, M, seed=n + M)
+        s[M // 2:] = s[: M - M // 2] ^ (np.arange(M - M // 2)[:, None] % 7 == 0)      # structure: near-duplicates
+        xz = ops.pack(torch.from_numpy(s), n)
+        full = ops.commute(xz, xz)
+        assert torch.equal(full, full.T)
+        sym = ops.commute_self(xz, block_rows=blk)
+        assert sym.shape == full.shape and torch.equal(sym, full)
+    # a slice the oracle can check
+    ref = po.commutes_termwise(s[:300], s[:300])
+    assert np.array_equal(sym[:300, :300].cpu().numpy(), ref)
+
+
+@pytest.mark.timeout(600)
+def test_config_c3_rotations_of_100k_terms_against_oracle():
+    """BASELINE config C3 at full size: P = random(1000 q, 100 000 terms), one non-Clifford and one Clifford rotation,
+    every output term against the oracle (rows bit-exact, coefficients rtol 1e-12)."""
+    from symmer_b200 import PauliwordOp
+    n, M = 1000, 100_000
+    p_s, p_c = po.random_operator(n, M, seed=3)
+    q_s, _ = po.random_operator(n, 1, seed=4)
+    P = PauliwordOp(p_s, p_c)
+    Q = PauliwordOp(q_s, [1])
+    for angle in (0.37, np.pi / 2, None, 2.1):
+        rot = P.perform_rotations([(Q, angle)])
+        ref_s, ref_c = po.perform_rotations(p_s, p_c, [(q_s[0], angle)])
+        assert rot.n_terms == len(ref_c)
+        ok, why = po.compare_term_sets(rot.symp_matrix, rot.coeff_vec, ref_s, ref_c, scale=float(np.abs(p_c).max()))
+        assert ok, (angle, why)
+    # two rotations in sequence (the second acts on ~1.5e5 rows)
+    q2_s, _ = po.random_operator(n, 1, seed=5)
+    rot = P.perform_rotations([(Q, 0.37), (PauliwordOp(q2_s, [1]), 1.1)])
+    ref_s, ref_c = po.perform_rotations(p_s, p_c, [(q_s[0], 0.37), (q2_s[0], 1.1)])
+    ok, why = po.compare_term_sets(rot.symp_matrix, rot.coeff_vec, ref_s, ref_c, scale=float(np.abs(p_c).max()))
+    assert ok, why
+
+
+def _pauli_factor(a, b):
+    """<phi|sigma|phi> of one qubit state a|0> + b|1> for sigma = I, X, Y, Z."""
+    return np.array([abs(a) ** 2 + abs(b) ** 2, 2 * (np.conj(a) * b).real, 2 * (np.conj(a) * b).imag, abs(a) ** 2 - abs(b) ** 2])
+
+
+@pytest.mark.timeout(600)
+def test_config_c4_expval_24_qubits_independent_checks(ops):
+    from symmer_b200 import PauliwordOp
+    d = np.load(os.path.join(ROOT, "tests", "golden", "hamiltonians", "HOOH_STO3G.npz"))
+    n = int(d["n_qubits"][0])
+    symp = np.unpackbits(d["symp"], axis=1)[:, :2 * n].astype(bool)
+    coeff = d["coeff"]
+    assert n == 24 and symp.shape[0] == 14905
+    H = PauliwordOp(symp, coeff)
+    xm, zm, cp = H._terms_sorted()
+    dev = ops.device()
+    # (1) product state: the expectation value factorises over the qubits
+    rng = np.random.default_rng(7)
+    amps = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    amps /= np.linalg.norm(amps, axis=1, keepdims=True)
+    psi = np.ones(1, dtype=complex)
+    for q in range(n):                         # qubit 0 = most significant bit of the basis index (base.py:1502-1503)
+        psi = np.kron(psi, amps[q])
+    fac = np.array([_pauli_factor(amps[q, 0], amps[q, 1]) for q in range(n)])     # [n, 4]
+    x, z = symp[:, :n], symp[:, n:]
+    kind = np.where(x & z, 2, np.where(x, 1, np.where(z, 3, 0)))                   # I X Y Z -> 0 1 2 3
+    ref = np.sum(coeff * np.prod(fac[np.arange(n)[None, :], kind], axis=1))
+    psi_d = torch.from_numpy(psi).to(dev)
+    e = complex(ops.expval_dense(xm, zm, cp, n, psi_d).cpu().numpy())
+    assert np.isclose(e.real, ref.real, rtol=1e-11, atol=1e-12) and abs(e.imag) < 1e-10
+    # (2) the sum over 8 basis shards equals the unsharded value
+    side = 1 << n
+    parts = [complex(ops.expval_dense(xm, zm, cp, n, psi_d, k * side // 8, (k + 1) * side // 8).cpu().numpy()) for k in range(8)]
+    assert np.isclose(sum(parts), e, rtol=1e-12, atol=1e-13)
+    # (3) a basis state: only the diagonal terms contribute
+    hf = int("".join(str(int(b)) for b in d["hf_array"]), 2)                      # qubit 0 = most significant bit
+    onehot = torch.zeros(side, dtype=torch.complex128, device=dev)
+    onehot[hf] = 1.0
+    diag = ~x.any(axis=1)
+    bits = np.array([(hf >> (n - 1 - q)) & 1 for q in range(n)], dtype=bool)
+    e_ref = np.sum(coeff[diag] * (-1.0) ** np.count_nonzero(z[diag] & bits[None, :], axis=1))
+    e_hf = complex(ops.expval_dense(xm, zm, cp, n, onehot).cpu().numpy())
+    assert np.isclose(e_hf.real, e_ref.real, rtol=1e-12) and abs(e_hf.imag) < 1e-12
+    assert np.isclose(e_hf.real, float(d["hf_energy"][0]), rtol=1e-8)         # the reference data's own Hartree-Fock energy
