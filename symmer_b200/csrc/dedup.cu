@@ -928,8 +928,11 @@ template <int LW>
 __global__ void __launch_bounds__((TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256)
     tile_emit_kernel(const uint64_t *__restrict__ A, const double2 *__restrict__ Ac, const int32_t *__restrict__ Ay,
                      const uint64_t *__restrict__ B, const double2 *__restrict__ Bc, const int32_t *__restrict__ By,
-                     TileBlock blk, uint32_t qg, const uint32_t *__restrict__ drop, const uint32_t *__restrict__ segoff,
-                     uint64_t *__restrict__ out_xz, double2 *__restrict__ out_c) {
+                     TileBlock first, const TileBlock *__restrict__ blocks, uint32_t qg, const uint32_t *__restrict__ drop,
+                     const uint32_t *__restrict__ segoff, uint64_t *__restrict__ out_xz, double2 *__restrict__ out_c) {
+    // one launch covers every block of the list (blockIdx.z): no launch tails between the blocks of a sharded product
+    const TileBlock blk = blockIdx.z == 0 ? first : blocks[blockIdx.z];
+    if (blockIdx.x >= blk.ptiles || blockIdx.y * qg >= blk.nq) return;
     constexpr int TH = (TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256;
     constexpr int W = 1 << LW;            // words per X (and per Z) block = lanes per row
     constexpr int RP = TH >> LW;          // rows per pass
@@ -1367,17 +1370,22 @@ int dedup_product_emit_tiles(const uint64_t *recs, int64_t T, RecFmt fmt, const 
     double2 *oc = reinterpret_cast<double2 *>(out_c);
     const uint32_t qg = (uint32_t)(g_tile_qgroup < 1 ? 1 : g_tile_qgroup);
     if (g_emit_ev0) SYM_CUDA_OK(cudaEventRecord(g_emit_ev0, st));
+    uint32_t gx = 0, gy = 0;
     for (int b = 0; b < tm.nblk; ++b) {
         const TileBlock blk = blocks_host[b];
         if (blk.m_blk == 0 || blk.nq == 0) continue;
-        dim3 grid(blk.ptiles, (blk.nq + qg - 1) / qg);
-        if (grid.y > 65535) {
-            set_error("too many B rows for one tile launch");
-            return SYM_E_UNSUPPORTED;
-        }
+        gx = std::max(gx, blk.ptiles);
+        gy = std::max(gy, (blk.nq + qg - 1) / qg);
+    }
+    if (gy > 65535 || tm.nblk > 65535) {
+        set_error("too many B rows for one tile launch");
+        return SYM_E_UNSUPPORTED;
+    }
+    if (gx > 0 && gy > 0) {
+        dim3 grid(gx, gy, (unsigned)tm.nblk);
 #define TILE_EMIT(LW) \
     tile_emit_kernel<LW><<<grid, (TILE_ROWS << LW) < 256 ? (TILE_ROWS << LW) : 256, 0, st>>>(                 \
-        rows.A, Ac, a_y, rows.B, Bc, b_y, blk, qg, tm.drop, tm.segoff, out_xz, oc)
+        rows.A, Ac, a_y, rows.B, Bc, b_y, tm.first, tm.blocks, qg, tm.drop, tm.segoff, out_xz, oc)
         switch (chunks) {
             case 1: TILE_EMIT(0); break;
             case 2: TILE_EMIT(1); break;
