@@ -1276,7 +1276,14 @@ static int class_group_pass(const ProductRows &rows, const ProductRows &rows_sum
                             uint64_t *sr, int64_t T, int sort_shift, const uint32_t *begin, const uint32_t *end,
                             const DedupLayout &L, double thr, const TileMap &tm, cudaStream_t st) {
     const WorkList wl = class_worklist(L, T, begin, end);
+    // generic list for the long buckets: few regions (it is almost always empty, and its three kernels launch
+    // WORK_SPLIT CTAs per region whether or not there is anything on it)
     WorkList big = tile_worklist(L, T);
+    {
+        const int64_t nb = (T + CLS_TILE - 1) / CLS_TILE;
+        big.nreg = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(64, nb));
+        big.cap = (uint32_t)std::min<int64_t>(((nb + big.nreg - 1) / big.nreg) * CLS_TILE, T);
+    }
     big.begin_ptr = begin;
     big.end_ptr = end;
     SYM_CUDA_OK(cudaMemsetAsync(big.counts, 0, sizeof(uint32_t) * big.nreg, st));

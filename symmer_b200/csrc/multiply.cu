@@ -533,6 +533,7 @@ static TileMap tile_map_of(const MulBlocksPlan &P, int64_t M_total) {
     tm.blocks = P.d_blocks;
     tm.nblk = P.nblk;
     tm.M = (uint32_t)M_total;
+    tm.Minv = fastdiv_magic((uint32_t)M_total);
     tm.n_seg = P.n_seg;
     tm.drop = P.drop;
     tm.segoff = P.segoff;
@@ -629,6 +630,7 @@ extern "C" int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a
         off += (size_t)tb.m_blk * tb.nq;
     }
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
+    rows.Minv = fastdiv_magic((uint32_t)M_total);
     if (P.class_mode) {
         if (P.class_ws == nullptr) {
             set_error("workspace arena exhausted (class tables)");
@@ -656,6 +658,7 @@ extern "C" int sym_mul_blocks_emit(const uint64_t *a_xz, const double *a_c, int6
         return SYM_E_WORKSPACE;
     }
     ProductRows rows{a_xz, b_xz, a_c, b_c, (uint32_t)M_total, 2 * W, (uint32_t)N};
+    rows.Minv = fastdiv_magic((uint32_t)M_total);
     RecFmt fmt{t_bits_for(M_total * N)};
     if (P.mode == MODE_TILES)
         return dedup_product_emit_tiles(P.recs, P.T, fmt, rows, tile_map_of(P, M_total), P.blocks, P.a_y, P.b_y, U, out_xz,

@@ -23,6 +23,15 @@ static inline int t_bits_for(int64_t T) {
     return tb;
 }
 
+// Exact t / d for 32-bit t by one 64-bit multiply-high: magic = floor(2^64 / d) + 1 (the exact reciprocal when d is a
+// power of two). The integer division the hot kernels would otherwise run per lane costs ~20 instructions.
+static inline uint64_t fastdiv_magic(uint32_t d) { return d <= 1 ? 0ull : (~0ull / d) + 1ull; }
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fastdiv(uint32_t t, uint32_t d, uint64_t magic) {
+    return magic ? (uint32_t)__umul64hi((uint64_t)t, magic) : t / d;
+}
+#endif
+
 // Term t is the cross term (p, q) of a product A*B in the reference's flattened order t = q*M + p
 // (base.py:783-792); its row is A[p] ^ B[q] and is never stored.
 struct ProductRows {
@@ -34,11 +43,12 @@ struct ProductRows {
     int words;   // 2*W
     uint32_t N = 0;                                // rows of B (0 = unknown)
     const uint32_t *__restrict__ pass_all = nullptr;  // device flag: every single cross term passes |c| > thr
+    uint64_t Minv = 0;                             // fastdiv_magic(M), or 0: divide
 
     __device__ __forceinline__ bool all_pass() const { return pass_all != nullptr && *pass_all != 0u; }
 
     __device__ __forceinline__ void split(uint32_t t, uint32_t &p, uint32_t &q) const {
-        q = t / M;
+        q = fastdiv(t, M, Minv);
         p = t - q * M;
     }
     __device__ __forceinline__ uint4 chunk(uint32_t t, int c) const {  // 16-byte chunk c of the row
@@ -166,13 +176,14 @@ struct TileMap {
     const TileBlock *blocks;   // device, nblk entries
     int nblk;
     uint32_t M;                // rows of A: t = q*M + p
+    uint64_t Minv = 0;         // fastdiv_magic(M), or 0: divide
     uint32_t n_seg;
     uint32_t *drop;            // uint32[4 * n_seg]
     uint32_t *segoff;          // uint32[n_seg + 1]: counts, then their exclusive scan in place
 
 #ifdef __CUDACC__
     __device__ __forceinline__ bool locate(uint32_t t, TileBlock &blk, uint32_t &s, uint32_t &bit) const {
-        const uint32_t q = t / M, p = t - q * M;
+        const uint32_t q = fastdiv(t, M, Minv), p = t - q * M;
         blk = first;
         for (int b = 0;;) {
             const uint32_t pl = p - blk.p0, ql = q - blk.q0;
@@ -210,7 +221,13 @@ struct TileMap {
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint8_t keep_test(double re, double im, double thr) {
-    return (thr < 0.0) ? 1 : (hypot(re, im) > thr ? 1 : 0);
+    // |c| > thr like the reference (utils.py:275-278); hypot only when the cheap bounds max(|re|,|im|) <= |c| <= |re|+|im|
+    // do not decide it
+    if (thr < 0.0) return 1;
+    const double ar = fabs(re), ai = fabs(im);
+    if (ar > thr || ai > thr) return 1;
+    if (ar + ai <= thr) return 0;
+    return hypot(re, im) > thr ? 1 : 0;
 }
 #endif
 
