@@ -267,6 +267,23 @@ int sym_project(const uint64_t *xz, const double *c, int64_t M, int32_t W, int32
                 int32_t n_free, uint64_t *out_xz, double *out_c, int64_t *n_out, int64_t *n_out_host,
                 void *ws, size_t ws_bytes, void *stream);
 
+/* out[i] = words[perm[i] * pitch_words + column] (perm NULL = identity): one 64-bit word column of a row-major matrix
+ * in a given row order. Key of one pass of the word-by-word lexicographic sort that replaces
+ * `np.lexsort(symp_matrix.T)` (symmer/operators/base.py:469-470) and of `__eq__` (base.py:640-662). */
+int sym_gather_column(const uint64_t *words, int64_t M, int64_t pitch_words, int64_t column, const uint32_t *perm,
+                      uint64_t *out, void *stream);
+
+/* out row i = row perm[i] of (xz, c) (c / out_c may be NULL): reorders an operator on the device
+ * (`PauliwordOp.sort`, `__getitem__`: base.py:453-489). */
+int sym_gather_rows(const uint64_t *xz, const double *c, const uint32_t *perm, int64_t M_out, int32_t W, uint64_t *out_xz,
+                    double *out_c, void *stream);
+
+/* Exact join of two row sets (`words` uint64 per row) on equal rows: match[i] = index of the right row equal to left
+ * row i, or -1. keys_* are 64-bit row sketches; the right keys are sorted and perm_r maps sorted position -> row.
+ * Replaces the Python dict join of `QuantumState.__mul__` (bra * ket, base.py:1781-1830). */
+int sym_join_rows(const uint64_t *keys_l, const uint64_t *rows_l, int64_t M, const uint64_t *keys_r_sorted,
+                  const uint32_t *perm_r, const uint64_t *rows_r, int64_t N, int32_t words, int32_t *match, void *stream);
+
 /* ---- qubit relabelling / embedding: PauliwordOp.reindex (base.py:493-521), PauliwordOp.tensor
  * (base.py:1188-1204), QuantumState.reindex (base.py:1910-1936).
  * Output rows have n_out qubits (uint64[M][2*W'], W' = max(1, ceil(n_out/64))); bit k of the output

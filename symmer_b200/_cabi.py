@@ -43,6 +43,9 @@ SIGNATURES = {
     "sym_commute_mma": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
     "sym_commute_mma_pitched": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_i64, c_p, c_sz, c_p]),
     "sym_mirror_upper": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p]),
+    "sym_gather_column": (ctypes.c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p]),
+    "sym_gather_rows": (ctypes.c_int, [c_p, c_p, c_p, c_i64, c_i32, c_p, c_p, c_p]),
+    "sym_join_rows": (ctypes.c_int, [c_p, c_p, c_i64, c_p, c_p, c_p, c_i64, c_i32, c_p, c_p]),
     "sym_commute_bits": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p]),
     "sym_commute_qwc": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p]),
     "sym_gather_qubits": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i32, c_p, c_p]),
@@ -109,9 +112,16 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
-        from . import build as _build  # builds in-tree with nvcc; raises if nvcc is missing
-        _build.build()
+        _build.build()                 # builds in-tree with nvcc; raises if nvcc is missing
+    elif _build.needs_build():
+        # a .cu / .cuh / header newer than the library: a stale .so would silently run old kernels
+        if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            _build.build()
+        else:
+            import warnings
+            warnings.warn("symmer_b200: sources are newer than libsymmer_b200.so and nvcc is not available to rebuild it")
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"symmer_b200: CUDA library not found at {LIB_PATH}; run `python -m symmer_b200.build`")
     lib = ctypes.CDLL(LIB_PATH)

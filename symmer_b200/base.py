@@ -138,6 +138,10 @@ class PauliwordOp:
                 return self._c                                   # unchanged since the last upload
             self._c = torch.from_numpy(np.ascontiguousarray(host, dtype=complex)).to(self._xz.device)
             self._c_snapshot = np.array(host, dtype=complex) if host.size <= _HOST_COEFF_MAX_TERMS else None
+            # everything derived from the old coefficients is stale (the reference recomputes expval / the matrix
+            # from coeff_vec every time, so an in-place edit must be seen)
+            for key in ('terms_sorted', 'to_sparse_matrix'):
+                self._cache.pop(key, None)
         return self._c
 
     @property
@@ -187,7 +191,7 @@ class PauliwordOp:
         """Load an operator written by `to_packed_file` (packed uint64 rows + complex128 coefficients)
         straight into device memory: no string parsing, no bool matrix."""
         from .utils import load_packed
-        xz, coeff, n, _ = load_packed(path)
+        xz, coeff, n, _ = load_packed(path)        # validated: shapes, dtypes, zero padding bits
         dev = ops.device()
         return cls._from_device(torch.from_numpy(xz.view(np.int64).copy()).to(dev),
                                 torch.from_numpy(np.ascontiguousarray(coeff)).to(dev), n)
@@ -321,12 +325,19 @@ class PauliwordOp:
 
     # ------------------------------------------------------------------ ordering / indexing
     def sort(self, by: str = 'magnitude', key: str = 'decreasing') -> "PauliwordOp":
-        """base.py:453-489. Sort keys are computed on the host; rows are gathered on the device."""
+        """base.py:453-489. The lexicographic order (the canonical order behind every `==`) is a device-side radix
+        sort of the packed rows; the other sort keys are computed on the host; rows are gathered on the device."""
+        if by == 'lex':
+            if key not in ('increasing', 'decreasing'):
+                raise ValueError('Only permitted sort by values are increasing or decreasing')
+            perm = ops.lex_order(self._xz)
+            if key == 'increasing':
+                perm = perm.flip(0).contiguous()
+            xz, c = ops.gather_rows(self._xz, self._coeff_dev(), perm)
+            return PauliwordOp._from_device(xz, c, self.n_qubits)
         symp = self.symp_matrix
         if by == 'magnitude':
             order = np.argsort(-abs(self.coeff_vec))
-        elif by == 'lex':
-            order = np.lexsort(symp.T) if symp.shape[1] else np.arange(self.n_terms)
         elif by == 'weight':
             order = np.argsort(-np.sum(symp.astype(int), axis=1))
         elif by == 'support':
@@ -761,14 +772,16 @@ class PauliwordOp:
 
     # ------------------------------------------------------------------ a9/a10 matrix + expval
     def _terms_sorted(self):
+        c = self._coeff_dev()                      # first: drops the cached tables if coeff_vec was edited in place
         if 'terms_sorted' not in self._cache:
             assert 1 <= self.n_qubits <= 62, 'dense-index kernels need 1 <= n_qubits <= 62'
-            self._cache['terms_sorted'] = ops.term_masks_sorted(self._xz, self._coeff_dev(), self.n_qubits)
+            self._cache['terms_sorted'] = ops.term_masks_sorted(self._xz, c, self.n_qubits)
         return self._cache['terms_sorted']
 
     @property
     def to_sparse_matrix(self) -> csr_matrix:
         """base.py:1458-1510: CSR of the operator, qubit 0 = most significant bit."""
+        self._coeff_dev()                          # drops the cached matrix if coeff_vec was edited in place
         if 'to_sparse_matrix' not in self._cache:
             if self.n_qubits == 0:
                 self._cache['to_sparse_matrix'] = csr_matrix(self.coeff_vec)
@@ -794,9 +807,12 @@ class PauliwordOp:
         return ops.expval_dense(xm, zm, cp, self.n_qubits, psi, row_begin, row_end)
 
     def expval(self, psi: "QuantumState") -> complex:
-        """base.py:796-819. Dense matrix-free kernel when 2^n fits, symbolic products otherwise."""
+        """base.py:796-819. Like the reference, the path depends on how sparse psi is: the dense matrix-free kernel
+        (O(2^n * terms)) only when psi fills a fair share of the 2^n amplitudes and the dense vector fits comfortably;
+        a sparse state (a Hartree-Fock determinant, a few configurations) takes the symbolic products
+        psi^dagger * H * psi, O(terms * psi.n_terms), at any qubit count."""
         assert self.n_qubits == psi.n_qubits
-        if 1 <= self.n_qubits <= DENSE_STATE_MAX_QUBITS:
+        if dense_state_pays(self.n_qubits, psi.n_terms):
             dense = psi.to_dense_device()
             return complex(self.expval_dense(dense).cpu().numpy()).real
         return (psi.dagger * self * psi).real
@@ -893,6 +909,22 @@ class PauliwordOp:
             recon[np.ix_(ok, columns)] = part[ok]
             reconstructed |= ok
         return recon, reconstructed
+
+
+def dense_state_pays(n_qubits: int, n_state_terms: int) -> bool:
+    """Whether a state of `n_state_terms` basis states should be expanded to a dense 2^n vector for the matrix-free
+    kernels: it must populate at least 1/64 of the amplitudes, and the vector (16 B * 2^n) must fit in a quarter of
+    the free device memory. Otherwise the symbolic path (cost proportional to the state's term count) is used."""
+    if not 1 <= n_qubits <= DENSE_STATE_MAX_QUBITS:
+        return False
+    side = 1 << n_qubits
+    if n_state_terms * 64 < side and side > (1 << 16):
+        return False
+    try:
+        free, _ = torch.cuda.mem_get_info()
+    except Exception:       # no device (host-double runs)
+        return True
+    return 16 * side <= free // 4
 
 
 def _i_pow(k: torch.Tensor) -> torch.Tensor:
@@ -1134,6 +1166,7 @@ class QuantumState:
 
     @property
     def normalize(self) -> "QuantumState":
+        """base.py:1954-1962: divides by np.linalg.norm(coeff_vec) as given (no merge of repeated basis states)."""
         c = self.state_op._coeff_dev()
         return QuantumState._from_x_rows(self.state_op._xz, c / torch.linalg.vector_norm(c), self.n_qubits,
                                          self.vec_type)
@@ -1164,12 +1197,10 @@ class QuantumState:
             # sorted join on the 64-bit row sketches, verified on the packed bits (exact)
             kl, xl = left._bit_keys()
             kr, xr = right._bit_keys()
-            kr_sorted, perm = torch.sort(kr)
-            pos = torch.searchsorted(kr_sorted, kl).clamp_(max=kr_sorted.numel() - 1)
-            cand = perm[pos]
-            hit = (kr_sorted[pos] == kl) & (xr[cand] == xl).all(dim=1)
+            match = ops.join_rows(kl, xl, kr, xr).to(torch.int64)    # exact, also over runs of equal sketches
+            hit = match >= 0
             lc, rc = left.state_op._coeff_dev(), right.state_op._coeff_dev()
-            return np.complex128(torch.sum(lc[hit] * rc[cand[hit]]).cpu().numpy())     # NumPy scalar like the reference's
+            return np.complex128(torch.sum(lc[hit] * rc[match[hit]]).cpu().numpy())     # NumPy scalar like the reference's
         if isinstance(mul_obj, PauliwordOp):
             new = self.state_op * mul_obj
             y = ops.ycount(new._xz).to(torch.int64)

@@ -76,6 +76,42 @@ __global__ void sketch_kernel(const uint64_t *__restrict__ xz, int64_t M, int W,
     if (lane == 0) sk[row] = h;
 }
 
+// out[i] = words[perm[i] * pitch + column] (perm == nullptr: identity): one word column of a row-major matrix in a given
+// row order — the key of one pass of the word-by-word lexicographic sort (base.py:469-470)
+__global__ void gather_column_kernel(const uint64_t *__restrict__ words, int64_t M, int64_t pitch, int64_t column,
+                                     const uint32_t *__restrict__ perm, uint64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int64_t row = perm ? (int64_t)perm[i] : i;
+    out[i] = words[row * pitch + column];
+}
+
+// Exact join of two row sets on equal rows (bra * ket, base.py:1781-1830: the reference joins two Python dicts of bit
+// strings): match[i] = index of the row of the right set equal to left row i, or -1. The right keys (64-bit sketches)
+// are sorted; a left row binary-searches its key and compares the packed rows word by word over the WHOLE run of
+// equal keys, so sketch collisions between different rows cannot hide a match.
+__global__ void join_rows_kernel(const uint64_t *__restrict__ keys_l, const uint64_t *__restrict__ rows_l, int64_t M,
+                                 const uint64_t *__restrict__ keys_r, const uint32_t *__restrict__ perm_r,
+                                 const uint64_t *__restrict__ rows_r, int64_t N, int words, int32_t *__restrict__ match) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const uint64_t k = keys_l[i];
+    int64_t lo = 0, hi = N;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys_r[mid] < k) lo = mid + 1;
+        else hi = mid;
+    }
+    int32_t found = -1;
+    for (int64_t j = lo; j < N && keys_r[j] == k && found < 0; ++j) {
+        const uint32_t r = perm_r[j];
+        bool eq = true;
+        for (int w = 0; w < words && eq; ++w) eq = rows_l[i * words + w] == rows_r[(int64_t)r * words + w];
+        if (eq) found = (int32_t)r;
+    }
+    match[i] = found;
+}
+
 // basis-index masks (qubit 0 = most significant bit), n <= 62, and coefficient * (-i)^Y
 __global__ void term_masks_kernel(const uint64_t *__restrict__ xz, const double *__restrict__ c, int64_t M, int n,
                                   int64_t *__restrict__ xm, int64_t *__restrict__ zm, double *__restrict__ cp) {
@@ -235,6 +271,26 @@ extern "C" int sym_unpack_matrix(const uint64_t *bits, int64_t R, int64_t C, int
     SYM_REQUIRE(R >= 0 && C >= 0 && Cw * 64 >= C, "bad matrix shape");
     if (R == 0 || C == 0) return SYM_OK;
     unpack_matrix_kernel<<<blocks_for(R * C, 256), 256, 0, (cudaStream_t)stream>>>(bits, R, C, Cw, m);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_gather_column(const uint64_t *words, int64_t M, int64_t pitch_words, int64_t column, const uint32_t *perm,
+                                 uint64_t *out, void *stream) {
+    SYM_REQUIRE(M >= 0 && pitch_words >= 1 && column >= 0 && column < pitch_words, "bad size");
+    if (M == 0) return SYM_OK;
+    gather_column_kernel<<<blocks_for(M, 256), 256, 0, (cudaStream_t)stream>>>(words, M, pitch_words, column, perm, out);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+extern "C" int sym_join_rows(const uint64_t *keys_l, const uint64_t *rows_l, int64_t M, const uint64_t *keys_r_sorted,
+                             const uint32_t *perm_r, const uint64_t *rows_r, int64_t N, int32_t words, int32_t *match,
+                             void *stream) {
+    SYM_REQUIRE(M >= 0 && N >= 0 && words >= 1, "bad size");
+    if (M == 0) return SYM_OK;
+    join_rows_kernel<<<blocks_for(M, 256), 256, 0, (cudaStream_t)stream>>>(keys_l, rows_l, M, keys_r_sorted, perm_r, rows_r, N,
+                                                                          words, match);
     SYM_LAUNCH_OK();
     return SYM_OK;
 }

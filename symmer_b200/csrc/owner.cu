@@ -72,6 +72,18 @@ extern "C" int sym_owner_classes(const uint64_t *xz, int64_t M, int32_t W, int32
     return SYM_OK;
 }
 
+extern "C" int sym_gather_rows(const uint64_t *xz, const double *c, const uint32_t *perm, int64_t M_out, int32_t W, uint64_t *out_xz,
+                               double *out_c, void *stream) {
+    SYM_REQUIRE(M_out >= 0 && M_out < ((int64_t)1 << 31) && W >= 1, "bad size");
+    if (M_out == 0) return SYM_OK;
+    const int chunks = W;
+    gather_rows_kernel<<<(unsigned)((M_out * chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(xz), reinterpret_cast<const double2 *>(c), perm, M_out, chunks,
+        reinterpret_cast<uint4 *>(out_xz), reinterpret_cast<double2 *>(out_c), nullptr);
+    SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
 extern "C" size_t sym_class_partition_ws_bytes(int64_t M) {
     if (M < 1) M = 1;
     return arena_need((size_t)M, 8) * 3 + arena_need((size_t)M, 4) * 2 + arena_need(sort_hist_elems(M), 4) + 2048;

@@ -27,6 +27,8 @@ class IndependentOp(PauliwordOp):
                 coeff = coeff.real.astype(int).astype(complex)
         super().__init__(symp_matrix, coeff)
         self.target_sqp = target_sqp
+        self.stabilizer_rotations = None          # independent_op.py:41-42: filled by generate_stabilizer_rotations
+        self.used_indices = None
         self.coeff_vec = coeff                    # host view authoritative from the start (callers set sectors in place)
         self._check_independent()
 
@@ -38,6 +40,8 @@ class IndependentOp(PauliwordOp):
         self = PauliwordOp._from_device(xz, c, n_qubits)
         self.__class__ = cls
         self.target_sqp = target_sqp
+        self.stabilizer_rotations = None
+        self.used_indices = None
         self._nz = nonzero
         return self
 
@@ -269,8 +273,8 @@ def assign_value(S: PauliwordOp, ref_state: QuantumState, threshold: float = 0.5
     after CUDA initialisation). With a dense state the per-generator kernels are queued back to back and their
     results come back in one copy."""
     import torch
-    from .base import DENSE_STATE_MAX_QUBITS
-    if 1 <= S.n_qubits <= DENSE_STATE_MAX_QUBITS and S.n_terms:
+    from .base import dense_state_pays
+    if S.n_terms and dense_state_pays(S.n_qubits, ref_state.n_terms):
         dense = ref_state.to_dense_device()
         ones = torch.ones(1, dtype=torch.complex128, device=dense.device)
         parts = []

@@ -343,6 +343,58 @@ def gather_qubits(xz, src, n_in):
     return out
 
 
+# ------------------------------------------------------------------------------- ordering / joins
+def gather_rows(xz, c, perm):
+    """Rows (and coefficients, if given) in the order of the int32 device permutation `perm`."""
+    M, W = _rows(xz)
+    n = int(perm.numel())
+    assert perm.dtype == torch.int32 and perm.is_contiguous()
+    out_xz = torch.empty((n, 2 * W), dtype=torch.int64, device=xz.device)
+    out_c = torch.empty(n, dtype=torch.complex128, device=xz.device) if c is not None else None
+    _cabi.check(lib().sym_gather_rows(_p(xz), _p(_coeff(c)) if c is not None else _p(None), _p(perm), n, W, _p(out_xz), _p(out_c),
+                                      _stream()))
+    return out_xz, out_c
+
+
+def lex_order(xz):
+    """int32 device permutation that sorts the packed rows like `np.lexsort(symp_matrix.T)` (base.py:469-470: the LAST
+    column is the primary key, i.e. rows ordered as integers whose most significant bits are the Z block's highest
+    qubits). Stable LSD radix sort word by word: X words from the lowest up, then Z words; all-zero word columns
+    (padding, sparse registers) are skipped. No host unpack, only 2W words of OR come back."""
+    M, W = _rows(xz)
+    perm = torch.arange(M, dtype=torch.int32, device=xz.device)
+    if M <= 1:
+        return perm
+    used = or_rows(xz).cpu().numpy()
+    keys = torch.empty(M, dtype=torch.int64, device=xz.device)
+    L = lib()
+    first = True
+    for col in range(2 * W):                       # least significant word first
+        w = int(used[col]) & 0xFFFFFFFFFFFFFFFF
+        if w == 0:
+            continue
+        _cabi.check(L.sym_gather_column(_p(xz), M, 2 * W, col, _p(None) if first else _p(perm), _p(keys), _stream()))
+        begin_bit = (w & -w).bit_length() - 1      # bits below the lowest used bit are zero in every row
+        sort_pairs(keys, perm, begin_bit=begin_bit)
+        first = False
+    return perm
+
+
+def join_rows(keys_l, rows_l, keys_r, rows_r):
+    """int32[M]: for every left row the index of the equal right row, or -1 (exact: sketches only locate candidates)."""
+    M, N = int(keys_l.numel()), int(keys_r.numel())
+    words = int(rows_l.shape[1])
+    match = torch.full((M,), -1, dtype=torch.int32, device=keys_l.device)
+    if M == 0 or N == 0:
+        return match
+    kr = keys_r.clone()                                  # sorted as uint64, like the kernel compares them
+    perm = torch.arange(N, dtype=torch.int32, device=keys_r.device)
+    sort_pairs(kr, perm)
+    _cabi.check(lib().sym_join_rows(_p(keys_l.contiguous()), _p(rows_l.contiguous()), M, _p(kr), _p(perm), _p(rows_r.contiguous()),
+                                    N, words, _p(match), _stream()))
+    return match
+
+
 # --------------------------------------------------------------------------------------- rotations
 def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0):
     """One rotation step (no dedup). mode 0 general (returns M + M_ac rows), 1/2 Clifford."""
@@ -498,10 +550,12 @@ def expval_dense(xm, zm, cp, n_qubits, psi, row_begin=0, row_end=None):
 def to_csr(xm, zm, cp, n_qubits):
     """(data, indices, indptr) device tensors; every row has G = #distinct x entries sorted by column."""
     dev = xm.device
-    xg, counts = torch.unique_consecutive(xm, return_counts=True)
-    G = xg.numel()
-    start = torch.zeros(G + 1, dtype=torch.int32, device=dev)
-    start[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    # group boundaries of the sorted x masks: a few thousand terms, found on the host (one small copy each way)
+    xh = xm.cpu().numpy()
+    first = np.flatnonzero(np.concatenate([[True], xh[1:] != xh[:-1]])) if xh.size else np.zeros(0, dtype=np.int64)
+    G = int(first.size)
+    xg = torch.from_numpy(np.ascontiguousarray(xh[first])).to(dev)
+    start = torch.from_numpy(np.concatenate([first, [xh.size]]).astype(np.int32)).to(dev)
     side = 1 << int(n_qubits)
     data = torch.empty(side * G, dtype=torch.complex128, device=dev)
     indices = torch.empty(side * G, dtype=torch.int64, device=dev)

@@ -7,6 +7,8 @@ that wants to stay on the device uses `symmer_b200.base.PauliwordOp` / `symmer_b
 """
 from typing import Tuple
 
+import os
+
 import numpy as np
 import torch
 
@@ -194,18 +196,44 @@ def save_packed(path, symp_matrix, coeff_vec, **extra) -> None:
     symp_matrix = np.asarray(symp_matrix, dtype=bool)
     M, two_n = symp_matrix.shape
     n = two_n // 2
+    path = _npz_path(path)
     np.savez_compressed(path, format_version=np.array([PACKED_FORMAT_VERSION]), n_qubits=np.array([n]),
                         xz=pack_rows_host(symp_matrix), coeff=np.asarray(coeff_vec, dtype=complex),
                         **{k: np.asarray(v) for k, v in extra.items()})
 
 
+def _npz_path(path):
+    """np.savez appends '.npz' to a name without it: save and load agree on the name actually written."""
+    path = os.fspath(path) if not hasattr(path, "write") and not hasattr(path, "read") else path
+    if isinstance(path, str) and not path.endswith(".npz"):
+        path += ".npz"
+    return path
+
+
 def load_packed(path):
-    """(xz uint64[M, 2W], coeff complex128[M], n_qubits, extra dict) from a file written by save_packed."""
+    """(xz uint64[M, 2W], coeff complex128[M], n_qubits, extra dict) from a file written by save_packed. The
+    contents are checked before they reach a kernel: dtypes, shapes (2W words per row, one coefficient per row)
+    and zero padding bits above qubit n-1 (dedup, equality and the GF(2) reductions rely on them)."""
+    path = _npz_path(path)
     d = np.load(path)
     if int(d["format_version"][0]) != PACKED_FORMAT_VERSION:
         raise ValueError(f"unsupported packed operator format {int(d['format_version'][0])}")
+    xz, coeff, n = d["xz"], d["coeff"], int(d["n_qubits"][0])
+    W = max(1, (n + 63) // 64)
+    if xz.dtype != np.uint64 or xz.ndim != 2 or xz.shape[1] != 2 * W:
+        raise ValueError(f"packed rows must be uint64[M, {2 * W}] for {n} qubits, got {xz.dtype}{list(xz.shape)}")
+    coeff = np.ascontiguousarray(coeff, dtype=complex)
+    if coeff.ndim != 1 or coeff.shape[0] != xz.shape[0]:
+        raise ValueError(f"{xz.shape[0]} packed rows but {coeff.shape} coefficients")
+    used = n - 64 * (W - 1)                                     # qubits in the last word of each block
+    if n == 0:
+        pad = np.uint64(0xFFFFFFFFFFFFFFFF)
+    else:
+        pad = np.uint64(0) if used == 64 else np.uint64(0xFFFFFFFFFFFFFFFF) << np.uint64(used)
+    if pad and xz.shape[0] and (np.any(xz[:, W - 1] & pad) or np.any(xz[:, 2 * W - 1] & pad)):
+        raise ValueError("packed rows carry bits above the last qubit (padding must be zero)")
     extra = {k: d[k] for k in d.files if k not in ("format_version", "n_qubits", "xz", "coeff")}
-    return d["xz"], d["coeff"], int(d["n_qubits"][0]), extra
+    return np.ascontiguousarray(xz), coeff, n, extra
 
 
 def pack_rows_host(symp_matrix: np.ndarray) -> np.ndarray:

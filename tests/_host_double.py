@@ -130,6 +130,27 @@ def commute(a_xz, b_xz):
     return torch.from_numpy(po.commutes_termwise(a, b))
 
 
+def commute_self(a_xz, row_begin=0, row_end=None, block_rows=None):
+    return commute(a_xz, a_xz)
+
+
+def gather_rows(xz, c, perm):
+    idx = perm.to(torch.int64)
+    return xz[idx].contiguous(), (c[idx].contiguous() if c is not None else None)
+
+
+def lex_order(xz):
+    """np.lexsort over the unpacked columns (last column = primary key), like base.py:469-470."""
+    rows, _ = _wide(xz)
+    order = np.lexsort(rows.T) if rows.shape[0] else np.zeros(0, dtype=np.int64)
+    return torch.from_numpy(order.astype(np.int32))
+
+
+def join_rows(keys_l, rows_l, keys_r, rows_r):
+    table = {r.tobytes(): i for i, r in reversed(list(enumerate(rows_r.numpy())))}
+    return torch.tensor([table.get(r.tobytes(), -1) for r in rows_l.numpy()], dtype=torch.int32)
+
+
 def commute_qwc(a_xz, b_xz):
     a, _ = _wide(a_xz)
     b, _ = _wide(b_xz)
@@ -334,7 +355,7 @@ def or_rows(bits, rows=None):
 
 
 _SWAPPED = ["device", "pack", "unpack", "ycount", "sketch", "gather_qubits", "cleanup", "mul_cleanup", "cross_mul",
-            "commute", "commute_qwc", "rotate", "rotate_dedup", "project", "term_masks_sorted", "to_csr", "apply_dense",
+            "commute", "commute_self", "gather_rows", "lex_order", "join_rows", "commute_qwc", "rotate", "rotate_dedup", "project", "term_masks_sorted", "to_csr", "apply_dense",
             "expval_dense", "pauli_decompose_dense", "pauli_decompose_diagonals", "rows_from_masks", "pack_matrix", "unpack_matrix", "rref_packed", "bit_transpose", "or_rows"]
 
 

@@ -108,3 +108,43 @@ def test_config_c4_expval_24_qubits_independent_checks(ops):
     e_hf = complex(ops.expval_dense(xm, zm, cp, n, onehot).cpu().numpy())
     assert np.isclose(e_hf.real, e_ref.real, rtol=1e-12) and abs(e_hf.imag) < 1e-12
     assert np.isclose(e_hf.real, float(d["hf_energy"][0]), rtol=1e-8)         # the reference data's own Hartree-Fock energy
+
+
+@pytest.mark.parametrize("n,m", [(1, 7), (5, 200), (64, 300), (65, 257), (130, 1000), (1000, 5000)])
+def test_lex_order_on_device_matches_numpy_lexsort(ops, n, m):
+    """sort('lex') (base.py:469-470, the canonical order behind every `==`) as a device radix sort of the packed rows."""
+    from symmer_b200 import PauliwordOp
+    s, c = po.random_operator(n, m, seed=n * 7 + m)
+    s[m // 2:] = s[: m - m // 2]                    # ties: the sort must be stable like np.lexsort
+    s[:, -3:] = False                                # all-zero high columns: skipped word bits
+    order = np.lexsort(s.T)
+    perm = ops.lex_order(ops.pack(torch.from_numpy(s), n)).cpu().numpy()
+    assert np.array_equal(perm, order)
+    P = PauliwordOp(s, c)
+    for key in ("decreasing", "increasing"):
+        srt = P.sort(by="lex", key=key)
+        ref = order if key == "decreasing" else order[::-1]
+        assert np.array_equal(srt.symp_matrix, s[ref]) and np.array_equal(srt.coeff_vec, c[ref])
+    Q = PauliwordOp(s[::-1].copy(), c[::-1].copy())
+    assert P == Q and not (P == PauliwordOp(s, c * 1.5))
+
+
+def test_state_inner_product_join_is_exact(ops):
+    """bra * ket (base.py:1781-1830) joins the two states on equal bit strings: against the dict join of the oracle
+    semantics, with repeated basis states and at widths beyond one word."""
+    from symmer_b200 import QuantumState
+    rng = np.random.default_rng(3)
+    for n, k1, k2 in [(10, 300, 200), (70, 500, 400), (130, 64, 64)]:
+        pool = rng.integers(0, 2, size=(150, n))
+        left, right = pool[rng.integers(0, 150, k1)], pool[rng.integers(0, 150, k2)]
+        cl = rng.standard_normal(k1) + 1j * rng.standard_normal(k1)
+        cr = rng.standard_normal(k2) + 1j * rng.standard_normal(k2)
+        bra = QuantumState(left, cl, vec_type='bra')
+        ket = QuantumState(right, cr, vec_type='ket')
+        dl, dr = {}, {}
+        for r, v in zip(left, cl):
+            dl[r.tobytes()] = dl.get(r.tobytes(), 0) + v
+        for r, v in zip(right, cr):
+            dr[r.tobytes()] = dr.get(r.tobytes(), 0) + v
+        ref = sum(v * dr[k] for k, v in dl.items() if k in dr)
+        assert np.isclose(bra * ket, ref, rtol=1e-12, atol=1e-12)
