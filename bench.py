@@ -547,7 +547,7 @@ def one_gpu_extras(torch, ops, sdist, PauliwordOp, dev, timed, flush):
     del big, blk
     out["commute"] = {"metric": "commute-pair checks/s", "value": pairs / (min(cms) * 1e-3), "unit": "pairs/s",
                       "workload": "16384 x 65536 block of a 1024-bit-wide (1000-qubit layout) adjacency matrix, random rows",
-                      "kernel": "commute_mma_kernel (tcgen05 kind::i8, TMEM accumulators)",
+                      "kernel": "commute_mma_ws_kernel (tcgen05 kind::i8, TMEM accumulators, warp-specialised expander / issuer warps)",
                       "int8_tops": pairs * 2 * 2048 / (min(cms) * 1e-3) / 1e12,
                       "note": "K = 2048 unpacked bits per pair; nominal dense int8 peak 4500 TOP/s"}
 

@@ -369,7 +369,7 @@ static int g_ordered_tiles = 1;
 // key costs two 64-bit multiplies and runs twice, in the histogram and in pass 0, against 0.15 ms
 // for pair_keys_kernel writing 1 GB once) = a separate kernel writes them first
 static int g_fused_keys = 0;
-namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; extern int g_rref_variant; extern int g_tile_qgroup; extern int g_onesweep; extern int g_class_dedup; extern int g_class_variant; }
+namespace symb { extern int g_emit_variant; extern int g_scatter_variant; extern int g_sort_extra_bits; extern int g_apply_variant; extern int g_rref_variant; extern int g_tile_qgroup; extern int g_onesweep; extern int g_class_dedup; extern int g_class_variant; extern int g_commute_variant; }
 
 extern "C" int sym_set_tuning(int32_t which, int64_t value) {
     if (which == 0) {
@@ -418,6 +418,10 @@ extern "C" int sym_set_tuning(int32_t which, int64_t value) {
     }
     if (which == 11) {
         symb::g_class_variant = (int)value;
+        return SYM_OK;
+    }
+    if (which == 12) {
+        symb::g_commute_variant = (int)value;
         return SYM_OK;
     }
     set_error("unknown tuning knob %d", which);
