@@ -44,9 +44,9 @@ __device__ __forceinline__ int cd_block_of(const uint32_t *base, int nblk, uint3
 
 // cnt[0, tab): rows of A per table index; cnt[tab, 2 tab): rows of B per table index
 __global__ void __launch_bounds__(256) cd_hist_kernel(ClassJob J, const uint64_t *__restrict__ a_sk, uint32_t *__restrict__ cnt,
-                                                       uint32_t tab) {
+                                                       uint32_t tab, uint32_t n_rows_a) {   // n_rows_a: J.n_entries, or 0 (done elsewhere)
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < J.n_entries) {
+    if (e < n_rows_a) {
         const int b = cd_block_of(J.entry_base, J.nblk, e);
         const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
         atomicAdd(cnt + (((uint32_t)b << (J.k + 1)) | cd_class_of(a_sk[p], J.k)), 1u);
@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(256) cd_place_kernel(ClassJob J, const uint64_
                                                         uint32_t *__restrict__ cursor, uint32_t tab, uint64_t *__restrict__ look8,
                                                         uint32_t *__restrict__ lookp, uint32_t *__restrict__ vkey,
                                                         uint32_t *__restrict__ vq, uint64_t *__restrict__ vsk,
-                                                        uint32_t *__restrict__ bits, uint32_t n_visits_padded) {
+                                                        uint32_t *__restrict__ bits, uint32_t n_visits_padded, uint32_t n_rows_a) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= J.n_visits && e < n_visits_padded) vkey[e] = 1u << J.k;   // never matches: classes stop at 2^k - 1
-    if (e < J.n_entries) {
+    if (e < n_rows_a) {
         const int b = cd_block_of(J.entry_base, J.nblk, e);
         const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
         const uint64_t sk = a_sk[p];
@@ -92,6 +92,58 @@ __global__ void __launch_bounds__(256) cd_place_kernel(ClassJob J, const uint64_
             if (t < tab && off[t + 1] > off[t]) w |= 1u << i;
         }
         bits[e] = w;
+    }
+}
+
+// Many rows per table entry (a rotation as a block-list product: 1e7 rows of A over a few thousand classes): the global
+// atomics of the two kernels above would pile up on the same counters. These forms privatise the counters per CTA in
+// shared memory: a CTA owns CD_CHUNK consecutive rows of A, counts them in shared memory and touches every global
+// counter at most once.
+constexpr uint32_t CD_CHUNK = 65536;
+
+__global__ void __launch_bounds__(1024) cd_hist_priv_kernel(ClassJob J, const uint64_t *__restrict__ a_sk, uint32_t *__restrict__ cnt,
+                                                             uint32_t tab) {
+    extern __shared__ uint32_t cd_priv[];
+    for (uint32_t i = threadIdx.x; i < tab; i += blockDim.x) cd_priv[i] = 0u;
+    __syncthreads();
+    const uint32_t e0 = blockIdx.x * CD_CHUNK, e1 = min(J.n_entries, e0 + CD_CHUNK);
+    for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int b = cd_block_of(J.entry_base, J.nblk, e);
+        const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
+        atomicAdd(cd_priv + (((uint32_t)b << (J.k + 1)) | cd_class_of(a_sk[p], J.k)), 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tab; i += blockDim.x)
+        if (cd_priv[i]) atomicAdd(cnt + i, cd_priv[i]);
+}
+
+__global__ void __launch_bounds__(1024) cd_place_priv_kernel(ClassJob J, const uint64_t *__restrict__ a_sk,
+                                                              const uint32_t *__restrict__ off, uint32_t *__restrict__ cursor,
+                                                              uint32_t tab, uint64_t *__restrict__ look8, uint32_t *__restrict__ lookp) {
+    extern __shared__ uint32_t cd_priv[];
+    uint32_t *count = cd_priv, *base = cd_priv + tab;
+    for (uint32_t i = threadIdx.x; i < tab; i += blockDim.x) count[i] = 0u;
+    __syncthreads();
+    const uint32_t e0 = blockIdx.x * CD_CHUNK, e1 = min(J.n_entries, e0 + CD_CHUNK);
+    for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int b = cd_block_of(J.entry_base, J.nblk, e);
+        const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
+        atomicAdd(count + (((uint32_t)b << (J.k + 1)) | cd_class_of(a_sk[p], J.k)), 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tab; i += blockDim.x) {
+        base[i] = count[i] ? off[i] + atomicAdd(cursor + i, count[i]) : 0u;   // this CTA's range of the entry
+        count[i] = 0u;
+    }
+    __syncthreads();
+    for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int b = cd_block_of(J.entry_base, J.nblk, e);
+        const uint32_t p = J.p0[b] + (e - J.entry_base[b]);
+        const uint64_t sk = a_sk[p];
+        const uint32_t key = ((uint32_t)b << (J.k + 1)) | cd_class_of(sk, J.k);
+        const uint32_t pos = base[key] + atomicAdd(count + key, 1u);
+        look8[pos] = sk;
+        lookp[pos] = p;
     }
 }
 
@@ -598,16 +650,35 @@ int class_dedup_run(ClassJob &J, const uint64_t *a_sk, const uint64_t *b_sk, con
     J.vkey = vkey;
     J.vq = vq;
     J.vsk = vsk;
-    const uint32_t n1 = J.n_entries > J.n_visits ? J.n_entries : J.n_visits;
+    // many rows of A per table entry: privatised counters (the visits still take the plain kernels, with no rows of A)
+    const bool priv = tab <= 12288 && (size_t)J.n_entries >= 16 * tab && J.n_entries >= (1u << 18);
+    const uint32_t n_rows_a = priv ? 0u : J.n_entries;
+    if (priv) {
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+            SYM_CUDA_OK(cudaFuncSetAttribute(cd_place_priv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 12288 * 4));
+            attr_done[dev] = true;
+        }
+        cd_hist_priv_kernel<<<(J.n_entries + CD_CHUNK - 1) / CD_CHUNK, 1024, tab * 4, st>>>(J, a_sk, off, (uint32_t)tab);
+        SYM_LAUNCH_OK();
+    }
+    const uint32_t n1 = n_rows_a > J.n_visits ? n_rows_a : J.n_visits;
     if (n1) {
-        cd_hist_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(J, a_sk, off, (uint32_t)tab);
+        cd_hist_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(J, a_sk, off, (uint32_t)tab, n_rows_a);
         SYM_LAUNCH_OK();
     }
     SYM_TRY(scan_exclusive_u32(off, off, (int64_t)(2 * tab), nullptr, scratch, st));
+    if (priv) {
+        cd_place_priv_kernel<<<(J.n_entries + CD_CHUNK - 1) / CD_CHUNK, 1024, 2 * tab * 4, st>>>(J, a_sk, off, cursor, (uint32_t)tab,
+                                                                                                 look8, lookp);
+        SYM_LAUNCH_OK();
+    }
     uint32_t n2 = n1 > (uint32_t)((tab + 31) / 32) ? n1 : (uint32_t)((tab + 31) / 32);
     if (n2 < (uint32_t)nvp) n2 = (uint32_t)nvp;
     cd_place_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(J, a_sk, off, cursor, (uint32_t)tab, look8, lookp, vkey, vq, vsk, bits,
-                                                     (uint32_t)nvp);
+                                                     (uint32_t)nvp, n_rows_a);
     SYM_LAUNCH_OK();
     if (class_cap(J.variant) == 9216) SYM_TRY((cd_launch<1024, 9216, 14, 1>(J, rows, tm, thr, cand, over, counters, st)));
     else SYM_TRY((cd_launch<512, 4096, 13, 2>(J, rows, tm, thr, cand, over, counters, st)));
