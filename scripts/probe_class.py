@@ -51,7 +51,7 @@ def main():
             continue
         a, ac = ops.pack(torch.from_numpy(xs), N_QUBITS), torch.from_numpy(xc).to(dev)
         b, bc = ops.pack(torch.from_numpy(ys), N_QUBITS), torch.from_numpy(yc).to(dev)
-        for label, knobs in (("sort", {10: 0}), ("class512", {10: 1, 11: 0}), ("class1024", {10: 1, 11: 1})):
+        for label, knobs in (("sort", {10: 0}), ("class1024", {10: 1, 11: 1}), ("class32", {10: 1, 11: 2})):
             if os.environ.get("PROBE_ONLY") and os.environ["PROBE_ONLY"] not in label:
                 continue
             for k, v in knobs.items():
@@ -59,7 +59,7 @@ def main():
             ms, U = time_product(a, ac, b, bc)
             print(json.dumps({"operands": name, "dedup": label, "ms": ms, "U": U, "T": rows_a * rows_b}), flush=True)
     ops.set_tuning(10, 1)
-    ops.set_tuning(11, 1)
+    ops.set_tuning(11, 2)
 
 
 if __name__ == "__main__":

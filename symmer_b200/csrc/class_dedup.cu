@@ -208,9 +208,15 @@ __device__ __forceinline__ uint32_t cd_block_prefix(uint32_t x, uint32_t *s_warp
 // every thread a private range of the list, then it writes its pairs — no atomics, no warp votes, and the list
 // ends up in visit order. OVER = false: pairs (entry of A, visit) go to the shared-memory list (beyond CAP they are
 // only counted); OVER = true: the records themselves go to the overflow array at over_base.
-template <int THREADS, int CAP, bool OVER>
+__device__ __forceinline__ void cd_store_pair(uint2 *pairs, uint32_t pos, uint32_t lo, uint32_t v, int) { pairs[pos] = make_uint2(lo, v); }
+__device__ __forceinline__ void cd_store_pair(uint32_t *pairs, uint32_t pos, uint32_t lo, uint32_t v, int vbits) {
+    pairs[pos] = (lo << vbits) | v;
+}
+
+template <int THREADS, int CAP, bool OVER, typename PairT = uint2>
 __device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, const uint32_t *bm, bool bm_shared, uint32_t *s_count,
-                                             uint32_t *s_warp, uint2 *pairs, uint64_t *__restrict__ over, uint32_t over_base) {
+                                             uint32_t *s_warp, PairT *pairs, uint64_t *__restrict__ over, uint32_t over_base,
+                                             int vbits = 0) {
     constexpr int VPT = CD_VPT;
     const int tid = threadIdx.x;
     for (uint32_t v0 = 0; v0 < J.n_visits; v0 += THREADS * VPT) {   // vkey is padded with never-matching keys to whole chunks
@@ -248,10 +254,10 @@ __device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, cons
                 for (int u = 0; u < VPT; ++u) {
                     if (n[u] == 0u) continue;
                     const uint32_t v = vb + u;
-                    pairs[pos++] = make_uint2(lo[u], v);
+                    cd_store_pair(pairs, pos++, lo[u], v, vbits);
                     if (n[u] > 1u) {
-                        pairs[pos++] = make_uint2(lo[u] + 1, v);
-                        for (uint32_t j = 2; j < n[u]; ++j) pairs[pos++] = make_uint2(lo[u] + j, v);
+                        cd_store_pair(pairs, pos++, lo[u] + 1, v, vbits);
+                        for (uint32_t j = 2; j < n[u]; ++j) cd_store_pair(pairs, pos++, lo[u] + j, v, vbits);
                     }
                 }
             } else {
@@ -259,7 +265,7 @@ __device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, cons
                 for (int u = 0; u < VPT; ++u) {
                     const uint32_t v = vb + u;
                     for (uint32_t j = 0; j < n[u]; ++j, ++pos)
-                        if (pos < (uint32_t)CAP) pairs[pos] = make_uint2(lo[u] + j, v);
+                        if (pos < (uint32_t)CAP) cd_store_pair(pairs, pos, lo[u] + j, v, vbits);
                 }
             }
         } else {
@@ -286,6 +292,7 @@ __device__ __forceinline__ uint32_t cd_fold(uint64_t ent) {
 }
 
 constexpr int CD_BM_WORDS = 2048;
+constexpr int CD32_BM_WORDS = 1024; // the same for the compact kernel (4 KB)
 constexpr int CD_SMALL_GROUP = 16;  // hash groups up to this size are ordered by insertion inside the class kernel   // shared-memory copy of the non-empty bitmap when the table has <= 65536 entries
 
 // counters: [0] candidates written, [1] overflow records written, [2] overflowed classes, [3] = [0] + [1] (set afterwards)
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
         }
         for (int i = tid; i < CAP / 4; i += THREADS) reinterpret_cast<uint32_t *>(mate)[i] = 0u;
         __syncthreads();
-        cd_enumerate<THREADS, CAP, false>(J, c, s_bits, bm_shared, &s_count, s_warp, pairs, nullptr, 0u);
+        cd_enumerate<THREADS, CAP, false, uint2>(J, c, s_bits, bm_shared, &s_count, s_warp, pairs, nullptr, 0u);
         __syncthreads();
         const uint32_t total = s_count;
         if (total > (uint32_t)CAP) {   // the class does not fit: its records take the global sort
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
                 s_count = 0;
             }
             __syncthreads();
-            cd_enumerate<THREADS, CAP, true>(J, c, s_bits, bm_shared, &s_count, s_warp, nullptr, over, s_base);
+            cd_enumerate<THREADS, CAP, true, uint2>(J, c, s_bits, bm_shared, &s_count, s_warp, (uint2 *)nullptr, over, s_base);
             __syncthreads();
             continue;
         }
@@ -514,6 +521,209 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compact form of the class kernel (tuning knob 11 = 2, the default when the table indices fit 32 bits): 4-byte pair
+// entries ((entry of A << vbits) | visit) and 4-byte table entries [hash : 16 | local id : 16] (with the slot, 31 hash
+// bits decide "same hash": ~0.03 false candidate pairs per class), so one CTA holds 18 432 records instead of 9 216 and
+// the product needs HALF the classes: half the visits, half the per-class barriers. Candidates are placed straight
+// into the global candidate array by the counting sort (small groups ordered by their owner thread afterwards); a
+// class with a large hash group, or with records that never found a slot, sends its candidates to the overflow array.
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int CAP, int LOG_SLOTS>
+__global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, ProductRows rows, TileMap tm, double thr,
+                                                                    uint64_t *__restrict__ cand, uint64_t *__restrict__ over,
+                                                                    uint32_t *__restrict__ counters, int vbits) {
+    constexpr int SLOTS = 1 << LOG_SLOTS;
+    constexpr int RPT = CAP / THREADS;
+    static_assert(CAP % THREADS == 0 && CAP <= 65536 && RPT <= 32, "record ids are 16 bits, one state bit per record");
+    static_assert(CAP <= SLOTS, "the group counters live in the table after the rounds");
+    extern __shared__ __align__(16) unsigned char cd_smem[];
+    uint32_t *table = reinterpret_cast<uint32_t *>(cd_smem);
+    uint32_t *pairs = table + SLOTS;
+    uint8_t *mate = reinterpret_cast<uint8_t *>(pairs + CAP);
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(mate + CAP);
+    __shared__ uint32_t s_count, s_ncand, s_base;
+    __shared__ uint32_t s_warp[33];
+    const int tid = threadIdx.x;
+    const uint32_t K = 1u << J.k;
+    const uint32_t vmask = (1u << vbits) - 1u;
+    const bool check_thr = !(thr < 0.0 || rows.all_pass());
+    const uint32_t bm_words = (((uint32_t)J.nblk << (J.k + 1)) + 31u) / 32u;
+    const bool bm_shared = bm_words <= (uint32_t)CD32_BM_WORDS;
+    if (bm_shared)
+        for (uint32_t i = tid; i < bm_words; i += THREADS) s_bits[i] = J.bits[i];
+
+    for (uint32_t c = blockIdx.x; c < K; c += gridDim.x) {
+        if (tid == 0) {
+            s_count = 0;
+            s_ncand = 0;
+        }
+        for (int i = tid; i < CAP / 4; i += THREADS) reinterpret_cast<uint32_t *>(mate)[i] = 0u;
+        __syncthreads();
+        cd_enumerate<THREADS, CAP, false, uint32_t>(J, c, s_bits, bm_shared, &s_count, s_warp, pairs, nullptr, 0u, vbits);
+        __syncthreads();
+        const uint32_t total = s_count;
+        if (total > (uint32_t)CAP) {   // the class does not fit: its records take the global sort
+            __syncthreads();
+            if (tid == 0) {
+                s_base = atomicAdd(counters + 1, total);
+                atomicAdd(counters + 2, 1u);
+                s_count = 0;
+            }
+            __syncthreads();
+            cd_enumerate<THREADS, CAP, true, uint32_t>(J, c, s_bits, bm_shared, &s_count, s_warp, (uint32_t *)nullptr, over, s_base, vbits);
+            __syncthreads();
+            continue;
+        }
+        // ---- records of this thread: the top 32 bits of the mixed sketch are THE hash of this kernel
+        uint32_t h32[RPT];
+        uint32_t rr[RPT];      // representative (local id) of the record's hash group; later | rank << 16
+        uint32_t unres = 0, candm = 0, winm = 0;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const uint32_t i = tid + j * THREADS;
+            h32[j] = 0;
+            rr[j] = i;
+            if (i < total) {
+                const uint32_t pr = pairs[i];
+                h32[j] = (uint32_t)((mix64(__ldg(J.look8 + (pr >> vbits)) ^ __ldg(J.vsk + (pr & vmask))) & J.key_mask) >> 32);
+                unres |= 1u << j;
+            }
+        }
+        for (int round = 0; round < CD_MAX_ROUNDS; ++round) {
+            const uint32_t mult = 0x9E3779B1u + 2u * (uint32_t)round * 0x632BE5ABu;   // odd for every round
+            const uint32_t add = (uint32_t)round * 0x7F4A7C15u;
+            if (unres) {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j)
+                    if ((unres >> j) & 1u) table[(h32[j] * mult + add) >> (32 - LOG_SLOTS)] = (h32[j] & 0xffff0000u) | (tid + j * THREADS);
+            }
+            if (!__syncthreads_or(unres != 0u)) break;
+            if (unres) {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    if ((unres >> j) & 1u) {
+                        const uint32_t mine = (h32[j] & 0xffff0000u) | (tid + j * THREADS);
+                        const uint32_t v = table[(h32[j] * mult + add) >> (32 - LOG_SLOTS)];
+                        if (v == mine) {
+                            winm |= 1u << j;
+                            unres &= ~(1u << j);
+                        } else if (((v ^ mine) >> 16) == 0u) {
+                            rr[j] = v & 0xffffu;
+                            mate[rr[j]] = 1;
+                            candm |= 1u << j;
+                            unres &= ~(1u << j);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        candm |= unres;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j)
+            if (((winm >> j) & 1u) && mate[tid + j * THREADS] != 0) candm |= 1u << j;
+        if (check_thr) {   // unique rows survive unless their own coefficient fails the threshold
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const uint32_t i = tid + j * THREADS;
+                if (i < total && !((candm >> j) & 1u)) {
+                    const uint32_t pr = pairs[i];
+                    const uint32_t t = J.vq[pr & vmask] * J.M_total + J.lookp[pr >> vbits];
+                    double re, im;
+                    rows.coeff_unphased(t, re, im);
+                    if (!keep_test(re, im, thr)) tm.mark_dropped(t);
+                }
+            }
+        }
+        if (__syncthreads_or(candm != 0u)) {
+            uint32_t *cnt = table;   // CAP group counters, then their offsets
+            for (int i = tid; i < CAP; i += THREADS) cnt[i] = 0u;
+            __syncthreads();
+            bool slow = (candm & unres) != 0u;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                if (((candm & ~unres) >> j) & 1u) rr[j] |= atomicAdd(cnt + rr[j], 1u) << 16;
+            __syncthreads();
+            uint32_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const uint32_t cj = cnt[tid + j * THREADS];
+                slow |= cj > (uint32_t)CD_SMALL_GROUP;
+                sum += cj;
+            }
+            if (!__syncthreads_or(slow)) {
+                uint32_t nc;
+                const uint32_t first = cd_block_prefix<THREADS>(sum, s_warp, &s_ncand, nc);
+                if (tid == 0) s_base = atomicAdd(counters, nc);
+                uint32_t base = first;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    const uint32_t cj = cnt[tid + j * THREADS];
+                    cnt[tid + j * THREADS] = base;
+                    base += cj;
+                }
+                __syncthreads();
+                uint64_t *dst = cand + s_base;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    if ((candm >> j) & 1u) {
+                        const uint32_t pr = pairs[tid + j * THREADS];
+                        const uint32_t v = pr & vmask, lo = pr >> vbits;
+                        const int b = J.nblk == 1 ? 0 : (int)(J.vkey[v] >> (J.k + 1));
+                        dst[cnt[rr[j] & 0xffffu] + (rr[j] >> 16)] =
+                            ((uint64_t)(h32[j] >> (32 - J.hbits)) << 32) | cd_ord_of(J, b, J.lookp[lo], J.vq[v]);
+                    }
+                }
+                __syncthreads();
+                // the thread that owns a representative orders its group (2-3 records) by enumeration position
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    const uint32_t off_j = cnt[tid + j * THREADS];
+                    const uint32_t end_j = j + 1 < RPT ? cnt[tid + (j + 1) * THREADS] : first + sum;
+                    const uint32_t cj = end_j - off_j;
+                    if (cj >= 2u) {
+                        uint64_t *seg = dst + off_j;
+                        for (uint32_t a = 1; a < cj; ++a) {
+                            const uint64_t key = seg[a];
+                            uint32_t bpos = a;
+                            while (bpos > 0 && seg[bpos - 1] > key) {
+                                seg[bpos] = seg[bpos - 1];
+                                --bpos;
+                            }
+                            seg[bpos] = key;
+                        }
+                    }
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i < nc; i += THREADS) {   // [hash | ord] -> candidate record [hash | t | 0]
+                    const uint64_t key = dst[i];
+                    dst[i] = ((key >> 32) << (64 - J.hbits)) | ((uint64_t)cd_t_of_ord(J, (uint32_t)key) << 2);
+                }
+            } else {
+                // a large hash group (a square's identity terms, a molecular H*H) or records without a slot: this class's
+                // candidates take the global sort with the overflowed classes
+                uint32_t nc;
+                uint32_t pos = cd_block_prefix<THREADS>((uint32_t)__popc(candm), s_warp, &s_ncand, nc);
+                if (tid == 0) s_base = atomicAdd(counters + 1, nc);
+                __syncthreads();
+                const uint32_t ob = s_base;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    if ((candm >> j) & 1u) {
+                        const uint32_t pr = pairs[tid + j * THREADS];
+                        const uint32_t v = pr & vmask, lo = pr >> vbits;
+                        const int b = J.nblk == 1 ? 0 : (int)(J.vkey[v] >> (J.k + 1));
+                        const uint64_t ord = cd_ord_of(J, b, J.lookp[lo], J.vq[v]);
+                        over[(size_t)ob + pos++] = ((((uint64_t)h32[j] << 32) >> (J.tb + 2)) << (J.tb + 2)) | (ord << 2);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void cd_total_kernel(uint32_t *counters) { counters[3] = counters[0] + counters[1]; }
 
 // overflow records were sorted on (hash, ord): put t back into their term field
@@ -538,7 +748,12 @@ int class_ord_to_t(const ClassJob &J, uint64_t *recs, uint32_t n, cudaStream_t s
 int g_class_dedup = 1;   // tuning knob 10: 1 (default) = class-local duplicate detection for ordered-tile products, 0 = global record sort
 
 extern int g_class_variant;
-static int class_cap(int variant) { return variant == 1 ? 9216 : 4096; }
+static int cd_bits_for(uint32_t n) {   // bits that hold every index below n
+    int b = 1;
+    while (b < 32 && (1ull << b) < n) ++b;
+    return b;
+}
+static int class_cap(int variant) { return variant == 2 ? 18432 : (variant == 1 ? 9216 : 4096); }
 
 bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t T, int tb, uint64_t key_mask, ClassJob &J,
                     bool ignore_knob) {   // ignore_knob: workspace sizing — the shape with the larger tables
@@ -568,6 +783,7 @@ bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t 
     // classes: the average class fills at most 85 % of a CTA's pair list; small products still get enough classes
     // to occupy the GPU
     J.variant = ignore_knob ? 0 : g_class_variant;
+    if (J.variant == 2 && cd_bits_for((uint32_t)entries) + cd_bits_for((uint32_t)cd_padded_visits((uint32_t)visits)) > 32) J.variant = 1;
     int64_t target = (int64_t)(0.85 * class_cap(J.variant));
     if (T / 1024 < target) target = T / 1024 > 256 ? T / 1024 : 256;
     int k = 0;
@@ -597,7 +813,8 @@ size_t class_job_ws_bytes(const ClassJob &J) {
            arena_need(ne, 8) + arena_need(ne, 4) + arena_need(cd_padded_visits(J.n_visits), 4) + arena_need(nv, 4) + arena_need(nv, 8) + 1024;
 }
 
-int g_class_variant = 1;    // tuning knob 11: CTA shape of the class kernel (0: 512 threads x 2 CTAs/SM, 1 (default, measured faster): 1024 threads x 1)
+int g_class_variant = 2;    // tuning knob 11: class kernel (0: 512 threads x 2 CTAs/SM, 4096 records; 1: 1024 threads, 9216 records;
+                            // 2 (default): compact 4-byte entries, 1024 threads, 18432 records per class)
 
 template <int THREADS, int CAP, int LOG_SLOTS, int MINB>
 static int cd_launch(const ClassJob &J, const ProductRows &rows, const TileMap &tm, double thr, uint64_t *cand, uint64_t *over,
@@ -680,8 +897,25 @@ int class_dedup_run(ClassJob &J, const uint64_t *a_sk, const uint64_t *b_sk, con
     cd_place_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(J, a_sk, off, cursor, (uint32_t)tab, look8, lookp, vkey, vq, vsk, bits,
                                                      (uint32_t)nvp, n_rows_a);
     SYM_LAUNCH_OK();
-    if (class_cap(J.variant) == 9216) SYM_TRY((cd_launch<1024, 9216, 14, 1>(J, rows, tm, thr, cand, over, counters, st)));
-    else SYM_TRY((cd_launch<512, 4096, 13, 2>(J, rows, tm, thr, cand, over, counters, st)));
+    if (J.variant == 2) {
+        constexpr int CAP = 18432, LOG_SLOTS = 15;
+        constexpr size_t smem = ((size_t)1 << LOG_SLOTS) * 4 + (size_t)CAP * 4 + CAP + (size_t)CD32_BM_WORDS * 4;
+        auto kern = class_dedup32_kernel<1024, CAP, LOG_SLOTS>;
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+            SYM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done[dev] = true;
+        }
+        const unsigned grid = (unsigned)std::min<uint32_t>(1u << J.k, (uint32_t)num_sms());
+        kern<<<grid, 1024, smem, st>>>(J, rows, tm, thr, cand, over, counters, cd_bits_for((uint32_t)nvp));
+        SYM_LAUNCH_OK();
+    } else if (class_cap(J.variant) == 9216) {
+        SYM_TRY((cd_launch<1024, 9216, 14, 1>(J, rows, tm, thr, cand, over, counters, st)));
+    } else {
+        SYM_TRY((cd_launch<512, 4096, 13, 2>(J, rows, tm, thr, cand, over, counters, st)));
+    }
     cd_total_kernel<<<1, 1, 0, st>>>(counters);
     SYM_LAUNCH_OK();
     return SYM_OK;

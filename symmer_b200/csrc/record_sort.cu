@@ -400,10 +400,12 @@ template <class Src, int TH, int IT, int MB>
 static int os_launch_shape(const Src &src, uint64_t *out, int64_t T, int shift, uint32_t mask, const uint32_t *bases,
                            uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st) {
     constexpr size_t smem = RS_TILE * 8 + (TH / 32) * RS_RADIX * 4 + 2 * RS_RADIX * 4 + 32 * 4 + 64;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};   // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
         SYM_CUDA_OK(cudaFuncSetAttribute(os_pass_kernel<Src, TH, IT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     SYM_CUDA_OK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * (size_t)RS_RADIX * (size_t)ntiles, st));
     os_pass_kernel<Src, TH, IT, MB><<<(unsigned)ntiles, TH, smem, st>>>(src, out, T, shift, mask, bases, state, ticket);
@@ -464,11 +466,13 @@ static int rs_pass(const uint64_t *in, uint64_t *out, int64_t T, int shift, uint
 #define RS_LAUNCH(TH, IT, MB)                                                                                     \
     {                                                                                                             \
         constexpr size_t smem = RS_TILE * 8 + (TH / 32) * RS_RADIX * 4 + 2 * RS_RADIX * 4 + 64;                   \
-        static bool attr_done = false;                                                                            \
-        if (!attr_done) {                                                                                         \
+        static bool attr_done[64] = {};                                                                           \
+        int dev_ = 0;                                                                                             \
+        cudaGetDevice(&dev_);                                                                                     \
+        if (dev_ >= 0 && dev_ < 64 && !attr_done[dev_]) {                                                         \
             SYM_CUDA_OK(cudaFuncSetAttribute(rs_scatter_kernel<TH, IT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem));                                                         \
-            attr_done = true;                                                                                     \
+            attr_done[dev_] = true;                                                                               \
         }                                                                                                         \
         rs_scatter_kernel<TH, IT, MB><<<(unsigned)ntiles, TH, smem, st>>>(in, out, T, shift, mask, hist, ntiles); \
     }

@@ -44,8 +44,10 @@ def check_both_paths(ops, a_s, a_c, b_s, b_c, thr=1e-15, scale_mult=1.0, order=T
     out = {}
     try:
         ops.set_tuning(0, 0)                      # force the large-product (ordered-tile) path
-        for knob in (1, 0):
-            ops.set_tuning(10, knob)
+        # (knob 10, knob 11): class mode with the compact kernel (default), with the 8-byte-entry kernel, and the record sort
+        for knob in ((1, 2), (1, 1), (0, 2)):
+            ops.set_tuning(10, knob[0])
+            ops.set_tuning(11, knob[1])
             xz, c = ops.mul_cleanup(*dev_op(ops, a_s, a_c), *dev_op(ops, b_s, b_c), thr)
             s, cc = host_op(ops, xz, c, n)
             ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=scale)
@@ -55,11 +57,14 @@ def check_both_paths(ops, a_s, a_c, b_s, b_c, thr=1e-15, scale_mult=1.0, order=T
             out[knob] = (s, cc)
     finally:
         ops.set_tuning(10, 1)
+        ops.set_tuning(11, 2)
         ops.set_tuning(0, 1 << 22)
-    if len(out[0][1]) == len(out[1][1]):
-        assert np.array_equal(out[0][0], out[1][0])
-        assert np.allclose(out[0][1], out[1][1], rtol=1e-12, atol=1e-12 * scale)
-    return out[1]
+    base = out[(0, 2)]
+    for knob in ((1, 2), (1, 1)):
+        if len(base[1]) == len(out[knob][1]):
+            assert np.array_equal(base[0], out[knob][0]), knob
+            assert np.allclose(base[1], out[knob][1], rtol=1e-12, atol=1e-12 * scale), knob
+    return out[(1, 2)]
 
 
 @pytest.mark.parametrize("n,m1,m2", [(1000, 700, 300), (64, 1500, 400), (200, 3000, 150), (30, 2000, 700)])
@@ -172,3 +177,39 @@ def test_class_mode_many_classes_medium_size(ops):
         slot = int((t_kept == t_head).nonzero()[0, 0])
         j = int(np.flatnonzero((ref_s == ops.unpack(xz[slot:slot + 1].contiguous(), n).cpu().numpy()[0]).all(axis=1))[0])
         assert np.isclose(c[slot].item(), ref_c[j], rtol=1e-12, atol=1e-14)
+
+
+def test_owner_partition_on_structured_operators(ops, hamiltonians):
+    """The exchange-free multi-GPU product (GF(2)-linear owner classes) on operators that are NOT random: a molecular
+    Hamiltonian squared (rows in a 28-dimensional space, heavy multiplicities) and operands from a 10-generator span.
+    Every "rank" is played in turn on one device: the parts must be disjoint, carry their owner class, cover every cross
+    term exactly once, and their union must be the oracle product; the linear owner must not collapse onto few ranks."""
+    from symmer_b200 import dist as sdist
+    h_s, h_c, _ = hamiltonians("H2O_STO3G")
+    rng = np.random.default_rng(5)
+    gens = rng.random((10, 2 * 200)) < 0.3
+    sa, sac = span_operator(gens, 700, rng)
+    sb, sbc = span_operator(gens, 300, rng)
+    for (a_s, a_c, b_s, b_c, scale_mult) in ((h_s, h_c, h_s, h_c, 1086.0), (sa, sac, sb, sbc, 700 * 300 / 1024.0 * 4)):
+        n = a_s.shape[1] // 2
+        ref_s, ref_c = po.multiply_by_operator(a_s, a_c, b_s, b_c)
+        a, ac = dev_op(ops, a_s, a_c)
+        b, bc = dev_op(ops, b_s, b_c)
+        for log2g in (1, 3):
+            rows, coeffs, generated, sizes = [], [], 0, []
+            for r in range(1 << log2g):
+                xz, c, info = sdist.owned_product(a, ac, b, bc, log2g, r)
+                generated += info["cross_terms_generated"]
+                sizes.append(info["cross_terms_generated"])
+                if xz.shape[0]:
+                    assert bool((ops.owner_classes(xz, log2g) == r).all())
+                s, cc = host_op(ops, xz, c, n)
+                rows.append(s)
+                coeffs.append(cc)
+            assert generated == a_s.shape[0] * b_s.shape[0]
+            assert max(sizes) <= 2.0 * generated / len(sizes), sizes          # no rank gets more than twice its share
+            s, cc = np.vstack(rows), np.hstack(coeffs)
+            assert len(np.unique(s, axis=0)) == len(s)
+            scale = float(np.abs(a_c).max() * np.abs(b_c).max()) * scale_mult
+            ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=scale)
+            assert ok, (n, log2g, why)
