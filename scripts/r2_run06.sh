@@ -19,6 +19,6 @@ for r in rows[hi+1:]:
         seen.setdefault(r[ki][:48],[]).append(float(r[vi].replace(',',''))/1e6)
 for k,v in seen.items(): print(k, ' '.join(f'{x:.3f}' for x in v[2::6][:8]))
 PY
-PROBE_ONLY=${NCU_VARIANT:-class32} timeout 200 ncu --set full --clock-control none --import-source on -k regex:"class_dedup_kernel" -s 2 -c 1 \
+PROBE_ONLY=${NCU_VARIANT:-class32} timeout 200 ncu --set full --clock-control none --import-source on -k regex:"class_dedup" -s 2 -c 1 \
     -o gpurun_out/${T}_classk python scripts/probe_class.py > gpurun_out/${T}_ncu1.log 2>&1
 tail -1 gpurun_out/${T}_ncu1.log

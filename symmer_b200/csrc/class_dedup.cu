@@ -251,14 +251,14 @@ __device__ __forceinline__ void cd_enumerate(const ClassJob &J, uint32_t c, cons
         if (!OVER) {
             if (running <= (uint32_t)CAP) {   // block-uniform: the whole chunk fits, no bound checks
 #pragma unroll
-                for (int u = 0; u < VPT; ++u) {
-                    if (n[u] == 0u) continue;
-                    const uint32_t v = vb + u;
-                    cd_store_pair(pairs, pos++, lo[u], v, vbits);
-                    if (n[u] > 1u) {
-                        cd_store_pair(pairs, pos++, lo[u] + 1, v, vbits);
-                        for (uint32_t j = 2; j < n[u]; ++j) cd_store_pair(pairs, pos++, lo[u] + j, v, vbits);
-                    }
+                for (int u = 0; u < VPT; ++u) {   // predicated stores for the common counts (no divergent branches), a loop beyond
+                    const uint32_t v = vb + u, nn = n[u];
+                    if (nn > 0u) cd_store_pair(pairs, pos, lo[u], v, vbits);
+                    if (nn > 1u) cd_store_pair(pairs, pos + 1, lo[u] + 1, v, vbits);
+                    if (nn > 2u) cd_store_pair(pairs, pos + 2, lo[u] + 2, v, vbits);
+                    if (nn > 3u) cd_store_pair(pairs, pos + 3, lo[u] + 3, v, vbits);
+                    for (uint32_t j = 4; j < nn; ++j) cd_store_pair(pairs, pos + j, lo[u] + j, v, vbits);
+                    pos += nn;
                 }
             } else {
 #pragma unroll
