@@ -292,7 +292,7 @@ __device__ __forceinline__ uint32_t cd_fold(uint64_t ent) {
 }
 
 constexpr int CD_BM_WORDS = 2048;
-constexpr int CD32_BM_WORDS = 1024; // the same for the compact kernel (4 KB)
+constexpr int CD32_BM_WORDS = 5120; // the same for the compact kernel (20 KB: 8 blocks of 2^14 table entries)
 constexpr int CD_SMALL_GROUP = 16;  // hash groups up to this size are ordered by insertion inside the class kernel   // shared-memory copy of the non-empty bitmap when the table has <= 65536 entries
 
 // counters: [0] candidates written, [1] overflow records written, [2] overflowed classes, [3] = [0] + [1] (set afterwards)
@@ -540,8 +540,8 @@ __global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, P
     extern __shared__ __align__(16) unsigned char cd_smem[];
     uint32_t *table = reinterpret_cast<uint32_t *>(cd_smem);
     uint32_t *pairs = table + SLOTS;
-    uint8_t *mate = reinterpret_cast<uint8_t *>(pairs + CAP);
-    uint32_t *s_bits = reinterpret_cast<uint32_t *>(mate + CAP);
+    uint32_t *mate = pairs + CAP;                       // one bit per record: a same-hash record saw it holding a slot
+    uint32_t *s_bits = mate + CAP / 32;
     __shared__ uint32_t s_count, s_ncand, s_base;
     __shared__ uint32_t s_warp[33];
     const int tid = threadIdx.x;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, P
             s_count = 0;
             s_ncand = 0;
         }
-        for (int i = tid; i < CAP / 4; i += THREADS) reinterpret_cast<uint32_t *>(mate)[i] = 0u;
+        for (int i = tid; i < CAP / 32; i += THREADS) mate[i] = 0u;
         __syncthreads();
         cd_enumerate<THREADS, CAP, false, uint32_t>(J, c, s_bits, bm_shared, &s_count, s_warp, pairs, nullptr, 0u, vbits);
         __syncthreads();
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, P
                             unres &= ~(1u << j);
                         } else if (((v ^ mine) >> 16) == 0u) {
                             rr[j] = v & 0xffffu;
-                            mate[rr[j]] = 1;
+                            atomicOr(mate + (rr[j] >> 5), 1u << (rr[j] & 31u));
                             candm |= 1u << j;
                             unres &= ~(1u << j);
                         }
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, P
         candm |= unres;
 #pragma unroll
         for (int j = 0; j < RPT; ++j)
-            if (((winm >> j) & 1u) && mate[tid + j * THREADS] != 0) candm |= 1u << j;
+            if (((winm >> j) & 1u) && ((mate[(tid + j * THREADS) >> 5] >> (tid & 31)) & 1u)) candm |= 1u << j;
         if (check_thr) {   // unique rows survive unless their own coefficient fails the threshold
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
@@ -899,7 +899,7 @@ int class_dedup_run(ClassJob &J, const uint64_t *a_sk, const uint64_t *b_sk, con
     SYM_LAUNCH_OK();
     if (J.variant == 2) {
         constexpr int CAP = 18432, LOG_SLOTS = 15;
-        constexpr size_t smem = ((size_t)1 << LOG_SLOTS) * 4 + (size_t)CAP * 4 + CAP + (size_t)CD32_BM_WORDS * 4;
+        constexpr size_t smem = ((size_t)1 << LOG_SLOTS) * 4 + (size_t)CAP * 4 + CAP / 8 + (size_t)CD32_BM_WORDS * 4;
         auto kern = class_dedup32_kernel<1024, CAP, LOG_SLOTS>;
         static bool attr_done[64] = {};
         int dev = 0;
