@@ -73,13 +73,17 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64
         : "memory");
 }
 
-// 16 packed bits -> 16 bytes of 0/1: (nibble * 0x00204081) & 0x01010101 spreads 4 bits to 4 bytes
+// 16 packed bits -> 16 operand bytes: nibble * 0x00204081 puts bit k of the nibble at the LEAST SIGNIFICANT bit of byte k
+// (the copies n, n<<7, n<<14, n<<21 do not overlap, so no carries). The higher bits of every byte are left as they
+// fall: only the PARITY of the int32 dot product is used, and the parity of sum(a_i * b_i) depends on the low bits of
+// a_i and b_i alone (bytes are unsigned and <= 227, so the sum stays below 2^31 up to ~20 000 qubits). Dropping
+// the `& 0x01010101` of the 0/1 encoding saves a third of the expansion's ALU work, which is what limits the kernel.
 __device__ __forceinline__ uint4 expand16(uint32_t bits) {
     uint4 v;
-    v.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
-    v.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-    v.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-    v.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    v.x = (bits & 0xFu) * 0x00204081u;
+    v.y = ((bits >> 4) & 0xFu) * 0x00204081u;
+    v.z = ((bits >> 8) & 0xFu) * 0x00204081u;
+    v.w = ((bits >> 12) & 0xFu) * 0x00204081u;
     return v;
 }
 
