@@ -213,3 +213,33 @@ def test_owner_partition_on_structured_operators(ops, hamiltonians):
             scale = float(np.abs(a_c).max() * np.abs(b_c).max()) * scale_mult
             ok, why = po.compare_term_sets(s, cc, ref_s, ref_c, scale=scale)
             assert ok, (n, log2g, why)
+
+
+def test_fused_rotation_large_uses_privatised_tables_and_matches_two_step(ops):
+    """A general rotation of 6e5 rows as ONE block-list product (rotate_dedup: the class tables are built with the
+    per-CTA privatised counters because A has hundreds of rows per class) against the two-step form (rotate, then
+    cleanup) that the small-size tests pin to the oracle; plus the oracle itself on the rows that involve a sample."""
+    import math
+    n, M = 128, 600_000
+    rng = np.random.default_rng(9)
+    base_s, _ = po.random_operator(n, 200_000, seed=17)
+    idx = rng.integers(0, 200_000, size=M)
+    s = base_s[idx]                                                      # every row ~3 times: the dedup merges
+    c = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+    q_s, _ = po.random_operator(n, 1, seed=18)
+    xz, cc = dev_op(ops, s, c)
+    q = ops.pack(torch.from_numpy(q_s), n)
+    ang = 0.37
+    f_xz, f_c = ops.rotate_dedup(xz, cc, q, math.cos(ang), math.sin(ang))
+    t_xz, t_c = ops.cleanup(*ops.rotate(xz, cc, q, math.cos(ang), math.sin(ang), 0))
+    assert f_xz.shape == t_xz.shape
+    pf, pt = ops.lex_order(f_xz).to(torch.int64), ops.lex_order(t_xz).to(torch.int64)
+    assert torch.equal(f_xz[pf], t_xz[pt])
+    assert torch.allclose(f_c[pf], t_c[pt], rtol=1e-12, atol=1e-12)
+    # oracle on a slice: all copies of 300 distinct base rows
+    pick = np.isin(idx, np.arange(300))
+    ref_s, ref_c = po.perform_rotations(s[pick], c[pick], [(q_s[0], ang)])
+    got_s, got_c = host_op(ops, f_xz, f_c, n)
+    keys = {r.tobytes(): v for r, v in zip(got_s, got_c)}
+    for r, v in zip(ref_s, ref_c):
+        assert np.isclose(keys[r.tobytes()], v, rtol=1e-12, atol=1e-12)
