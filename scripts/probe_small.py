@@ -1,0 +1,30 @@
+"""Launch-bound configs: wall time per call of C1 (1000 q, 500 x 500 terms), a C2-sized product and one C3 rotation."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+from oracle import pauli_oracle as po
+from symmer_b200 import PauliwordOp, ops
+dev = ops.device()
+reps = int(os.environ.get("REPS", "200"))
+def wall(fn, reps=reps, warm=20):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize(); t = time.perf_counter()
+    for _ in range(reps): out = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t) / reps * 1e3
+s, c = po.random_operator(1000, 500, seed=1)
+A = PauliwordOp(s, c); A._coeff_dev()
+print("C1 A*A (500x500 @1000q) ms/call:", round(wall(lambda: A * A), 4), flush=True)
+axz, ac = A._xz, A._coeff_dev()
+print("C1 ops.mul_cleanup only      :", round(wall(lambda: ops.mul_cleanup(axz, ac, axz, ac)), 4), flush=True)
+s2, c2 = po.random_operator(14, 1086, seed=2)
+B = PauliwordOp(s2, c2).cleanup(); B._coeff_dev()
+print("C2-size adjacency (14q, %d)  :" % B.n_terms, round(wall(lambda: B.adjacency_matrix), 4), flush=True)
+s3, c3 = po.random_operator(1000, 100000, seed=3)
+C = PauliwordOp(s3, c3); C._coeff_dev()
+q = PauliwordOp(po.random_operator(1000, 1, seed=4)[0], [1.0])
+print("C3 one rotation 100k rows    :", round(wall(lambda: C._rotate_by_single_Pword(q, 0.3), reps=50, warm=5), 4), flush=True)
+if os.environ.get("ONE"):
+    torch.cuda.synchronize()
+    A * A
+    torch.cuda.synchronize()

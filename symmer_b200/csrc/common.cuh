@@ -155,6 +155,10 @@ __device__ __forceinline__ uint64_t group8_sketch_row(const uint64_t *__restrict
 
 __host__ __device__ __forceinline__ bool group8_ok(int W) { return W <= 16 && (W % 2 == 0); }
 
+// sketches and Y counts of both operands of a product, one launch when the rows fit the 8-lane form (layout.cu)
+int operand_tables(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int W, uint64_t *a_sk, int32_t *a_y,
+                   uint64_t *b_sk, int32_t *b_y, cudaStream_t st);
+
 // i^k applied to a complex number (k mod 4), exact.
 __device__ __forceinline__ void mul_i_pow(double &re, double &im, int k) {
     double r = re, i = im;

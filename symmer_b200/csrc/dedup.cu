@@ -50,12 +50,83 @@ __device__ __forceinline__ void link_one(const Rows &rows, const RecFmt &fmt, co
     flag[i] = f;
 }
 
+// Thread per sorted record; the exact row compares are done by the warp, 8 lanes per pair with 16-byte loads.
+// A thread comparing two rows alone touches a new 32-byte sector with every load, and a product with many true
+// duplicates (A*A: every P_i P_j meets P_j P_i) then sits on the L1 wavefront rate: 40 us for the 250 000 cross
+// terms of config C1, against 3 us without duplicates. Eight lanes read 128 contiguous bytes of each row.
 template <class Rows>
 __global__ void __launch_bounds__(256) link_kernel(Rows rows, RecFmt fmt, const uint64_t *__restrict__ sr, int64_t T,
                                                     int sort_shift, uint8_t *__restrict__ flag, uint32_t *__restrict__ link) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= T) return;
-    link_one(rows, fmt, sr, i, sort_shift, flag, link);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, g = lane & 7, grp = lane >> 3;
+    const bool valid = i < T;
+    // nearest earlier record of the bucket with the same full hash: the candidate
+    int64_t j = -1;
+    uint64_t ri = 0;
+    uint32_t ti = 0, tj = 0;
+    if (valid && i > 0) {
+        ri = sr[i];
+        ti = fmt.t(ri);
+        for (int64_t jj = i - 1; jj >= 0; --jj) {
+            const uint64_t rj = sr[jj];
+            if (((ri ^ rj) >> sort_shift) != 0) break;   // left the bucket
+            if (fmt.same_hash(ri, rj)) {
+                j = jj;
+                tj = fmt.t(rj);
+                break;
+            }
+        }
+    }
+    bool eq = false;
+    const int chunks = rows.words >> 1;
+    for (uint32_t pend = __ballot_sync(0xffffffffu, j >= 0); pend;) {   // uniform: four candidates per step
+        int src[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            src[k] = pend ? __ffs(pend) - 1 : -1;
+            pend &= pend - 1u;   // 0 stays 0
+        }
+        const int mine = src[grp];
+        const uint32_t t1 = __shfl_sync(0xffffffffu, ti, mine < 0 ? 0 : mine);
+        const uint32_t t2 = __shfl_sync(0xffffffffu, tj, mine < 0 ? 0 : mine);
+        bool same = true;
+        if (mine >= 0) {
+            const uint2 h1 = rows.locate(t1), h2 = rows.locate(t2);
+            for (int c = g; c < chunks; c += 8) {
+                const uint4 a = rows.chunk_at(h1, c), b = rows.chunk_at(h2, c);
+                same &= !((a.x != b.x) | (a.y != b.y) | (a.z != b.z) | (a.w != b.w));
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, same);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (lane == src[k]) eq = ((bal >> (8 * k)) & 0xffu) == 0xffu;
+    }
+    if (!valid) return;
+    uint8_t f = FLAG_HEAD;
+    if (j >= 0) {
+        if (!eq) {   // same hash, different row (2^-40 per pair): go on alone from the record before the candidate
+            int64_t jj = j - 1;
+            j = -1;
+            for (; jj >= 0; --jj) {
+                const uint64_t rj = sr[jj];
+                if (((ri ^ rj) >> sort_shift) != 0) break;
+                if (fmt.same_hash(ri, rj) && rows.equal(ti, fmt.t(rj))) {
+                    j = jj;
+                    break;
+                }
+            }
+        }
+        if (j >= 0) {
+            if (j == i - 1) {
+                f = FLAG_PREV;
+            } else {
+                f = FLAG_LINK;
+                link[i] = (uint32_t)j;
+            }
+        }
+    }
+    flag[i] = f;
 }
 
 // Worklist of sorted positions (ordered-tile mode: only the records of non-singleton buckets), kept as
@@ -234,10 +305,14 @@ __device__ __forceinline__ bool sum_one(const Rows &rows, const RecFmt &fmt, con
     return false;
 }
 
-// The same walk by a whole (converged) warp for the head at position i: lane l looks at record base + l, membership
-// of the FLAG_PREV chains is resolved with ballots (a PREV record follows the nearest earlier record that is not
-// PREV), coefficients are gathered in parallel and added by every lane in record order — the same additions in the
-// same order as the sequential walk, so the result is bit-identical to it. Every lane returns the sums.
+// The same walk by a whole (converged) warp for the head at position i: lane l looks at records base + 32u + l of
+// SUM_WIN windows at a time, membership of the FLAG_PREV chains is resolved with ballots (a PREV record follows
+// the nearest earlier record that is not PREV), coefficients are gathered in parallel and added by every lane in
+// record order — the same additions in the same order as the sequential walk, so the result is bit-identical to
+// it. Every lane returns the sums. The loads of the SUM_WIN windows (records and flags, then coefficients) are
+// issued together and the broadcasts of a window do not depend on the running sum, so a long group costs two
+// memory round trips per 128 records plus its chain of FP64 adds (the 500 identity terms of config C1: 35 -> 6 us).
+constexpr int SUM_WIN = 4;
 template <class Rows, bool TILE>
 __device__ __forceinline__ void sum_walk_warp(const Rows &rows, const RecFmt &fmt, const uint64_t *__restrict__ sr, int64_t T,
                                               int64_t i, int sort_shift, const uint8_t *__restrict__ flag,
@@ -247,33 +322,62 @@ __device__ __forceinline__ void sum_walk_warp(const Rows &rows, const RecFmt &fm
     head_coeff<Rows, TILE>(rows, fmt, r0, re, im);
     is_multi = false;
     bool carry = true;   // membership of the record just before this window (the head itself at first)
-    for (int64_t base = i + 1; base < T; base += 32) {
-        const int64_t j = base + lane;
-        const uint64_t rj = j < T ? sr[j] : 0ull;
-        const bool in = j < T && ((r0 ^ rj) >> sort_shift) == 0;
-        const uint32_t out_mask = __ballot_sync(0xffffffffu, !in);
-        const int n_in = out_mask ? __ffs(out_mask) - 1 : 32;        // the bucket is contiguous
-        if (n_in == 0) break;
-        const bool valid = lane < n_in;
-        const uint8_t fj = valid ? flag[j] : FLAG_HEAD;
-        const bool sh = valid && fmt.same_hash(r0, rj);
-        const bool is_prev = sh && fj == FLAG_PREV;
-        const bool m0 = sh && fj == FLAG_LINK && chain_root(flag, link, (int64_t)link[j]) == i;
-        const uint32_t decided = __ballot_sync(0xffffffffu, !is_prev);
-        const uint32_t m0_mask = __ballot_sync(0xffffffffu, m0);
-        const uint32_t lower = decided & ((1u << lane) - 1u);
-        const bool mine = is_prev ? (lower ? ((m0_mask >> (31 - __clz(lower))) & 1u) != 0u : carry) : m0;
-        const uint32_t mine_mask = __ballot_sync(0xffffffffu, mine);
-        carry = (mine_mask >> 31) & 1u;
-        double cr = 0.0, ci = 0.0;
-        if (mine) rows.coeff(fmt.t(rj), fmt.e(rj), cr, ci);
-        for (uint32_t m = mine_mask; m; m &= m - 1u) {               // uniform loop, record order
-            const int l = __ffs(m) - 1;
-            re += __shfl_sync(0xffffffffu, cr, l);
-            im += __shfl_sync(0xffffffffu, ci, l);
+    bool open = true;
+    for (int64_t base = i + 1; open && base < T; base += 32 * SUM_WIN) {
+        uint64_t rj[SUM_WIN];
+        uint8_t fj[SUM_WIN];
+#pragma unroll
+        for (int u = 0; u < SUM_WIN; ++u) {
+            const int64_t j = base + 32 * u + lane;
+            rj[u] = j < T ? sr[j] : 0ull;
+            fj[u] = j < T ? flag[j] : FLAG_HEAD;   // read before the bucket test: one round trip for both
         }
-        is_multi |= mine_mask != 0u;
-        if (n_in < 32) break;
+        uint32_t mine_mask[SUM_WIN];
+        bool mine[SUM_WIN];
+#pragma unroll
+        for (int u = 0; u < SUM_WIN; ++u) {
+            mine_mask[u] = 0u;
+            mine[u] = false;
+            if (!open) continue;   // uniform
+            const int64_t j = base + 32 * u + lane;
+            const bool in = j < T && ((r0 ^ rj[u]) >> sort_shift) == 0;
+            const uint32_t out_mask = __ballot_sync(0xffffffffu, !in);
+            const int n_in = out_mask ? __ffs(out_mask) - 1 : 32;        // the bucket is contiguous
+            if (n_in < 32) open = false;
+            if (n_in == 0) continue;
+            const bool valid = lane < n_in;
+            // only records with this head's hash can be members; in ordered-tile mode the others may not even
+            // have a flag (they never went on the worklist)
+            const bool sh = valid && fmt.same_hash(r0, rj[u]);
+            const bool is_prev = sh && fj[u] == FLAG_PREV;
+            const bool m0 = sh && fj[u] == FLAG_LINK && chain_root(flag, link, (int64_t)link[j]) == i;
+            const uint32_t decided = __ballot_sync(0xffffffffu, !is_prev);
+            const uint32_t m0_mask = __ballot_sync(0xffffffffu, m0);
+            const uint32_t lower = decided & ((1u << lane) - 1u);
+            mine[u] = is_prev ? (lower ? ((m0_mask >> (31 - __clz(lower))) & 1u) != 0u : carry) : m0;
+            mine_mask[u] = __ballot_sync(0xffffffffu, mine[u]);
+            carry = (mine_mask[u] >> 31) & 1u;
+        }
+        double cr[SUM_WIN], ci[SUM_WIN];
+#pragma unroll
+        for (int u = 0; u < SUM_WIN; ++u) {
+            cr[u] = 0.0;
+            ci[u] = 0.0;
+            if (mine[u]) rows.coeff(fmt.t(rj[u]), fmt.e(rj[u]), cr[u], ci[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < SUM_WIN; ++u) {
+            if (mine_mask[u] == 0u) continue;   // uniform
+            is_multi = true;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {      // record order; the broadcasts run ahead of the adds
+                const double vr = __shfl_sync(0xffffffffu, cr[u], l), vi = __shfl_sync(0xffffffffu, ci[u], l);
+                if ((mine_mask[u] >> l) & 1u) {
+                    re += vr;
+                    im += vi;
+                }
+            }
+        }
     }
 }
 

@@ -68,6 +68,52 @@ __global__ void sketch8_kernel(const uint64_t *__restrict__ xz, int64_t M, int W
     if (ok && (lane & 7) == 0) sk[row] = h;
 }
 
+// Sketch AND Y count of every row of two operands in one launch (what a product needs of A and B before it can
+// generate records): 8 lanes per row, lane g holds X chunk g and Z chunk g. same != 0: B is A (a square): the A
+// rows are read once and both tables written. A small product is a chain of short kernels, and four of them
+// (sketch, Y count, twice) were these.
+__global__ void __launch_bounds__(256) operand_tables8_kernel(const uint64_t *__restrict__ a, int64_t M, const uint64_t *__restrict__ b,
+                                                              int64_t N, int W, uint64_t *__restrict__ a_sk, int32_t *__restrict__ a_y,
+                                                              uint64_t *__restrict__ b_sk, int32_t *__restrict__ b_y, int same) {
+    const int lane = threadIdx.x & 31, g = lane & 7;
+    const int64_t r = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
+    const int64_t total = same ? M : M + N;
+    const bool ok = r < total;
+    const bool in_a = r < M;
+    const uint64_t *row = !ok ? a : (in_a ? a + r * 2 * W : b + (r - M) * 2 * W);
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
+    const int chunks = W >> 1;   // 16-byte chunks per block (X or Z)
+    uint64_t h = 0;
+    int y = 0;
+    if (g < chunks) {
+        const uint4 xv = r4[g], zv = r4[chunks + g];
+        const uint64_t x0 = ((uint64_t)xv.y << 32) | xv.x, x1 = ((uint64_t)xv.w << 32) | xv.z;
+        const uint64_t z0 = ((uint64_t)zv.y << 32) | zv.x, z1 = ((uint64_t)zv.w << 32) | zv.z;
+        y = __popcll(x0 & z0) + __popcll(x1 & z1);
+        // word index = lane index of the sketch: X words 2g, 2g+1; Z words 2(chunks+g), 2(chunks+g)+1
+        h = lane_linear(x0, 2 * g) ^ lane_linear(x1, 2 * g + 1) ^ lane_linear(z0, 2 * (chunks + g)) ^
+            lane_linear(z1, 2 * (chunks + g) + 1);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        h ^= __shfl_xor_sync(0xffffffffu, h, o);
+        y += __shfl_xor_sync(0xffffffffu, y, o);
+    }
+    if (ok && g == 0) {
+        if (in_a) {
+            a_sk[r] = h;
+            a_y[r] = y;
+            if (same) {
+                b_sk[r] = h;
+                b_y[r] = y;
+            }
+        } else {
+            b_sk[r - M] = h;
+            b_y[r - M] = y;
+        }
+    }
+}
+
 __global__ void sketch_kernel(const uint64_t *__restrict__ xz, int64_t M, int W, uint64_t *__restrict__ sk) {
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -247,6 +293,24 @@ extern "C" int sym_sketch_rows(const uint64_t *xz, int64_t M, int32_t W, uint64_
     else
         sketch_kernel<<<blocks_for(M * 32, 256), 256, 0, (cudaStream_t)stream>>>(xz, M, W, sketch);
     SYM_LAUNCH_OK();
+    return SYM_OK;
+}
+
+// sketches and Y counts of both operands of a product (internal; declared in rows.cuh)
+int symb::operand_tables(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64_t N, int W, uint64_t *a_sk, int32_t *a_y,
+                         uint64_t *b_sk, int32_t *b_y, cudaStream_t st) {
+    if (group8_ok(W) && M > 0 && N > 0) {
+        const int same = (a_xz == b_xz && M == N) ? 1 : 0;
+        const int64_t total = same ? M : M + N;
+        symb::operand_tables8_kernel<<<blocks_for(((total + 3) / 4) * 32, 256), 256, 0, st>>>(a_xz, M, b_xz, N, W, a_sk, a_y, b_sk,
+                                                                                             b_y, same);
+        SYM_LAUNCH_OK();
+        return SYM_OK;
+    }
+    SYM_TRY(sym_sketch_rows(a_xz, M, W, a_sk, st));
+    SYM_TRY(sym_sketch_rows(b_xz, N, W, b_sk, st));
+    SYM_TRY(sym_ycount(a_xz, M, W, a_y, st));
+    SYM_TRY(sym_ycount(b_xz, N, W, b_y, st));
     return SYM_OK;
 }
 

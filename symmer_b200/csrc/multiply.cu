@@ -30,15 +30,16 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
     const uint64_t *__restrict__ a_xz, const uint64_t *__restrict__ a_sk, const int32_t *__restrict__ a_y, uint32_t M_total,
     uint32_t p_begin, uint32_t p_end, const uint64_t *__restrict__ b_xz, const uint64_t *__restrict__ b_sk,
     const int32_t *__restrict__ b_y, uint32_t N, uint32_t q_off, int W, uint64_t key_mask, RecFmt fmt,
-    uint64_t *__restrict__ recs) {
-    // B tile: QCH rows, (x_w, z_w) interleaved so one 16-byte shared load feeds a word step
+    uint64_t *__restrict__ recs, uint32_t qch) {
+    // B tile: qch <= QCH rows (fewer for small products, so that the grid still covers the SMs),
+    // (x_w, z_w) interleaved so one 16-byte shared load feeds a word step
     __shared__ ulonglong2 sb[PAIR_QCH][WT];
     __shared__ uint64_t sb_sk[PAIR_QCH];
     __shared__ int sb_y[PAIR_QCH];
 
-    const uint32_t q0 = blockIdx.y * PAIR_QCH;
-    const uint32_t nq = min((uint32_t)PAIR_QCH, N - q0);
-    for (int i = threadIdx.x; i < PAIR_QCH * WT; i += PAIR_THREADS) {
+    const uint32_t q0 = blockIdx.y * qch;
+    const uint32_t nq = min(qch, N - q0);
+    for (int i = threadIdx.x; i < (int)qch * WT; i += blockDim.x) {
         int qi = i / WT, w = i % WT;
         ulonglong2 v = make_ulonglong2(0ull, 0ull);
         if ((uint32_t)qi < nq && w < W) {
@@ -48,22 +49,40 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_records_kernel(
         }
         sb[qi][w] = v;
     }
-    for (int i = threadIdx.x; i < PAIR_QCH; i += PAIR_THREADS) {
+    for (int i = threadIdx.x; i < (int)qch; i += blockDim.x) {
         sb_sk[i] = ((uint32_t)i < nq) ? b_sk[q0 + i] : 0ull;
         sb_y[i] = ((uint32_t)i < nq) ? b_y[q0 + i] : 0;
     }
 
-    const uint32_t p = p_begin + blockIdx.x * PAIR_THREADS + threadIdx.x;
+    const uint32_t p = p_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < p_end;
     uint64_t xa[WT], za[WT];
     uint64_t ska = 0;
     int ya = 0;
     if (active) {
         const uint64_t *row = a_xz + (size_t)p * 2 * W;
+        if (WT >= 2 && (W & 1) == 0) {   // 16-byte loads: a thread's row is strided against its neighbours' either way
+            const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
 #pragma unroll
-        for (int w = 0; w < WT; ++w) {
-            xa[w] = (w < W) ? row[w] : 0ull;
-            za[w] = (w < W) ? row[W + w] : 0ull;
+            for (int w = 0; w < WT; w += 2) {
+                uint4 xv = make_uint4(0u, 0u, 0u, 0u), zv = make_uint4(0u, 0u, 0u, 0u);
+                if (w < W) {
+                    xv = row4[w >> 1];
+                    zv = row4[(W + w) >> 1];
+                }
+                xa[w] = ((uint64_t)xv.y << 32) | xv.x;
+                za[w] = ((uint64_t)zv.y << 32) | zv.x;
+                if (w + 1 < WT) {
+                    xa[w + 1] = ((uint64_t)xv.w << 32) | xv.z;
+                    za[w + 1] = ((uint64_t)zv.w << 32) | zv.z;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < WT; ++w) {
+                xa[w] = (w < W) ? row[w] : 0ull;
+                za[w] = (w < W) ? row[W + w] : 0ull;
+            }
         }
         ska = a_sk[p];
         ya = a_y[p];
@@ -140,11 +159,20 @@ static int launch_pair_records(const uint64_t *a_xz, const uint64_t *a_sk, const
     // b_xz / b_sk / b_y point at B row q_off; N rows from there. t uses the global index q_off + q.
     const int64_t m_blk = p_end - p_begin;
     if (m_blk <= 0 || N <= 0) return SYM_OK;
-    dim3 grid((unsigned)((m_blk + PAIR_THREADS - 1) / PAIR_THREADS), (unsigned)((N + PAIR_QCH - 1) / PAIR_QCH));
+    // CTA shape: 256 A rows x 64 B rows; a small product (C1: 500 x 500 terms would be 2 x 8 CTAs) takes 64-row CTAs and
+    // fewer B rows per CTA until the grid covers the SMs. Every CTA column re-reads the A rows with one 32-byte sector
+    // per load (a thread's row is strided against its neighbours'), so the B tile is not shrunk further than needed.
+    int threads = PAIR_THREADS;
+    uint32_t qch = PAIR_QCH;
+    if (((m_blk + PAIR_THREADS - 1) / PAIR_THREADS) * ((N + PAIR_QCH - 1) / PAIR_QCH) < 2 * 148) {
+        threads = 64;
+        while (qch > 8 && ((m_blk + 63) / 64) * ((N + qch - 1) / qch) < 256) qch >>= 1;
+    }
+    dim3 grid((unsigned)((m_blk + threads - 1) / threads), (unsigned)((N + qch - 1) / qch));
 #define PAIR_CASE(WT)                                                                                               \
-    pair_records_kernel<WT><<<grid, PAIR_THREADS, 0, st>>>(a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin,   \
+    pair_records_kernel<WT><<<grid, threads, 0, st>>>(a_xz, a_sk, a_y, (uint32_t)M_total, (uint32_t)p_begin,   \
                                                            (uint32_t)p_end, b_xz, b_sk, b_y, (uint32_t)N,           \
-                                                           (uint32_t)q_off, W, g_key_mask, fmt, recs)
+                                                           (uint32_t)q_off, W, g_key_mask, fmt, recs, qch)
     if (grid.y > 65535) {
         set_error("too many B rows for one launch (N=%lld)", (long long)N);
         return SYM_E_UNSUPPORTED;
@@ -240,11 +268,7 @@ static int prepare_operand_tables(const uint64_t *a_xz, int64_t M, const uint64_
         set_error("workspace arena exhausted");
         return SYM_E_WORKSPACE;
     }
-    SYM_TRY(sym_sketch_rows(a_xz, M, W, a_sk, st));
-    SYM_TRY(sym_sketch_rows(b_xz, N, W, b_sk, st));
-    SYM_TRY(sym_ycount(a_xz, M, W, a_y, st));
-    SYM_TRY(sym_ycount(b_xz, N, W, b_y, st));
-    return SYM_OK;
+    return operand_tables(a_xz, M, b_xz, N, W, a_sk, a_y, b_sk, b_y, st);
 }
 
 extern "C" int sym_pair_records(const uint64_t *a_xz, int64_t M_total, int64_t p_begin, int64_t p_end,
@@ -579,12 +603,11 @@ extern "C" int sym_mul_blocks_count_tables(const uint64_t *a_xz, const double *a
     if (a_sketch) {   // the caller already has A's tables (sym_rotate_split): two reads of A saved
         SYM_CUDA_OK(cudaMemcpyAsync(P.a_sk, a_sketch, sizeof(uint64_t) * (size_t)M_total, cudaMemcpyDeviceToDevice, st));
         SYM_CUDA_OK(cudaMemcpyAsync(P.a_y, a_ycount, sizeof(int32_t) * (size_t)M_total, cudaMemcpyDeviceToDevice, st));
+        SYM_TRY(sym_sketch_rows(b_xz, N, W, P.b_sk, st));
+        SYM_TRY(sym_ycount(b_xz, N, W, P.b_y, st));
     } else {
-        SYM_TRY(sym_sketch_rows(a_xz, M_total, W, P.a_sk, st));
-        SYM_TRY(sym_ycount(a_xz, M_total, W, P.a_y, st));
+        SYM_TRY(operand_tables(a_xz, M_total, b_xz, N, W, P.a_sk, P.a_y, P.b_sk, P.b_y, st));
     }
-    SYM_TRY(sym_sketch_rows(b_xz, N, W, P.b_sk, st));
-    SYM_TRY(sym_ycount(b_xz, N, W, P.b_y, st));
     RecFmt fmt{t_bits_for(M_total * N)};
     if (P.mode == MODE_TILES) {
         if (P.nblk > 1)   // block 0 travels inside the TileMap kernel argument
