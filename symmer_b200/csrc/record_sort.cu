@@ -389,16 +389,22 @@ __global__ void __launch_bounds__(THREADS, MINB) os_pass_kernel(Src src, uint64_
 
 int g_onesweep = 1;   // tuning knob 8
 
+// Short sorts keep one look-back state array PER PASS, so that a single memset clears them all (and the pass
+// counters behind them) instead of one memset in front of every pass: on a 250 000-record sort the passes take
+// 10 us each and every extra stream operation costs 3-4 us of launch gap.
+constexpr int64_t OS_MULTI_STATE_TILES = 1024;
+static inline int os_state_copies(int64_t ntiles) { return ntiles <= OS_MULTI_STATE_TILES ? OS_MAX_PASSES : 1; }
+
 size_t record_hist_elems(int64_t T) {
     int64_t ntiles = (T + RS_TILE - 1) / RS_TILE;
     if (ntiles < 1) ntiles = 1;
     size_t h = (size_t)RS_RADIX * (size_t)ntiles;
-    return h + scan_scratch_elems((int64_t)h) + 64 + OS_EXTRA_ELEMS;
+    return h * (size_t)os_state_copies(ntiles) + scan_scratch_elems((int64_t)h) + 64 + OS_EXTRA_ELEMS;
 }
 
 template <class Src, int TH, int IT, int MB>
 static int os_launch_shape(const Src &src, uint64_t *out, int64_t T, int shift, uint32_t mask, const uint32_t *bases,
-                           uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st) {
+                           uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st, bool clear_state) {
     constexpr size_t smem = RS_TILE * 8 + (TH / 32) * RS_RADIX * 4 + 2 * RS_RADIX * 4 + 32 * 4 + 64;
     static bool attr_done[64] = {};   // per device
     int dev = 0;
@@ -407,7 +413,7 @@ static int os_launch_shape(const Src &src, uint64_t *out, int64_t T, int shift, 
         SYM_CUDA_OK(cudaFuncSetAttribute(os_pass_kernel<Src, TH, IT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev] = true;
     }
-    SYM_CUDA_OK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * (size_t)RS_RADIX * (size_t)ntiles, st));
+    if (clear_state) SYM_CUDA_OK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * (size_t)RS_RADIX * (size_t)ntiles, st));
     os_pass_kernel<Src, TH, IT, MB><<<(unsigned)ntiles, TH, smem, st>>>(src, out, T, shift, mask, bases, state, ticket);
     SYM_LAUNCH_OK();
     return SYM_OK;
@@ -415,12 +421,12 @@ static int os_launch_shape(const Src &src, uint64_t *out, int64_t T, int shift, 
 
 template <class Src>
 static int os_launch_pass(const Src &src, uint64_t *out, int64_t T, int shift, uint32_t mask, const uint32_t *bases,
-                          uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st) {
+                          uint32_t *state, uint32_t *ticket, int64_t ntiles, cudaStream_t st, bool clear_state) {
     switch (g_scatter_variant) {   // tuning knob 2 (CTA shape); 3 = 256 threads x 16 records, 4 CTAs/SM is the default
-        case 1: return os_launch_shape<Src, 512, 8, 2>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
-        case 2: return os_launch_shape<Src, 512, 8, 3>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
-        case 5: return os_launch_shape<Src, 256, 16, 5>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
-        default: return os_launch_shape<Src, 256, 16, 4>(src, out, T, shift, mask, bases, state, ticket, ntiles, st);
+        case 1: return os_launch_shape<Src, 512, 8, 2>(src, out, T, shift, mask, bases, state, ticket, ntiles, st, clear_state);
+        case 2: return os_launch_shape<Src, 512, 8, 3>(src, out, T, shift, mask, bases, state, ticket, ntiles, st, clear_state);
+        case 5: return os_launch_shape<Src, 256, 16, 5>(src, out, T, shift, mask, bases, state, ticket, ntiles, st, clear_state);
+        default: return os_launch_shape<Src, 256, 16, 4>(src, out, T, shift, mask, bases, state, ticket, ntiles, st, clear_state);
     }
 }
 
@@ -431,9 +437,14 @@ static int onesweep_sort(const Src &first, uint64_t *a, uint64_t *b, int64_t T, 
     const int passes = (64 - begin_bit + 7) / 8;
     const int64_t ntiles = (T + RS_TILE - 1) / RS_TILE;
     uint32_t *state = hist;
-    uint32_t *extra = hist + (size_t)RS_RADIX * (size_t)ntiles + scan_scratch_elems((int64_t)RS_RADIX * ntiles) + 64;
+    const size_t h = (size_t)RS_RADIX * (size_t)ntiles;
+    const int copies = os_state_copies(ntiles);
+    uint32_t *extra = hist + h * (size_t)copies + scan_scratch_elems((int64_t)h) + 64;
     uint32_t *counts = extra, *bases = extra + OS_MAX_PASSES * RS_RADIX, *tickets = bases + OS_MAX_PASSES * RS_RADIX;
-    SYM_CUDA_OK(cudaMemsetAsync(extra, 0, sizeof(uint32_t) * OS_EXTRA_ELEMS, st));
+    if (copies > 1)   // every pass's state, the (unused) scan scratch between, and the counters: one memset
+        SYM_CUDA_OK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * ((size_t)(extra - hist) + OS_EXTRA_ELEMS), st));
+    else
+        SYM_CUDA_OK(cudaMemsetAsync(extra, 0, sizeof(uint32_t) * OS_EXTRA_ELEMS, st));
     const unsigned hgrid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms() * 8);
     os_hist_kernel<Src><<<hgrid, RS_THREADS, 0, st>>>(first, T, begin_bit, passes, ntiles, counts);
     SYM_LAUNCH_OK();
@@ -443,11 +454,12 @@ static int onesweep_sort(const Src &first, uint64_t *a, uint64_t *b, int64_t T, 
     for (int ps = 0; ps < passes; ++ps) {
         const int width = (64 - bit) < 8 ? (64 - bit) : 8;
         const uint32_t mask = (1u << width) - 1u;
+        uint32_t *state_ps = copies > 1 ? state + (size_t)ps * h : state;
         if (ps == 0) {
-            SYM_TRY(os_launch_pass(first, b, T, bit, mask, bases + ps * RS_RADIX, state, tickets + ps, ntiles, st));
+            SYM_TRY(os_launch_pass(first, b, T, bit, mask, bases + ps * RS_RADIX, state_ps, tickets + ps, ntiles, st, copies == 1));
         } else {
             PlainKeySrc src{a};
-            SYM_TRY(os_launch_pass(src, b, T, bit, mask, bases + ps * RS_RADIX, state, tickets + ps, ntiles, st));
+            SYM_TRY(os_launch_pass(src, b, T, bit, mask, bases + ps * RS_RADIX, state_ps, tickets + ps, ntiles, st, copies == 1));
         }
         uint64_t *t = a; a = b; b = t;
         bit += width;

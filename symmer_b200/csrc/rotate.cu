@@ -12,7 +12,8 @@ namespace symb {
 // info byte: bit0 = anticommutes with Q, bits1-2 = phase exponent e of P*Q (coefficient factor i^e)
 __global__ void __launch_bounds__(256) rotate_info_kernel(const uint64_t *__restrict__ xz, int64_t M, int W,
                                                            const uint64_t *__restrict__ q_xz, uint8_t *__restrict__ info,
-                                                           uint64_t *__restrict__ sk_out, int32_t *__restrict__ y_out) {
+                                                           uint64_t *__restrict__ sk_out, int32_t *__restrict__ y_out,
+                                                           uint8_t *__restrict__ anti_out) {
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) rotate_info_kernel(const uint64_t *__rest
     if (lane == 0) {
         int e = (3 * (ya + yb) + yout + 2 * sg) & 3;
         info[row] = (uint8_t)(par | (e << 1));
+        if (anti_out) anti_out[row] = (uint8_t)par;   // 0/1 flags for the rank scan
         if (y_out) y_out[row] = ya;
     }
     if (sk_out) {   // generic widths: a second pass over the row (uniform branch, whole warp)
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(256) rotate_info_kernel(const uint64_t *__rest
 // a product that follows (the fused rotation) need not read the rows again for its tables.
 __global__ void __launch_bounds__(256) rotate_info8_kernel(const uint64_t *__restrict__ xz, int64_t M, int W,
                                                             const uint64_t *__restrict__ q_xz, uint8_t *__restrict__ info,
-                                                            uint64_t *__restrict__ sk_out, int32_t *__restrict__ y_out) {
+                                                            uint64_t *__restrict__ sk_out, int32_t *__restrict__ y_out,
+                                                            uint8_t *__restrict__ anti_out) {
     const int lane = threadIdx.x & 31, g = lane & 7;
     int64_t row = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
     const bool ok = row < M;
@@ -99,15 +102,10 @@ __global__ void __launch_bounds__(256) rotate_info8_kernel(const uint64_t *__res
     if (ok && g == 0) {
         int e = (3 * (ya + yb) + yout + 2 * sg) & 3;
         info[row] = (uint8_t)(par | (e << 1));
+        if (anti_out) anti_out[row] = (uint8_t)par;   // 0/1 flags for the rank scan
         if (sk_out) sk_out[row] = h;
         if (y_out) y_out[row] = ya;
     }
-}
-
-__global__ void __launch_bounds__(256) rotate_anti_flag_kernel(const uint8_t *__restrict__ info, int64_t M,
-                                                                uint8_t *__restrict__ anti) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M) anti[i] = info[i] & 1;
 }
 
 // mode 0: general; mode 1: Clifford odd; mode 2: Clifford even
@@ -278,13 +276,11 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
     uint32_t *scratch = ar.take<uint32_t>(scan_scratch_elems(M));
     uint32_t *total = ar.take<uint32_t>(4);
     if (group8_ok(W))
-        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, nullptr, nullptr);
+        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, nullptr, nullptr, mode == 0 ? anti : nullptr);
     else
-        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, nullptr, nullptr);
+        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, nullptr, nullptr, mode == 0 ? anti : nullptr);
     SYM_LAUNCH_OK();
     if (mode == 0) {
-        rotate_anti_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(info, M, anti);
-        SYM_LAUNCH_OK();
         SYM_TRY(scan_exclusive_u8(anti, rank, M, total, scratch, st));
     } else {
         SYM_CUDA_OK(cudaMemsetAsync(total, 0, sizeof(uint32_t), st));
@@ -343,11 +339,9 @@ extern "C" int sym_rotate_split(const uint64_t *xz, const double *c, int64_t M, 
     uint64_t *sk = ar.take<uint64_t>((size_t)M);
     int32_t *yc = ar.take<int32_t>((size_t)M);
     if (group8_ok(W))
-        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, sk, yc);
+        rotate_info8_kernel<<<(unsigned)((((M + 3) / 4) * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, sk, yc, anti);
     else
-        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, sk, yc);
-    SYM_LAUNCH_OK();
-    rotate_anti_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(info, M, anti);
+        rotate_info_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, st>>>(xz, M, W, q_xz, info, sk, yc, anti);
     SYM_LAUNCH_OK();
     SYM_TRY(scan_exclusive_u8(anti, rank, M, total, scratch, st));
     const uint32_t chunks = (uint32_t)W;

@@ -135,12 +135,78 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const T *in, u
     }
 }
 
+// Short inputs (a few 1e4 flags): ONE CTA walks the array in strips of 16 384 elements,
+// next strip's loads in flight while this one is scanned. Three launches of a few microseconds each become one.
+constexpr int64_t SCAN_ONE_MAX = (int64_t)1 << 15;   // beyond two strips one SM is slower than three launches (measured: 48 us at 250 000)
+template <typename T>
+__global__ void __launch_bounds__(1024) scan_one_kernel(const T *in, uint32_t *out, int64_t n, uint32_t *total) {   // in may be out
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t strip_tot;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int64_t STRIP = 1024 * SCAN_ITEMS;
+    uint32_t carry = 0;
+    uint32_t v[SCAN_ITEMS], nxt[SCAN_ITEMS];
+    load_items(in, (int64_t)threadIdx.x * SCAN_ITEMS, n, v);
+    for (int64_t strip = 0; strip < n; strip += STRIP) {
+        const int64_t base = strip + (int64_t)threadIdx.x * SCAN_ITEMS;
+        if (strip + STRIP < n) load_items(in, base + STRIP, n, nxt);
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            const uint32_t t = v[j];
+            v[j] = s;
+            s += t;
+        }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t t = warp_tot[lane];
+            uint32_t ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += y;
+            }
+            warp_tot[lane] = ti - t;   // exclusive warp offsets
+            if (lane == 31) strip_tot = ti;
+        }
+        __syncthreads();
+        const uint32_t off = carry + warp_tot[wid] + inc - s;
+        carry += strip_tot;
+        if (base + SCAN_ITEMS <= n) {
+            uint4 *p = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                p[j] = make_uint4(v[4 * j] + off, v[4 * j + 1] + off, v[4 * j + 2] + off, v[4 * j + 3] + off);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j)
+                if (base + j < n) out[base + j] = v[j] + off;
+        }
+        __syncthreads();   // warp_tot / strip_tot are rewritten by the next strip
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = nxt[j];
+    }
+    if (threadIdx.x == 0 && total != nullptr) *total = carry;
+}
+
 size_t scan_scratch_elems(int64_t n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 64; }
 
 template <typename T>
 static int scan_impl(const T *in, uint32_t *out, int64_t n, uint32_t *total, uint32_t *scratch, cudaStream_t st) {
     if (n <= 0) {
         if (total) SYM_CUDA_OK(cudaMemsetAsync(total, 0, sizeof(uint32_t), st));
+        return SYM_OK;
+    }
+    if (n <= SCAN_ONE_MAX) {
+        scan_one_kernel<T><<<1, 1024, 0, st>>>(in, out, n, total);
+        SYM_LAUNCH_OK();
         return SYM_OK;
     }
     int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
