@@ -158,6 +158,10 @@ int sym_commute_qwc(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64
  *         out_xz/out_c capacity must be 2*M rows.
  * mode 1: Clifford, odd multiple of pi/2: anticommuting rows become (-i)*P*Q*sign; M rows out.
  * mode 2: Clifford, even multiple: anticommuting rows * sign; M rows out.
+ * mode 4: general angle, padded: exactly 2*M rows out, no flag scan and no count to read back. Row M+i is
+ *         the -i*sin*P*Q term of an anticommuting row i and, for a commuting row, a copy of row i with
+ *         coefficient 0, which the sym_cleanup that follows merges into row i (same survivors, same order,
+ *         same sums as mode 0). Needs W even and <= 16; takes no workspace.
  * `sign` is +1 or -1 (the reference's `int_part in [2,3]` rule, base.py:1148-1149).
  * n_out: device int64[1]. Fully asynchronous. */
 size_t sym_rotate_ws_bytes(int64_t M);

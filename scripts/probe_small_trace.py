@@ -13,10 +13,16 @@ if os.environ.get("AB"):
     s2, c2 = po.random_operator(1000, 500, seed=2)
     B = PauliwordOp(s2, c2); bc = B._coeff_dev(); bxz = B._xz
 if os.environ.get("TILE"): ops.set_tuning(0, 0)
-for _ in range(30): ops.mul_cleanup(axz, ac, bxz, bc)
+fn = lambda: ops.mul_cleanup(axz, ac, bxz, bc)
+if os.environ.get("ROT"):
+    s3, c3 = po.random_operator(1000, 100000, seed=3)
+    C = PauliwordOp(s3, c3); C._coeff_dev()
+    q = PauliwordOp(po.random_operator(1000, 1, seed=4)[0], [1.0])
+    fn = lambda: C._rotate_by_single_Pword(q, 0.3)
+for _ in range(30): fn()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for _ in range(10): ops.mul_cleanup(axz, ac, bxz, bc)
+    for _ in range(10): fn()
     torch.cuda.synchronize()
 prof.export_chrome_trace("/tmp/c1_trace.json")
 ev = json.load(open("/tmp/c1_trace.json"))["traceEvents"]

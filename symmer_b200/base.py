@@ -747,7 +747,7 @@ class PauliwordOp:
             # rotation + dedup as one block-list product: the rotated rows are never materialised in between
             xz, cc = ops.rotate_dedup(self._xz, c, Pword._xz, np.cos(angle), np.sin(angle))
             return PauliwordOp._from_device(xz, cc, self.n_qubits), 'clean'
-        xz, cc = ops.rotate(self._xz, c, Pword._xz, np.cos(angle), np.sin(angle), 0)
+        xz, cc = ops.rotate(self._xz, c, Pword._xz, np.cos(angle), np.sin(angle), 0, padded_ok=True)    # every caller cleans a dirty result
         return PauliwordOp._from_device(xz, cc, self.n_qubits), 'dirty'
 
     def _rotate_by_single_Pword(self, Pword: "PauliwordOp", angle: float = None,

@@ -217,6 +217,111 @@ __global__ void __launch_bounds__(256) rotate_write4_kernel(const uint4 *__restr
     }
 }
 
+// One-pass rotation for the 8-lane row form (W even, W <= 16): the commutation test, the phase exponent and the
+// write of the rotated rows in ONE kernel, no flag scan, no count to read back.
+//   MODE 1 / 2: the Clifford relabellings of rotate_write_kernel.
+//   MODE 4: general angle, PADDED: out has exactly 2M rows. Row p keeps P_p (cos*c if it anticommutes with Q);
+//           row M + p holds the second term of an anticommuting row (P_p Q, -i sin * c * i^e) and, for a commuting
+//           row, a copy of P_p with coefficient 0. The cleanup that always follows a general rotation merges the
+//           copy into its twin (c + 0 = c; the twin comes first, so first-occurrence order is that of the compact
+//           form) -- for operators of config size the extra rows cost less than the scan of the anticommuting
+//           flags plus the host round trip for the row count that the compact form needs.
+template <int MODE>
+__global__ void __launch_bounds__(256) rotate_fused8_kernel(const uint64_t *__restrict__ xz, const double2 *__restrict__ c, int64_t M,
+                                                            int W, const uint64_t *__restrict__ q_xz, double cos_a, double sin_a,
+                                                            double sign, uint4 *__restrict__ out_xz, double2 *__restrict__ out_c,
+                                                            int64_t *__restrict__ n_out) {
+    const int lane = threadIdx.x & 31, g = lane & 7;
+    const int64_t row = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2) + (lane >> 3);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = MODE == 4 ? 2 * M : M;
+    const bool ok = row < M;
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(xz + (ok ? row : 0) * 2 * W);
+    const uint4 *q4 = reinterpret_cast<const uint4 *>(q_xz);
+    const int chunks = W >> 1;   // 16-byte chunks per block (X or Z)
+    const bool mine = g < chunks;
+    uint4 xv = make_uint4(0u, 0u, 0u, 0u), zv = xv, qx = xv, qz = xv;
+    if (mine) {
+        xv = r4[g];
+        zv = r4[chunks + g];
+        qx = q4[g];
+        qz = q4[chunks + g];
+    }
+    const uint64_t xa[2] = {((uint64_t)xv.y << 32) | xv.x, ((uint64_t)xv.w << 32) | xv.z};
+    const uint64_t za[2] = {((uint64_t)zv.y << 32) | zv.x, ((uint64_t)zv.w << 32) | zv.z};
+    const uint64_t xb[2] = {((uint64_t)qx.y << 32) | qx.x, ((uint64_t)qx.w << 32) | qx.z};
+    const uint64_t zb[2] = {((uint64_t)qz.y << 32) | qz.x, ((uint64_t)qz.w << 32) | qz.z};
+    uint64_t comm = 0, s = 0;
+    int ya = 0, yb = 0, yout = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        comm ^= (xa[k] & zb[k]) ^ (za[k] & xb[k]);
+        s ^= xa[k] & zb[k];
+        ya += __popcll(xa[k] & za[k]);
+        yb += __popcll(xb[k] & zb[k]);
+        yout += __popcll((xa[k] ^ xb[k]) & (za[k] ^ zb[k]));
+    }
+    int par = __popcll(comm) & 1, sg = __popcll(s) & 1;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        par ^= __shfl_xor_sync(0xffffffffu, par, o);
+        sg ^= __shfl_xor_sync(0xffffffffu, sg, o);
+        ya += __shfl_xor_sync(0xffffffffu, ya, o);
+        yb += __shfl_xor_sync(0xffffffffu, yb, o);
+        yout += __shfl_xor_sync(0xffffffffu, yout, o);
+    }
+    if (!ok) return;
+    const bool anti = par != 0;
+    const int e = (3 * (ya + yb) + yout + 2 * sg) & 3;
+    const uint4 xq = make_uint4(xv.x ^ qx.x, xv.y ^ qx.y, xv.z ^ qx.z, xv.w ^ qx.w);
+    const uint4 zq = make_uint4(zv.x ^ qz.x, zv.y ^ qz.y, zv.z ^ qz.z, zv.w ^ qz.w);
+    uint4 *o1 = out_xz + (size_t)row * W;
+    if (MODE == 4) {
+        uint4 *o2 = out_xz + (size_t)(M + row) * W;
+        if (mine) {
+            o1[g] = xv;
+            o1[chunks + g] = zv;
+            o2[g] = anti ? xq : xv;
+            o2[chunks + g] = anti ? zq : zv;
+        }
+        if (g == 0) {
+            const double2 cc = c[row];
+            if (anti) {
+                out_c[row] = make_double2(cc.x * cos_a, cc.y * cos_a);
+                double re = cc.x, im = cc.y;
+                mul_i_pow(re, im, e);   // (P*Q coefficient) * (-i sin): i^e, then times -i*sin
+                out_c[M + row] = make_double2(im * sin_a, -re * sin_a);
+            } else {
+                out_c[row] = cc;
+                out_c[M + row] = make_double2(0.0, 0.0);
+            }
+        }
+    } else if (MODE == 1) {
+        if (mine) {
+            o1[g] = anti ? xq : xv;
+            o1[chunks + g] = anti ? zq : zv;
+        }
+        if (g == 0) {
+            const double2 cc = c[row];
+            if (anti) {
+                double re = cc.x, im = cc.y;
+                mul_i_pow(re, im, e + 3);   // times i^e, then times -i = i^3
+                out_c[row] = make_double2(re * sign, im * sign);
+            } else {
+                out_c[row] = cc;
+            }
+        }
+    } else {
+        if (mine) {
+            o1[g] = xv;
+            o1[chunks + g] = zv;
+        }
+        if (g == 0) {
+            const double2 cc = c[row];
+            out_c[row] = anti ? make_double2(cc.x * sign, cc.y * sign) : cc;
+        }
+    }
+}
+
 // sym_rotate_split: stable split of the rows into (commuting with Q | anticommuting with Q), coefficients untouched.
 // The general rotation is then ONE block-list product (sym_mul_blocks_*) of the split operator with the three-row
 // operator [I, cos I, -i sin Q]: commuting rows x [I], anticommuting rows x [cos I, -i sin Q] — the rotated
@@ -259,10 +364,22 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
                           double sin_a, int32_t mode, double sign, uint64_t *out_xz, double *out_c, int64_t *n_out,
                           void *ws, size_t ws_bytes, void *stream) {
     SYM_REQUIRE(M >= 0 && W >= 1, "bad size");
-    SYM_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    SYM_REQUIRE((mode >= 0 && mode <= 2) || mode == 4, "mode must be 0, 1, 2 or 4");
+    SYM_REQUIRE(mode != 4 || group8_ok(W), "the padded general rotation needs an even number of words per block, at most 16");
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 0) {
         SYM_CUDA_OK(cudaMemsetAsync(n_out, 0, sizeof(int64_t), st));
+        return SYM_OK;
+    }
+    if (mode != 0 && group8_ok(W)) {   // one pass: no flags, no scan, no workspace
+        const unsigned nbf = (unsigned)((((M + 3) / 4) * 32 + 255) / 256);
+        const double2 *c2 = reinterpret_cast<const double2 *>(c);
+        uint4 *o4 = reinterpret_cast<uint4 *>(out_xz);
+        double2 *oc2 = reinterpret_cast<double2 *>(out_c);
+        if (mode == 4) rotate_fused8_kernel<4><<<nbf, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, o4, oc2, n_out);
+        else if (mode == 1) rotate_fused8_kernel<1><<<nbf, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, o4, oc2, n_out);
+        else rotate_fused8_kernel<2><<<nbf, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, o4, oc2, n_out);
+        SYM_LAUNCH_OK();
         return SYM_OK;
     }
     if (ws_bytes < sym_rotate_ws_bytes(M)) {

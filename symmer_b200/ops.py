@@ -396,10 +396,23 @@ def join_rows(keys_l, rows_l, keys_r, rows_r):
 
 
 # --------------------------------------------------------------------------------------- rotations
-def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0):
-    """One rotation step (no dedup). mode 0 general (returns M + M_ac rows), 1/2 Clifford."""
+ROTATE_PADDED_MAX_ROWS = 1 << 19
+
+
+def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0, padded_ok=False):
+    """One rotation step (no dedup). mode 0 general (returns M + M_ac rows), 1/2 Clifford. padded_ok: the caller
+    runs a cleanup next, so a general rotation of a config-size operator may return its padded form (2M rows,
+    the second row of a commuting term a zero-coefficient copy: see sym_rotate mode 4) and skip the flag scan
+    and the host round trip for the row count."""
     M, W = _rows(xz)
     dev = xz.device
+    if mode == 0 and padded_ok and 0 < M <= ROTATE_PADDED_MAX_ROWS and W % 2 == 0 and W <= 16:
+        out_xz = torch.empty((2 * M, 2 * W), dtype=torch.int64, device=dev)
+        out_c = torch.empty(2 * M, dtype=torch.complex128, device=dev)
+        n_out = torch.empty(1, dtype=torch.int64, device=dev)
+        _cabi.check(lib().sym_rotate(_p(xz), _p(_coeff(c)), M, W, _p(q_xz), float(cos_a), float(sin_a), 4, float(sign),
+                                     _p(out_xz), _p(out_c), _p(n_out), None, 0, _stream()))
+        return out_xz, out_c
     cap = 2 * M if mode == 0 else M
     out_xz = torch.empty((cap, 2 * W), dtype=torch.int64, device=dev)
     out_c = torch.empty(cap, dtype=torch.complex128, device=dev)

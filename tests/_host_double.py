@@ -157,9 +157,10 @@ def commute_qwc(a_xz, b_xz):
     return torch.from_numpy(po.qubitwise_commutes_termwise(a, b))
 
 
-def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0):
+def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0, padded_ok=False):
     """The contract of sym_rotate (include/symmer_b200.h): no dedup; mode 0 keeps row i in slot i and appends
-    -i sin P Q for the anticommuting rows; modes 1 / 2 are the Clifford relabels."""
+    -i sin P Q for the anticommuting rows; modes 1 / 2 are the Clifford relabels. (padded_ok only allows the
+    device library a different intermediate layout; the compact form is always a valid answer.)"""
     rows, W = _wide(xz)
     q, _ = _wide(q_xz.reshape(1, -1))
     cc = _c(c).copy()

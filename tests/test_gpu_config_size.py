@@ -148,3 +148,38 @@ def test_state_inner_product_join_is_exact(ops):
             dr[r.tobytes()] = dr.get(r.tobytes(), 0) + v
         ref = sum(v * dr[k] for k, v in dl.items() if k in dr)
         assert np.isclose(bra * ket, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_qubits,n_terms", [(1000, 20000), (128, 5000), (100, 3000)])
+def test_padded_general_rotation_cleans_up_to_the_compact_one(n_qubits, n_terms):
+    """sym_rotate mode 4 (one pass, 2M rows, zero-coefficient copies of the commuting rows) followed by the cleanup
+    gives the same rows, in the same order, with the same sums as mode 0 followed by the cleanup."""
+    from symmer_b200 import ops
+    s, c = po.random_operator(n_qubits, n_terms, seed=n_terms)
+    s[n_terms // 2:n_terms // 2 + 50] = s[:50]                      # some duplicates inside the operand
+    q_s, _ = po.random_operator(n_qubits, 1, seed=99)
+    xz = ops.pack(torch.from_numpy(s), n_qubits)
+    cc = torch.from_numpy(c).cuda()
+    q = ops.pack(torch.from_numpy(q_s), n_qubits)
+    ca, sa = np.cos(0.37), np.sin(0.37)
+    r0 = ops.rotate(xz, cc, q, ca, sa, 0)
+    r4 = ops.rotate(xz, cc, q, ca, sa, 0, padded_ok=True)
+    W = xz.shape[1] // 2
+    if W % 2 == 0 and W <= 16:
+        assert r4[0].shape[0] == 2 * n_terms and r0[0].shape[0] < 2 * n_terms
+    else:
+        assert r4[0].shape[0] == r0[0].shape[0]                      # odd word counts keep the compact form
+    a_xz, a_c = ops.cleanup(*r0)
+    b_xz, b_c = ops.cleanup(*r4)
+    assert torch.equal(a_xz, b_xz)
+    assert torch.equal(a_c, b_c)
+    # and both are the reference's rotation followed by its cleanup, as a set of terms
+    o_s, o_c = po.perform_rotations(s, c, [(q_s[0], 0.37)])
+    got_s = po.unpack_bits(b_xz.cpu().numpy().view(np.uint64), n_qubits)
+    got_c = b_c.cpu().numpy()
+    assert got_s.shape == o_s.shape
+    order_o = np.lexsort(o_s.T[::-1])
+    order_g = np.lexsort(got_s.T[::-1])
+    assert np.array_equal(got_s[order_g], o_s[order_o])
+    np.testing.assert_allclose(got_c[order_g], o_c[order_o], rtol=1e-12, atol=1e-15)
