@@ -161,7 +161,7 @@ int sym_commute_qwc(const uint64_t *a_xz, int64_t M, const uint64_t *b_xz, int64
  * mode 4: general angle, padded: exactly 2*M rows out, no flag scan and no count to read back. Row M+i is
  *         the -i*sin*P*Q term of an anticommuting row i and, for a commuting row, a copy of row i with
  *         coefficient 0, which the sym_cleanup that follows merges into row i (same survivors, same order,
- *         same sums as mode 0). Needs W even and <= 16; takes no workspace.
+ *         same sums as mode 0). Takes no workspace.
  * `sign` is +1 or -1 (the reference's `int_part in [2,3]` rule, base.py:1148-1149).
  * n_out: device int64[1]. Fully asynchronous. */
 size_t sym_rotate_ws_bytes(int64_t M);

@@ -920,6 +920,8 @@ def dense_state_pays(n_qubits: int, n_state_terms: int) -> bool:
     side = 1 << n_qubits
     if n_state_terms * 64 < side and side > (1 << 16):
         return False
+    if side <= (1 << 24):   # at most 256 MB: always fits; cudaMemGetInfo costs milliseconds, more than a small expval
+        return True
     try:
         free, _ = torch.cuda.mem_get_info()
     except Exception:       # no device (host-double runs)

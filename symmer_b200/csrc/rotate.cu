@@ -322,6 +322,62 @@ __global__ void __launch_bounds__(256) rotate_fused8_kernel(const uint64_t *__re
     }
 }
 
+// The same one-pass rotation for any word count, one thread per row (operators of <= 64 qubits have W = 1: a row is
+// 16 bytes, and the stabilizer rotations of a tapering are dozens of such calls on a handful of rows each).
+template <int MODE>
+__global__ void __launch_bounds__(256) rotate_fused_row_kernel(const uint64_t *__restrict__ xz, const double2 *__restrict__ c, int64_t M,
+                                                               int W, const uint64_t *__restrict__ q_xz, double cos_a, double sin_a,
+                                                               double sign, uint64_t *__restrict__ out_xz, double2 *__restrict__ out_c,
+                                                               int64_t *__restrict__ n_out) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row == 0) *n_out = MODE == 4 ? 2 * M : M;
+    if (row >= M) return;
+    const uint64_t *r = xz + row * 2 * W;
+    uint64_t comm = 0, s = 0;
+    int ya = 0, yb = 0, yout = 0;
+    for (int w = 0; w < W; ++w) {
+        const uint64_t xa = r[w], za = r[W + w], xb = q_xz[w], zb = q_xz[W + w];
+        comm ^= (xa & zb) ^ (za & xb);
+        s ^= xa & zb;
+        ya += __popcll(xa & za);
+        yb += __popcll(xb & zb);
+        yout += __popcll((xa ^ xb) & (za ^ zb));
+    }
+    const bool anti = (__popcll(comm) & 1) != 0;
+    const int e = (3 * (ya + yb) + yout + 2 * (__popcll(s) & 1)) & 3;
+    uint64_t *o1 = out_xz + row * 2 * W;
+    const double2 cc = c[row];
+    if (MODE == 4) {
+        uint64_t *o2 = out_xz + (M + row) * 2 * W;
+        for (int w = 0; w < 2 * W; ++w) {
+            const uint64_t v = r[w];
+            o1[w] = v;
+            o2[w] = anti ? v ^ q_xz[w] : v;
+        }
+        if (anti) {
+            out_c[row] = make_double2(cc.x * cos_a, cc.y * cos_a);
+            double re = cc.x, im = cc.y;
+            mul_i_pow(re, im, e);
+            out_c[M + row] = make_double2(im * sin_a, -re * sin_a);
+        } else {
+            out_c[row] = cc;
+            out_c[M + row] = make_double2(0.0, 0.0);
+        }
+    } else if (MODE == 1) {
+        for (int w = 0; w < 2 * W; ++w) o1[w] = anti ? r[w] ^ q_xz[w] : r[w];
+        if (anti) {
+            double re = cc.x, im = cc.y;
+            mul_i_pow(re, im, e + 3);
+            out_c[row] = make_double2(re * sign, im * sign);
+        } else {
+            out_c[row] = cc;
+        }
+    } else {
+        for (int w = 0; w < 2 * W; ++w) o1[w] = r[w];
+        out_c[row] = anti ? make_double2(cc.x * sign, cc.y * sign) : cc;
+    }
+}
+
 // sym_rotate_split: stable split of the rows into (commuting with Q | anticommuting with Q), coefficients untouched.
 // The general rotation is then ONE block-list product (sym_mul_blocks_*) of the split operator with the three-row
 // operator [I, cos I, -i sin Q]: commuting rows x [I], anticommuting rows x [cos I, -i sin Q] — the rotated
@@ -365,7 +421,6 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
                           void *ws, size_t ws_bytes, void *stream) {
     SYM_REQUIRE(M >= 0 && W >= 1, "bad size");
     SYM_REQUIRE((mode >= 0 && mode <= 2) || mode == 4, "mode must be 0, 1, 2 or 4");
-    SYM_REQUIRE(mode != 4 || group8_ok(W), "the padded general rotation needs an even number of words per block, at most 16");
     cudaStream_t st = (cudaStream_t)stream;
     if (M == 0) {
         SYM_CUDA_OK(cudaMemsetAsync(n_out, 0, sizeof(int64_t), st));
@@ -379,6 +434,16 @@ extern "C" int sym_rotate(const uint64_t *xz, const double *c, int64_t M, int32_
         if (mode == 4) rotate_fused8_kernel<4><<<nbf, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, o4, oc2, n_out);
         else if (mode == 1) rotate_fused8_kernel<1><<<nbf, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, o4, oc2, n_out);
         else rotate_fused8_kernel<2><<<nbf, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, o4, oc2, n_out);
+        SYM_LAUNCH_OK();
+        return SYM_OK;
+    }
+    if (mode != 0 && (W <= 2 || mode == 4)) {   // narrow rows (or any width for the padded form): one thread per row
+        const unsigned nbr = (unsigned)((M + 255) / 256);
+        const double2 *c2 = reinterpret_cast<const double2 *>(c);
+        double2 *oc2 = reinterpret_cast<double2 *>(out_c);
+        if (mode == 4) rotate_fused_row_kernel<4><<<nbr, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, out_xz, oc2, n_out);
+        else if (mode == 1) rotate_fused_row_kernel<1><<<nbr, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, out_xz, oc2, n_out);
+        else rotate_fused_row_kernel<2><<<nbr, 256, 0, st>>>(xz, c2, M, W, q_xz, cos_a, sin_a, sign, out_xz, oc2, n_out);
         SYM_LAUNCH_OK();
         return SYM_OK;
     }

@@ -66,7 +66,14 @@ def device():
     return dev
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    # the raw handle of torch's current stream; the private accessor skips building a Stream object (this runs once
+    # per library call, and a tapering makes hundreds of microsecond-sized calls)
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -406,7 +413,7 @@ def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0, padded_ok=False):
     and the host round trip for the row count."""
     M, W = _rows(xz)
     dev = xz.device
-    if mode == 0 and padded_ok and 0 < M <= ROTATE_PADDED_MAX_ROWS and W % 2 == 0 and W <= 16:
+    if mode == 0 and padded_ok and 0 < M <= ROTATE_PADDED_MAX_ROWS and ((W % 2 == 0 and W <= 16) or W == 1):
         out_xz = torch.empty((2 * M, 2 * W), dtype=torch.int64, device=dev)
         out_c = torch.empty(2 * M, dtype=torch.complex128, device=dev)
         n_out = torch.empty(1, dtype=torch.int64, device=dev)
@@ -416,7 +423,7 @@ def rotate(xz, c, q_xz, cos_a, sin_a, mode, sign=1.0, padded_ok=False):
     cap = 2 * M if mode == 0 else M
     out_xz = torch.empty((cap, 2 * W), dtype=torch.int64, device=dev)
     out_c = torch.empty(cap, dtype=torch.complex128, device=dev)
-    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    n_out = torch.empty(1, dtype=torch.int64, device=dev)      # always written by the library
     L = lib()
     ws = workspace(L.sym_rotate_ws_bytes(M))
     _cabi.check(L.sym_rotate(_p(xz), _p(_coeff(c)), M, W, _p(q_xz), float(cos_a), float(sin_a), int(mode), float(sign),
