@@ -51,7 +51,7 @@ def main():
             continue
         a, ac = ops.pack(torch.from_numpy(xs), N_QUBITS), torch.from_numpy(xc).to(dev)
         b, bc = ops.pack(torch.from_numpy(ys), N_QUBITS), torch.from_numpy(yc).to(dev)
-        for label, knobs in (("sort", {10: 0}), ("class1024", {10: 1, 11: 1}), ("class32", {10: 1, 11: 2})):
+        for label, knobs in (("sort", {10: 0}), ("class1024", {10: 1, 11: 1}), ("class32-table", {10: 1, 11: 3}), ("class32-prefilter", {10: 1, 11: 2})):
             if os.environ.get("PROBE_ONLY") and os.environ["PROBE_ONLY"] not in label:
                 continue
             for k, v in knobs.items():

@@ -19,6 +19,12 @@ if os.environ.get("ROT"):
     C = PauliwordOp(s3, c3); C._coeff_dev()
     q = PauliwordOp(po.random_operator(1000, 1, seed=4)[0], [1.0])
     fn = lambda: C._rotate_by_single_Pword(q, 0.3)
+if os.environ.get("C2"):
+    from symmer_b200 import IndependentOp
+    d = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "hamiltonians", "H2O_STO3G.npz"))
+    n = int(d["n_qubits"][0])
+    H = PauliwordOp(np.unpackbits(d["symp"], axis=1)[:, :2 * n].astype(bool), d["coeff"]); H._coeff_dev()
+    fn = lambda: IndependentOp.symmetry_generators(H)
 for _ in range(30): fn()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

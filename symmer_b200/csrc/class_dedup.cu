@@ -529,17 +529,25 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
 // into the global candidate array by the counting sort (small groups ordered by their owner thread afterwards); a
 // class with a large hash group, or with records that never found a slot, sends its candidates to the overflow array.
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int CAP, int LOG_SLOTS>
+// PRE_LOG > 0: a presence filter in front of the table rounds. Two bitmaps of 2^PRE_LOG bits, indexed by a function of
+// the hash alone: every record sets its bit in the first map and, if it was already set, in the second. After a
+// barrier a record whose bit is clear in the SECOND map shares its hash with nobody in the class: it is unique, and
+// it never enters the rounds (one shared-memory atomic and one load instead of a store, a load and a compare per
+// round). On a product without duplicates ~95 % of the records stop here, and the table can be half the size.
+template <int THREADS, int CAP, int LOG_SLOTS, int PRE_LOG>
 __global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, ProductRows rows, TileMap tm, double thr,
                                                                     uint64_t *__restrict__ cand, uint64_t *__restrict__ over,
                                                                     uint32_t *__restrict__ counters, int vbits) {
     constexpr int SLOTS = 1 << LOG_SLOTS;
     constexpr int RPT = CAP / THREADS;
+    constexpr int PRE_WORDS = PRE_LOG > 0 ? (1 << PRE_LOG) / 32 : 0;
     static_assert(CAP % THREADS == 0 && CAP <= 65536 && RPT <= 32, "record ids are 16 bits, one state bit per record");
-    static_assert(CAP <= SLOTS, "the group counters live in the table after the rounds");
+    static_assert(CAP <= SLOTS + 2 * PRE_WORDS, "the group counters live in the table (and the maps behind it) after the rounds");
     extern __shared__ __align__(16) unsigned char cd_smem[];
     uint32_t *table = reinterpret_cast<uint32_t *>(cd_smem);
-    uint32_t *pairs = table + SLOTS;
+    uint32_t *map1 = table + SLOTS;                     // contiguous with the table: the group counters may run into them
+    uint32_t *map2 = map1 + PRE_WORDS;
+    uint32_t *pairs = map2 + PRE_WORDS;
     uint32_t *mate = pairs + CAP;                       // one bit per record: a same-hash record saw it holding a slot
     uint32_t *s_bits = mate + CAP / 32;
     __shared__ uint32_t s_count, s_ncand, s_base;
@@ -559,6 +567,7 @@ __global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, P
             s_ncand = 0;
         }
         for (int i = tid; i < CAP / 32; i += THREADS) mate[i] = 0u;
+        for (int i = tid; i < 2 * PRE_WORDS; i += THREADS) map1[i] = 0u;
         __syncthreads();
         cd_enumerate<THREADS, CAP, false, uint32_t>(J, c, s_bits, bm_shared, &s_count, s_warp, pairs, nullptr, 0u, vbits);
         __syncthreads();
@@ -588,6 +597,24 @@ __global__ void __launch_bounds__(THREADS, 1) class_dedup32_kernel(ClassJob J, P
                 const uint32_t pr = pairs[i];
                 h32[j] = (uint32_t)((mix64(__ldg(J.look8 + (pr >> vbits)) ^ __ldg(J.vsk + (pr & vmask))) & J.key_mask) >> 32);
                 unres |= 1u << j;
+            }
+        }
+        if constexpr (PRE_LOG > 0) {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                if ((unres >> j) & 1u) {
+                    const uint32_t b = (h32[j] * 0x85EBCA6Bu) >> (32 - PRE_LOG);
+                    const uint32_t bit = 1u << (b & 31u);
+                    if (atomicOr(map1 + (b >> 5), bit) & bit) atomicOr(map2 + (b >> 5), bit);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                if ((unres >> j) & 1u) {
+                    const uint32_t b = (h32[j] * 0x85EBCA6Bu) >> (32 - PRE_LOG);
+                    if (!((map2[b >> 5] >> (b & 31u)) & 1u)) unres &= ~(1u << j);   // nobody shares this hash: unique
+                }
             }
         }
         for (int round = 0; round < CD_MAX_ROUNDS; ++round) {
@@ -753,7 +780,7 @@ static int cd_bits_for(uint32_t n) {   // bits that hold every index below n
     while (b < 32 && (1ull << b) < n) ++b;
     return b;
 }
-static int class_cap(int variant) { return variant == 2 ? 18432 : (variant == 1 ? 9216 : 4096); }
+static int class_cap(int variant) { return (variant == 2 || variant == 3) ? 18432 : (variant == 1 ? 9216 : 4096); }
 
 bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t T, int tb, uint64_t key_mask, ClassJob &J,
                     bool ignore_knob) {   // ignore_knob: workspace sizing — the shape with the larger tables
@@ -783,7 +810,7 @@ bool class_job_plan(int64_t M_total, const TileBlock *blocks, int nblk, int64_t 
     // classes: the average class fills at most 85 % of a CTA's pair list; small products still get enough classes
     // to occupy the GPU
     J.variant = ignore_knob ? 0 : g_class_variant;
-    if (J.variant == 2 && cd_bits_for((uint32_t)entries) + cd_bits_for((uint32_t)cd_padded_visits((uint32_t)visits)) > 32) J.variant = 1;
+    if ((J.variant == 2 || J.variant == 3) && cd_bits_for((uint32_t)entries) + cd_bits_for((uint32_t)cd_padded_visits((uint32_t)visits)) > 32) J.variant = 1;
     int64_t target = (int64_t)(0.85 * class_cap(J.variant));
     if (T / 1024 < target) target = T / 1024 > 256 ? T / 1024 : 256;
     int k = 0;
@@ -897,19 +924,22 @@ int class_dedup_run(ClassJob &J, const uint64_t *a_sk, const uint64_t *b_sk, con
     cd_place_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(J, a_sk, off, cursor, (uint32_t)tab, look8, lookp, vkey, vq, vsk, bits,
                                                      (uint32_t)nvp, n_rows_a);
     SYM_LAUNCH_OK();
-    if (J.variant == 2) {
-        constexpr int CAP = 18432, LOG_SLOTS = 15;
-        constexpr size_t smem = ((size_t)1 << LOG_SLOTS) * 4 + (size_t)CAP * 4 + CAP / 8 + (size_t)CD32_BM_WORDS * 4;
-        auto kern = class_dedup32_kernel<1024, CAP, LOG_SLOTS>;
+    if (J.variant == 2 || J.variant == 3) {
+        constexpr int CAP = 18432;
+        constexpr size_t smem = ((size_t)1 << 15) * 4 + (size_t)CAP * 4 + CAP / 8 + (size_t)CD32_BM_WORDS * 4;   // both shapes
+        auto kern_pre = class_dedup32_kernel<1024, CAP, 14, 18>;   // 64 KB table + 2 x 32 KB presence maps
+        auto kern_old = class_dedup32_kernel<1024, CAP, 15, 0>;    // 128 KB table (tuning knob 11 = 3)
         static bool attr_done[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
         if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-            SYM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SYM_CUDA_OK(cudaFuncSetAttribute(kern_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SYM_CUDA_OK(cudaFuncSetAttribute(kern_old, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_done[dev] = true;
         }
         const unsigned grid = (unsigned)std::min<uint32_t>(1u << J.k, (uint32_t)num_sms());
-        kern<<<grid, 1024, smem, st>>>(J, rows, tm, thr, cand, over, counters, cd_bits_for((uint32_t)nvp));
+        if (J.variant == 2) kern_pre<<<grid, 1024, smem, st>>>(J, rows, tm, thr, cand, over, counters, cd_bits_for((uint32_t)nvp));
+        else kern_old<<<grid, 1024, smem, st>>>(J, rows, tm, thr, cand, over, counters, cd_bits_for((uint32_t)nvp));
         SYM_LAUNCH_OK();
     } else if (class_cap(J.variant) == 9216) {
         SYM_TRY((cd_launch<1024, 9216, 14, 1>(J, rows, tm, thr, cand, over, counters, st)));

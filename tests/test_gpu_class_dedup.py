@@ -45,7 +45,7 @@ def check_both_paths(ops, a_s, a_c, b_s, b_c, thr=1e-15, scale_mult=1.0, order=T
     try:
         ops.set_tuning(0, 0)                      # force the large-product (ordered-tile) path
         # (knob 10, knob 11): class mode with the compact kernel (default), with the 8-byte-entry kernel, and the record sort
-        for knob in ((1, 2), (1, 1), (0, 2)):
+        for knob in ((1, 2), (1, 3), (1, 1), (0, 2)):
             ops.set_tuning(10, knob[0])
             ops.set_tuning(11, knob[1])
             xz, c = ops.mul_cleanup(*dev_op(ops, a_s, a_c), *dev_op(ops, b_s, b_c), thr)
@@ -60,7 +60,7 @@ def check_both_paths(ops, a_s, a_c, b_s, b_c, thr=1e-15, scale_mult=1.0, order=T
         ops.set_tuning(11, 2)
         ops.set_tuning(0, 1 << 22)
     base = out[(0, 2)]
-    for knob in ((1, 2), (1, 1)):
+    for knob in ((1, 2), (1, 3), (1, 1)):
         if len(base[1]) == len(out[knob][1]):
             assert np.array_equal(base[0], out[knob][0]), knob
             assert np.allclose(base[1], out[knob][1], rtol=1e-12, atol=1e-12 * scale), knob
