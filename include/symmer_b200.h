@@ -361,7 +361,11 @@ int sym_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t T, int32_t begin_bit,
  * order (0); 7: B rows per CTA of the tiled row emission (default 16); 8: record sort as one-sweep
  * passes with decoupled look-back (1, default) or histogram + scan + scatter per pass (0); 9: in
  * ordered-tile mode the first radix pass generates the records itself (1) or pair_keys_kernel writes them
- * first (0, default: measured faster). */
+ * first (0, default: measured faster); 10: duplicate detection of ordered-tile products by class-local
+ * enumeration (1, default) or by the global record sort (0); 11: class kernel shape (2, default: compact
+ * 4-byte entries with the presence filter; 3: the same without the filter, 128 KB table; 1: 8-byte entries,
+ * 9216 records per class; 0: 512-thread CTAs, 4096 records); 12: tensor-core commute kernel (2, default:
+ * warp-specialised, 2 stages, 2 CTAs/SM; 1, 3, 4: other stage / expander-warp counts; 0: the round-1 kernel). */
 int sym_set_tuning(int32_t which, int64_t value);
 /* Measurement hook: two cudaEvent_t (as void*, NULL to disable) recorded on the stream immediately
  * before and after the row-emission kernel (emit_kernel) of the next *_emit calls, so that a

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(THREADS, MINB) class_dedup_kernel(ClassJob J, 
 
 // ------------------------------------------------------------------------------------------------
 // Compact form of the class kernel (tuning knob 11 = 2, the default when the table indices fit 32 bits): 4-byte pair
-// entries ((entry of A << vbits) | visit) and 4-byte table entries [hash : 16 | local id : 16] (with the slot, 31 hash
+// entries ((entry of A << vbits) | visit) and 4-byte table entries [hash : 16 | local id : 16] (with the slot, 30-31 hash
 // bits decide "same hash": ~0.03 false candidate pairs per class), so one CTA holds 18 432 records instead of 9 216 and
 // the product needs HALF the classes: half the visits, half the per-class barriers. Candidates are placed straight
 // into the global candidate array by the counting sort (small groups ordered by their owner thread afterwards); a
@@ -841,7 +841,8 @@ size_t class_job_ws_bytes(const ClassJob &J) {
 }
 
 int g_class_variant = 2;    // tuning knob 11: class kernel (0: 512 threads x 2 CTAs/SM, 4096 records; 1: 1024 threads, 9216 records;
-                            // 2 (default): compact 4-byte entries, 1024 threads, 18432 records per class)
+                            // 2 (default): compact 4-byte entries, 1024 threads, 18432 records per class, presence filter;
+                            // 3: the same without the filter and with a 32768-slot table)
 
 template <int THREADS, int CAP, int LOG_SLOTS, int MINB>
 static int cd_launch(const ClassJob &J, const ProductRows &rows, const TileMap &tm, double thr, uint64_t *cand, uint64_t *over,
